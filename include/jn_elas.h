@@ -1,0 +1,170 @@
+/*
+ * jn_elas.h -- C ABI of the B200-native stereo-to-obstacle hot path.
+ *
+ * This is the drop-in boundary.  Every entry point
+ * replaces one interface of the reference (paths relative to the reference
+ * tree, sourishg/jackal-navigation):
+ *
+ *   jn_elas_params           <- Elas::parameters            src/elas/elas.h:59-145
+ *   jn_elas_params_default   <- parameters(setting s)       src/elas/elas.h:87-144
+ *   jn_elas_create/destroy   <- Elas(parameters) / ~Elas    src/elas/elas.h:148-151
+ *   jn_elas_process          <- Elas::process               src/elas/elas.h:162, elas.cpp:32-151
+ *   jn_elas_process_batch    <- the per-frame call site     src/obstacle_avoidance/point_cloud.cpp:416-419
+ *                               (one call per left frame), batched over independent frames
+ *   jn_calib_load_yaml       <- cv::FileStorage reads       point_cloud.cpp:530-538
+ *   jn_calib_set_q           <- stereoRectify -> Q          point_cloud.cpp:543-544
+ *   jn_scan_cache_gate       <- cacheDisparityValues        point_cloud.cpp:104-147
+ *   jn_scan_from_disparity   <- generateDisparityMap's convertTo(CV_8U) (point_cloud.cpp:421-422)
+ *                               + publishObstacleScan(Mat&) (point_cloud.cpp:213-296)
+ *   jn_points_from_disparity <- publishPointCloud (-g path) point_cloud.cpp:298-404
+ *   jn_scan_from_points      <- publishObstacleScan(vector<Point3d>) point_cloud.cpp:149-211
+ *
+ * Plain pointers and sizes only.  All compute runs in hand-written CUDA
+ * kernels for sm_100a; there is no CPU fallback: every compute entry point
+ * returns JN_ERR_CUDA if no device is usable.
+ */
+#ifndef JN_ELAS_H
+#define JN_ELAS_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Same 23 fields, same order and meaning as Elas::parameters (elas.h:60-84);
+ * the reference's `bool` members are int32 here (0/1). */
+typedef struct jn_elas_params {
+  int32_t disp_min;
+  int32_t disp_max;
+  float   support_threshold;
+  int32_t support_texture;
+  int32_t candidate_stepsize;
+  int32_t incon_window_size;
+  int32_t incon_threshold;
+  int32_t incon_min_support;
+  int32_t add_corners;
+  int32_t grid_size;
+  float   beta;
+  float   gamma;
+  float   sigma;
+  float   sradius;
+  int32_t match_texture;
+  int32_t lr_threshold;
+  float   speckle_sim_threshold;
+  int32_t speckle_size;
+  int32_t ipol_gap_width;
+  int32_t filter_median;
+  int32_t filter_adaptive_mean;
+  int32_t postprocess_only_left;
+  int32_t subsampling;
+} jn_elas_params;
+
+enum { JN_ROBOTICS = 0, JN_MIDDLEBURY = 1 };   /* Elas::setting, elas.h:56 */
+
+/* Return codes.  The reference's process() is void; it reports "<3 support
+ * points" by printing and returning with D1/D2 untouched (elas.cpp:66-71).
+ * JN_FEW_SUPPORT is that case (outputs untouched, same message printed by the
+ * C++ shim). */
+enum {
+  JN_OK            = 0,
+  JN_FEW_SUPPORT   = 1,
+  JN_ERR_ARG       = -1,
+  JN_ERR_CUDA      = -2,
+  JN_ERR_UNSUPPORTED = -3,  /* parameter combination not built yet (subsampling=1) */
+  JN_ERR_IO        = -4
+};
+
+typedef struct jn_elas jn_elas;
+
+void jn_elas_params_default(jn_elas_params* p, int setting);
+
+/* device: CUDA ordinal.  max_batch: frames processed per launch wave
+ * (workspace is sized for it lazily at the first process call). */
+jn_elas* jn_elas_create(const jn_elas_params* p, int device);
+void     jn_elas_destroy(jn_elas* e);
+const char* jn_last_error(void);
+
+/* Host pointers, synchronous.  dims = {width, height, bytes_per_line}.
+ * D1, D2: caller-allocated width*height floats.  Returns JN_OK,
+ * JN_FEW_SUPPORT (outputs untouched) or an error. */
+int jn_elas_process(jn_elas* e, const uint8_t* I1, const uint8_t* I2,
+                    float* D1, float* D2, const int32_t dims[3]);
+
+/* Batched, device-resident.  I1/I2: n frames, frame-major, device pointers,
+ * each frame height rows of bytes_per_line bytes.  D1/D2: device pointers,
+ * n*width*height floats (D2 may be NULL: right map not returned).
+ * status: device pointer to n int32 (JN_OK / JN_FEW_SUPPORT per frame), may be
+ * NULL.  Work is enqueued on `stream` (a cudaStream_t passed as void*); the
+ * call does not synchronise.  A frame with <3 support points leaves its
+ * D1/D2 slice untouched. */
+int jn_elas_process_batch(jn_elas* e, int n, const uint8_t* I1, const uint8_t* I2,
+                          float* D1, float* D2, int32_t* status,
+                          const int32_t dims[3], void* stream);
+
+/* ------------------------------------------------------------------ */
+/* Calibration + obstacle scan (point_cloud.cpp)                       */
+
+typedef struct jn_calib {
+  double K1[9], K2[9];
+  double D1[5], D2[5];
+  double R[9];
+  double T[3];
+  double XR[9];
+  double XT[3];
+  double Q[16];       /* disparity-to-depth matrix; set by jn_calib_set_q */
+  int32_t has_q;
+} jn_calib;
+
+/* Reads the OpenCV-YAML calibration file (keys K1,K2,D1,D2,R,T,XR,XT; T is a
+ * bare 3-sequence, the rest !!opencv-matrix with dt: d). */
+int jn_calib_load_yaml(const char* path, jn_calib* c);
+/* Q = [[1,0,0,-cx],[0,1,0,-cy],[0,0,0,f],[0,0,-1/Tx,0]] (CALIB_ZERO_DISPARITY). */
+void jn_calib_set_q(jn_calib* c, double cx, double cy, double f, double tx);
+
+#define JN_SCAN_BINS 90
+
+typedef struct jn_scan_meta {
+  double angle_min, angle_max;   /* radians; 400 / -400 if no point */
+  double range_min, range_max;   /* 1e9 / -500 if no point */
+  int32_t n_finite;              /* number of finite bins */
+  int32_t n_points;              /* pixels that passed the gate */
+} jn_scan_meta;
+
+typedef struct jn_scan jn_scan;
+
+/* Builds the per-pixel ground-plane gate cache on the device
+ * (cacheDisparityValues, point_cloud.cpp:104-147). */
+jn_scan* jn_scan_create(const jn_calib* c, int width, int height,
+                        int crop_offset_x, int crop_offset_y, int device);
+void     jn_scan_destroy(jn_scan* s);
+/* Copies the W*H*2 gate cache (Vec2b {dmin,255}) to the host. */
+int jn_scan_gate_cache(jn_scan* s, uint8_t* gate_out);
+
+/* Device-resident batched: D float n*W*H (output of jn_elas_process_batch),
+ * ranges: device n*90 doubles (1e9 = empty bin), meta: device n jn_scan_meta.
+ * dmap_u8: optional device n*W*H u8 output of the convertTo(CV_8U) step. */
+int jn_scan_from_disparity_batch(jn_scan* s, int n, const float* D,
+                                 double* ranges, jn_scan_meta* meta,
+                                 uint8_t* dmap_u8, void* stream);
+/* Host-pointer, synchronous single frame. */
+int jn_scan_from_disparity(jn_scan* s, const float* D, double ranges[JN_SCAN_BINS],
+                           jn_scan_meta* meta, uint8_t* dmap_u8);
+
+/* -g path: every pixel with u8 disparity >= 2 -> robot-frame XYZ (double,
+ * 3 per point, pixel order columns-outer like the reference) and the scan
+ * from those points with the ground gate applied per point.
+ * points: host W*H*3 doubles capacity; n_points out. */
+int jn_points_from_disparity(jn_scan* s, const float* D, double* points,
+                             int32_t* n_points, double ranges[JN_SCAN_BINS],
+                             jn_scan_meta* meta);
+
+/* Compacted LaserScan.ranges as the reference publishes them: finite bins,
+ * k = 89..0 (point_cloud.cpp:278-282).  Returns the count. */
+int jn_scan_compact(const double ranges[JN_SCAN_BINS], float* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JN_ELAS_H */
