@@ -3,7 +3,7 @@
  *
  * Shared C interface of the two CPU checkers:
  *   oracle/_ref/libelas_ref.so   the UNMODIFIED reference sources
- *                                (/root/reference/src/elas/*.cpp) compiled in
+ *                                (/root/reference/src/elas, five .cpp files) compiled in
  *                                place by oracle/Makefile, plus ref_shim.cpp
  *   oracle/libelas_port.so       the plain-C restatement (elas_port.c,
  *                                delaunay_port.c, scan_port.c)
