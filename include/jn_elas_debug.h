@@ -1,0 +1,62 @@
+/*
+ * jn_elas_debug.h -- stage-dump entry point of the CUDA path (used by the
+ * parity tests and profiling only; not part of the reference-facing API).
+ *
+ * jn_elas_stages runs the same device pipeline as jn_elas_process on one frame
+ * and copies every intermediate back to the host so each kernel can be
+ * compared with the oracle's dump of the matching reference stage
+ * (elas.cpp:57-140).
+ */
+#ifndef JN_ELAS_DEBUG_H
+#define JN_ELAS_DEBUG_H
+#include "jn_elas.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Every pointer may be NULL.  Sizes as in the reference: W,H image; Wc,Hc
+ * candidate lattice (elas.cpp:386-387); gw,gh grid (elas.cpp:90-91). */
+typedef struct jn_stage_dump {
+  uint8_t* desc1;        /* H*W*16 */
+  uint8_t* desc2;
+  int16_t* dcan_raw;     /* Hc*Wc */
+  int16_t* dcan_incon;
+  int16_t* dcan_final;
+  int32_t* support;      /* (u,v,d) triples */
+  int32_t  cap_support;
+  int32_t  n_support;    /* out */
+  int32_t* tri1;         /* (c1,c2,c3) */
+  float*   planes1;      /* 6 floats per triangle */
+  int32_t* tri2;
+  float*   planes2;
+  int32_t  cap_tri;
+  int32_t  n_tri1;       /* out */
+  int32_t  n_tri2;       /* out */
+  int32_t* grid1;        /* gh*gw*(disp_max+2), reference list format */
+  int32_t* grid2;
+  float*   D1_raw;
+  float*   D2_raw;
+  float*   D1_lr;
+  float*   D2_lr;
+  float*   D1_seg;
+  float*   D2_seg;
+  float*   D1_gap;
+  float*   D2_gap;
+  float*   D1_mean;
+  float*   D2_mean;
+  float*   D1;
+  float*   D2;
+  int64_t  dense_evals;  /* unused by the CUDA path */
+  int64_t  dense_pixels;
+} jn_stage_dump;
+
+int jn_elas_stages(jn_elas* e, const uint8_t* I1, const uint8_t* I2, const int32_t dims[3],
+                   jn_stage_dump* out);
+
+/* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
+long long jn_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,305 @@
+"""jackal-navigation_b200 -- B200-native stereo-to-obstacle hot path.
+
+Host-side mirror of the reference interface for this path:
+
+    Elas.parameters / Elas(param).process(I1, I2, D1, D2, dims)   src/elas/elas.h:59-162
+    calibration YAML (K1,K2,D1,D2,R,T,XR,XT) + Q                  point_cloud.cpp:530-544
+    generateDisparityMap / publishObstacleScan                    point_cloud.cpp:406-429, 213-296
+
+All compute happens in libjn_elas.so (hand-written CUDA for sm_100a) behind the C ABI
+declared in include/jn_elas.h; this module only marshals pointers with ctypes.  There is
+no CPU fallback: if the library is missing or no CUDA device is usable, calls raise.
+PyTorch is used by callers for device memory and streams only.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libjn_elas.so")
+
+ROBOTICS, MIDDLEBURY = 0, 1
+JN_OK, JN_FEW_SUPPORT = 0, 1
+SCAN_BINS = 90
+SCAN_INF = 1e9
+
+
+class JnError(RuntimeError):
+    pass
+
+
+class parameters(C.Structure):
+    """Elas::parameters (elas.h:59-145): same 23 fields, same order."""
+    _fields_ = [
+        ("disp_min", C.c_int32), ("disp_max", C.c_int32),
+        ("support_threshold", C.c_float), ("support_texture", C.c_int32),
+        ("candidate_stepsize", C.c_int32), ("incon_window_size", C.c_int32),
+        ("incon_threshold", C.c_int32), ("incon_min_support", C.c_int32),
+        ("add_corners", C.c_int32), ("grid_size", C.c_int32),
+        ("beta", C.c_float), ("gamma", C.c_float), ("sigma", C.c_float),
+        ("sradius", C.c_float), ("match_texture", C.c_int32),
+        ("lr_threshold", C.c_int32), ("speckle_sim_threshold", C.c_float),
+        ("speckle_size", C.c_int32), ("ipol_gap_width", C.c_int32),
+        ("filter_median", C.c_int32), ("filter_adaptive_mean", C.c_int32),
+        ("postprocess_only_left", C.c_int32), ("subsampling", C.c_int32),
+    ]
+
+    def __init__(self, setting=ROBOTICS, **overrides):
+        super().__init__()
+        lib().jn_elas_params_default(C.byref(self), int(setting))
+        for k, v in overrides.items():
+            if not hasattr(self, k):
+                raise AttributeError(k)
+            setattr(self, k, v)
+
+
+class Calib(C.Structure):
+    _fields_ = [("K1", C.c_double * 9), ("K2", C.c_double * 9), ("D1", C.c_double * 5), ("D2", C.c_double * 5),
+                ("R", C.c_double * 9), ("T", C.c_double * 3), ("XR", C.c_double * 9), ("XT", C.c_double * 3),
+                ("Q", C.c_double * 16), ("has_q", C.c_int32)]
+
+
+class ScanMeta(C.Structure):
+    _fields_ = [("angle_min", C.c_double), ("angle_max", C.c_double), ("range_min", C.c_double),
+                ("range_max", C.c_double), ("n_finite", C.c_int32), ("n_points", C.c_int32)]
+
+
+_P = C.c_void_p
+
+
+class StageDump(C.Structure):
+    """include/jn_elas_debug.h: jn_stage_dump."""
+    _fields_ = [
+        ("desc1", _P), ("desc2", _P),
+        ("dcan_raw", _P), ("dcan_incon", _P), ("dcan_final", _P),
+        ("support", _P), ("cap_support", C.c_int32), ("n_support", C.c_int32),
+        ("tri1", _P), ("planes1", _P), ("tri2", _P), ("planes2", _P),
+        ("cap_tri", C.c_int32), ("n_tri1", C.c_int32), ("n_tri2", C.c_int32),
+        ("grid1", _P), ("grid2", _P),
+        ("D1_raw", _P), ("D2_raw", _P), ("D1_lr", _P), ("D2_lr", _P),
+        ("D1_seg", _P), ("D2_seg", _P), ("D1_gap", _P), ("D2_gap", _P),
+        ("D1_mean", _P), ("D2_mean", _P), ("D1", _P), ("D2", _P),
+        ("dense_evals", C.c_int64), ("dense_pixels", C.c_int64),
+    ]
+
+
+_lib = None
+
+
+def lib():
+    """Loads libjn_elas.so.  Fails loudly: there is no fallback implementation."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise JnError("%s not built: run `python jackal-navigation_b200/build.py` "
+                          "(there is no CPU fallback)" % LIB_PATH)
+        l = C.CDLL(LIB_PATH)
+        l.jn_last_error.restype = C.c_char_p
+        l.jn_launch_count.restype = C.c_longlong
+        l.jn_elas_create.restype = _P
+        l.jn_elas_create.argtypes = [C.POINTER(parameters), C.c_int]
+        l.jn_elas_destroy.argtypes = [_P]
+        l.jn_elas_process.argtypes = [_P, _P, _P, _P, _P, C.POINTER(C.c_int32)]
+        l.jn_elas_process_batch.argtypes = [_P, C.c_int, _P, _P, _P, _P, _P, C.POINTER(C.c_int32), _P]
+        l.jn_elas_stages.argtypes = [_P, _P, _P, C.POINTER(C.c_int32), C.POINTER(StageDump)]
+        l.jn_calib_load_yaml.argtypes = [C.c_char_p, C.POINTER(Calib)]
+        l.jn_calib_set_q.argtypes = [C.POINTER(Calib), C.c_double, C.c_double, C.c_double, C.c_double]
+        l.jn_scan_create.restype = _P
+        l.jn_scan_create.argtypes = [C.POINTER(Calib), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        l.jn_scan_destroy.argtypes = [_P]
+        l.jn_scan_gate_cache.argtypes = [_P, _P]
+        l.jn_scan_from_disparity_batch.argtypes = [_P, C.c_int, _P, _P, _P, _P, _P]
+        l.jn_scan_from_disparity.argtypes = [_P, _P, _P, C.POINTER(ScanMeta), _P]
+        l.jn_points_from_disparity.argtypes = [_P, _P, _P, C.POINTER(C.c_int32), _P, C.POINTER(ScanMeta)]
+        l.jn_scan_compact.argtypes = [_P, _P]
+        _lib = l
+    return _lib
+
+
+def last_error():
+    return lib().jn_last_error().decode()
+
+
+def launch_count():
+    return int(lib().jn_launch_count())
+
+
+def _check(rc, what):
+    if rc < 0:
+        raise JnError("%s failed (%d): %s" % (what, rc, last_error()))
+    return rc
+
+
+def _ptr(a):
+    return a.ctypes.data_as(_P) if a is not None else None
+
+
+class Elas:
+    """Mirror of class Elas (elas.h:52-234)."""
+    ROBOTICS, MIDDLEBURY = ROBOTICS, MIDDLEBURY
+    parameters = parameters
+
+    def __init__(self, param=None, device=0):
+        self.param = param if param is not None else parameters()
+        self._h = lib().jn_elas_create(C.byref(self.param), int(device))
+        if not self._h:
+            raise JnError("jn_elas_create: " + last_error())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().jn_elas_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def process(self, I1, I2, D1, D2, dims):
+        """Elas::process(I1, I2, D1, D2, dims) with numpy host arrays (elas.h:162).
+
+        Returns JN_OK or JN_FEW_SUPPORT; in the latter case D1/D2 are untouched and the
+        reference's message is printed (elas.cpp:66-71)."""
+        for a, dt in ((I1, np.uint8), (I2, np.uint8), (D1, np.float32), (D2, np.float32)):
+            if not (isinstance(a, np.ndarray) and a.dtype == dt and a.flags["C_CONTIGUOUS"]):
+                raise TypeError("process expects C-contiguous numpy arrays (uint8 images, float32 maps)")
+        d = (C.c_int32 * 3)(*[int(x) for x in dims])
+        rc = _check(lib().jn_elas_process(self._h, _ptr(I1), _ptr(I2), _ptr(D1), _ptr(D2), d), "jn_elas_process")
+        if rc == JN_FEW_SUPPORT:
+            print("ERROR: Need at least 3 support points!")
+        return rc
+
+    def process_batch(self, I1, I2, D1, D2, status, dims, n, stream=0):
+        """Device pointers (ints), frame-major batch of n frames; asynchronous on `stream`."""
+        d = (C.c_int32 * 3)(*[int(x) for x in dims])
+        return _check(lib().jn_elas_process_batch(self._h, int(n), _P(I1), _P(I2), _P(D1), _P(D2) if D2 else None,
+                                                  _P(status) if status else None, d, _P(stream) if stream else None),
+                      "jn_elas_process_batch")
+
+    def stages(self, I1, I2, want_desc=True, want_grid=True):
+        """Runs the device pipeline on one frame and returns every intermediate (tests only)."""
+        H, W = I1.shape
+        p = self.param
+        step, gs = p.candidate_stepsize, p.grid_size
+        Wc, Hc = (W + step - 1) // step, (H + step - 1) // step
+        gw = int(np.ceil(np.float32(W) / np.float32(gs)))
+        gh = int(np.ceil(np.float32(H) / np.float32(gs)))
+        I1 = np.ascontiguousarray(I1)
+        I2 = np.ascontiguousarray(I2)
+        cap_s, cap_t = Wc * Hc + 8, 2 * (Wc * Hc + 8)
+        o = {}
+        if want_desc:
+            o["desc1"] = np.zeros((H, W, 16), np.uint8)
+            o["desc2"] = np.zeros((H, W, 16), np.uint8)
+        for k in ("dcan_raw", "dcan_incon", "dcan_final"):
+            o[k] = np.zeros((Hc, Wc), np.int16)
+        o["support"] = np.zeros((cap_s, 3), np.int32)
+        o["tri1"] = np.zeros((cap_t, 3), np.int32)
+        o["tri2"] = np.zeros((cap_t, 3), np.int32)
+        o["planes1"] = np.zeros((cap_t, 6), np.float32)
+        o["planes2"] = np.zeros((cap_t, 6), np.float32)
+        if want_grid:
+            o["grid1"] = np.zeros((gh, gw, p.disp_max + 2), np.int32)
+            o["grid2"] = np.zeros((gh, gw, p.disp_max + 2), np.int32)
+        for k in ("D1_raw", "D2_raw", "D1_lr", "D2_lr", "D1_seg", "D2_seg", "D1_gap", "D2_gap",
+                  "D1_mean", "D2_mean", "D1", "D2"):
+            o[k] = np.zeros((H, W), np.float32)
+        st = StageDump()
+        for k, a in o.items():
+            setattr(st, k, _ptr(a))
+        st.cap_support, st.cap_tri = cap_s, cap_t
+        d = (C.c_int32 * 3)(W, H, W)
+        rc = _check(lib().jn_elas_stages(self._h, _ptr(I1), _ptr(I2), d, C.byref(st)), "jn_elas_stages")
+        o["rc"] = rc
+        o["n_support"] = st.n_support
+        o["support"] = o["support"][:st.n_support]
+        if rc == 0:
+            o["tri1"], o["tri2"] = o["tri1"][:st.n_tri1], o["tri2"][:st.n_tri2]
+            o["planes1"], o["planes2"] = o["planes1"][:st.n_tri1], o["planes2"][:st.n_tri2]
+        return o
+
+
+class Calibration:
+    """K1,K2,D1,D2,R,T,XR,XT from the OpenCV YAML + the reprojection matrix Q."""
+
+    def __init__(self, path=None):
+        self.c = Calib()
+        if path is not None:
+            _check(lib().jn_calib_load_yaml(os.fsencode(path), C.byref(self.c)), "jn_calib_load_yaml")
+
+    def set_q(self, cx, cy, f, tx):
+        lib().jn_calib_set_q(C.byref(self.c), cx, cy, f, tx)
+
+    def set_q_matrix(self, Q):
+        Q = np.asarray(Q, np.float64).reshape(16)
+        for i in range(16):
+            self.c.Q[i] = Q[i]
+        self.c.has_q = 1
+
+    def arrays(self):
+        g = lambda a, s: np.array(list(a), np.float64).reshape(s)
+        return {"K1": g(self.c.K1, (3, 3)), "K2": g(self.c.K2, (3, 3)), "D1": g(self.c.D1, (1, 5)),
+                "D2": g(self.c.D2, (1, 5)), "R": g(self.c.R, (3, 3)), "T": g(self.c.T, (3,)),
+                "XR": g(self.c.XR, (3, 3)), "XT": g(self.c.XT, (3, 1)), "Q": g(self.c.Q, (4, 4))}
+
+
+class ObstacleScan:
+    """cacheDisparityValues + publishObstacleScan without ROS (point_cloud.cpp:104-147, 213-296)."""
+
+    def __init__(self, calib, width, height, crop_offset_x=0, crop_offset_y=0, device=0):
+        self.W, self.H = width, height
+        self._h = lib().jn_scan_create(C.byref(calib.c), width, height, crop_offset_x, crop_offset_y, device)
+        if not self._h:
+            raise JnError("jn_scan_create: " + last_error())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().jn_scan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def gate_cache(self):
+        out = np.zeros((self.H, self.W, 2), np.uint8)
+        _check(lib().jn_scan_gate_cache(self._h, _ptr(out)), "jn_scan_gate_cache")
+        return out
+
+    def from_disparity(self, D, want_u8=False):
+        D = np.ascontiguousarray(D, np.float32)
+        ranges = np.zeros(SCAN_BINS, np.float64)
+        meta = ScanMeta()
+        u8 = np.zeros((self.H, self.W), np.uint8) if want_u8 else None
+        _check(lib().jn_scan_from_disparity(self._h, _ptr(D), _ptr(ranges), C.byref(meta), _ptr(u8)),
+               "jn_scan_from_disparity")
+        return ranges, meta, u8
+
+    def from_disparity_batch(self, n, D, ranges, meta, dmap_u8=0, stream=0):
+        """Device pointers (ints); asynchronous on `stream`."""
+        return _check(lib().jn_scan_from_disparity_batch(self._h, int(n), _P(D), _P(ranges), _P(meta),
+                                                         _P(dmap_u8) if dmap_u8 else None,
+                                                         _P(stream) if stream else None),
+                      "jn_scan_from_disparity_batch")
+
+    def points(self, D):
+        D = np.ascontiguousarray(D, np.float32)
+        pts = np.zeros((self.W * self.H, 3), np.float64)
+        n = C.c_int32(0)
+        ranges = np.zeros(SCAN_BINS, np.float64)
+        meta = ScanMeta()
+        _check(lib().jn_points_from_disparity(self._h, _ptr(D), _ptr(pts), C.byref(n), _ptr(ranges), C.byref(meta)),
+               "jn_points_from_disparity")
+        return pts[:n.value], ranges, meta
+
+
+def scan_compact(ranges):
+    """LaserScan.ranges as the reference publishes them (finite bins, k = 89..0)."""
+    ranges = np.ascontiguousarray(ranges, np.float64)
+    out = np.zeros(SCAN_BINS, np.float32)
+    n = lib().jn_scan_compact(_ptr(ranges), _ptr(out))
+    return out[:n]

@@ -1,0 +1,458 @@
+// api.cu -- the C ABI (include/jn_elas.h) over the CUDA stages: parameter presets,
+// workspace management, Elas::process sequencing (elas.cpp:32-151) for a batch of
+// independent frames, the stage dump used by the parity tests, and the calibration
+// YAML reader (point_cloud.cpp:530-538).
+//
+// There is no CPU implementation of any stage in this library.  If the CUDA device
+// cannot be used every compute entry point fails with JN_ERR_CUDA.
+#include <math.h>
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include "common.cuh"
+#include "../../include/jn_elas_debug.h"
+
+long long g_jn_launches = 0;
+static thread_local char g_err[512] = "";
+
+void jn_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// step-wise post-processing (post.cu)
+void post_lr(const Geo& g, int B, Workspace& ws, cudaStream_t s);
+void post_segments(const Geo& g, int B, Workspace& ws, int side, cudaStream_t s);
+void post_gap(const Geo& g, int B, Workspace& ws, int side, cudaStream_t s);
+void post_mean(const Geo& g, int B, Workspace& ws, const float* in, float* tmp, float* out, size_t ostride, cudaStream_t s);
+void post_median(const Geo& g, int B, Workspace& ws, const float* in, float* tmp, float* out, size_t ostride, cudaStream_t s);
+void post_copy(const Geo& g, int B, Workspace& ws, const float* in, float* out, int32_t* status, cudaStream_t s);
+
+struct jn_elas {
+  jn_elas_params p;
+  int device;
+  Geo g;            // geometry the workspace was built for
+  Workspace ws;
+  void* arena;      // one cudaMalloc
+  // single-frame staging for the host-pointer entry point
+  uint8_t* dI[2];
+  float* dD[2];
+  int32_t* dStatus;
+  size_t stage_pixels, stage_bytes;
+};
+
+extern "C" const char* jn_last_error(void) { return g_err; }
+extern "C" long long jn_launch_count(void) { return g_jn_launches; }
+
+extern "C" void jn_elas_params_default(jn_elas_params* p, int setting) {
+  // Elas::parameters(setting), elas.h:87-144
+  p->disp_min = 0;
+  p->disp_max = 255;
+  p->support_texture = 10;
+  p->candidate_stepsize = 5;
+  p->incon_window_size = 5;
+  p->incon_threshold = 5;
+  p->incon_min_support = 5;
+  p->grid_size = 20;
+  p->beta = 0.02f;
+  p->sigma = 1;
+  p->lr_threshold = 2;
+  p->speckle_sim_threshold = 1;
+  p->speckle_size = 200;
+  p->subsampling = 0;
+  if (setting == JN_ROBOTICS) {
+    p->support_threshold = 0.85f;
+    p->add_corners = 0;
+    p->gamma = 3;
+    p->sradius = 2;
+    p->match_texture = 1;
+    p->ipol_gap_width = 3;
+    p->filter_median = 0;
+    p->filter_adaptive_mean = 1;
+    p->postprocess_only_left = 1;
+  } else {
+    p->support_threshold = 0.95f;
+    p->add_corners = 1;
+    p->gamma = 5;
+    p->sradius = 3;
+    p->match_texture = 0;
+    p->ipol_gap_width = 5000;
+    p->filter_median = 1;
+    p->filter_adaptive_mean = 0;
+    p->postprocess_only_left = 0;
+  }
+}
+
+extern "C" jn_elas* jn_elas_create(const jn_elas_params* p, int device) {
+  if (!p) { jn_set_error("jn_elas_create: null parameters"); return nullptr; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+    jn_set_error("jn_elas_create: CUDA device %d not available (%d devices); this library has no CPU path", device, ndev);
+    return nullptr;
+  }
+  jn_elas* e = new jn_elas();
+  memset(e, 0, sizeof(*e));
+  e->p = *p;
+  e->device = device;
+  return e;
+}
+
+static void free_workspace(jn_elas* e) {
+  if (e->arena) cudaFree(e->arena);
+  e->arena = nullptr;
+  memset(&e->ws, 0, sizeof(e->ws));
+}
+
+extern "C" void jn_elas_destroy(jn_elas* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  free_workspace(e);
+  for (int k = 0; k < 2; k++) { cudaFree(e->dI[k]); cudaFree(e->dD[k]); }
+  cudaFree(e->dStatus);
+  delete e;
+}
+
+static int make_geo(const jn_elas_params& p, const int32_t dims[3], Geo* out) {
+  Geo g;
+  memset(&g, 0, sizeof(g));
+  g.p = p;
+  g.W = dims[0]; g.H = dims[1]; g.bpl = dims[2];
+  if (g.W < 16 || g.H < 16 || g.bpl < g.W) { jn_set_error("bad dims %dx%d stride %d", g.W, g.H, g.bpl); return JN_ERR_ARG; }
+  if (p.subsampling) { jn_set_error("subsampling=1 is not built yet"); return JN_ERR_UNSUPPORTED; }
+  if (p.add_corners) { jn_set_error("add_corners=1 is not built yet"); return JN_ERR_UNSUPPORTED; }
+  if (p.disp_max < 10 || p.disp_max > 4095 || p.disp_min > p.disp_max || p.candidate_stepsize < 1 ||
+      p.grid_size < 1 || p.incon_window_size < 0 || p.incon_window_size > 16) {
+    jn_set_error("parameter out of the supported range");
+    return JN_ERR_ARG;
+  }
+  if (g.W >= 8192 || g.H >= 8192) { jn_set_error("image too large for the 64-bit exact predicates"); return JN_ERR_UNSUPPORTED; }
+  const int step = p.candidate_stepsize;
+  g.Wc = (g.W + step - 1) / step;
+  g.Hc = (g.H + step - 1) / step;
+  g.gw = (int)ceilf((float)g.W / (float)p.grid_size);
+  g.gh = (int)ceilf((float)g.H / (float)p.grid_size);
+  g.gwords = (p.disp_max + 1 + 31) / 32;
+  g.cap_s = g.Wc * g.Hc + 8;
+  g.cap_t = 2 * g.cap_s;
+  // prior table and radius exactly as computeDisparity builds them (elas.cpp:802-806), float math
+  float two_sigma_squared = 2 * p.sigma * p.sigma;
+  g.plane_radius = (int)fmaxf(ceilf(p.sigma * p.sradius), 2.0f);
+  if (g.plane_radius > 7) { jn_set_error("plane radius %d > 7 not supported", g.plane_radius); return JN_ERR_UNSUPPORTED; }
+  for (int dd = 0; dd <= g.plane_radius; dd++)
+    g.P[dd] = (int32_t)((-logf(p.gamma + expf(-dd * dd / two_sigma_squared)) + logf(p.gamma)) / p.beta);
+  *out = g;
+  return JN_OK;
+}
+
+template <typename T>
+static void carve(char*& cur, T*& ptr, size_t count) {
+  ptr = reinterpret_cast<T*>(cur);
+  size_t bytes = (count * sizeof(T) + 255) & ~(size_t)255;
+  cur += bytes;
+}
+
+static void layout(const Geo& g, int B, Workspace& ws, char* base) {
+  char* cur = base;
+  const size_t n = (size_t)g.W * g.H, np = (size_t)g.Wc * g.Hc, b = (size_t)B;
+  const size_t gcw = (size_t)g.gw * g.gh * g.gwords;
+  ws.B = B;
+  for (int k = 0; k < 2; k++) carve(cur, ws.desc[k], b * n * 16);
+  carve(cur, ws.dcan, b * np);
+  carve(cur, ws.dcan_incon, b * np);
+  carve(cur, ws.dcan_final, b * np);
+  carve(cur, ws.cnt, b * np);
+  carve(cur, ws.frontier, b * 2 * np);
+  carve(cur, ws.sup, b * g.cap_s * 4);
+  for (int k = 0; k < 2; k++) carve(cur, ws.px[k], b * g.cap_s);
+  carve(cur, ws.py, b * g.cap_s);
+  carve(cur, ws.occ, b * 2 * (size_t)g.W * g.Hc);
+  for (int k = 0; k < 2; k++) {
+    carve(cur, ws.xlist[k], b * g.cap_s);
+    carve(cur, ws.ylist[k], b * g.cap_s);
+    carve(cur, ws.tmpA[k], b * g.cap_s);
+    carve(cur, ws.tmpB[k], b * g.cap_s);
+    carve(cur, ws.tmpC[k], b * g.cap_s);
+    carve(cur, ws.tmpD[k], b * g.cap_t);
+    carve(cur, ws.nb[k], b * g.cap_t * 3);
+    carve(cur, ws.vx[k], b * g.cap_t * 3);
+    carve(cur, ws.nodeL[k], b * g.cap_t);
+    carve(cur, ws.nodeR[k], b * g.cap_t);
+    carve(cur, ws.tri[k], b * g.cap_t * 3);
+    carve(cur, ws.planes[k], b * g.cap_t * 6);
+    carve(cur, ws.gridtmp[k], b * gcw);
+    carve(cur, ws.gridmask[k], b * gcw);
+    carve(cur, ws.trimap[k], b * n);
+    carve(cur, ws.Draw[k], b * n);
+    carve(cur, ws.Dlr[k], b * n);
+    carve(cur, ws.Dtmp[k], b * n);
+    carve(cur, ws.Dtmp2[k], b * n);
+  }
+  carve(cur, ws.label, b * n);
+  carve(cur, ws.segsize, b * n);
+  carve(cur, ws.info, b);
+  ws.bytes = (size_t)(cur - base);
+}
+
+static int ensure_workspace(jn_elas* e, const int32_t dims[3], int B) {
+  Geo g;
+  int rc = make_geo(e->p, dims, &g);
+  if (rc) return rc;
+  JN_CUDA_CHECK(cudaSetDevice(e->device));
+  if (e->arena && e->g.W == g.W && e->g.H == g.H && e->ws.B >= B) {
+    e->g = g;  // stride may differ between calls
+    return JN_OK;
+  }
+  free_workspace(e);
+  Workspace probe;
+  memset(&probe, 0, sizeof(probe));
+  layout(g, B, probe, nullptr);
+  JN_CUDA_CHECK(cudaMalloc(&e->arena, probe.bytes));
+  JN_CUDA_CHECK(cudaMemset(e->arena, 0, probe.bytes));
+  layout(g, B, e->ws, (char*)e->arena);
+  e->g = g;
+  return JN_OK;
+}
+
+// Elas::process for B frames (elas.cpp:57-140), everything enqueued on one stream.
+static int run_pipeline(jn_elas* e, int B, const uint8_t* I1, const uint8_t* I2, float* D1, float* D2,
+                        int32_t* status, cudaStream_t s) {
+  const Geo& g = e->g;
+  Workspace& ws = e->ws;
+  launch_descriptor(g, B, I1, I2, ws, s);
+  int rc = launch_support(g, B, ws, s);
+  if (rc) return rc;
+  rc = launch_delaunay(g, B, ws, s);
+  if (rc) return rc;
+  launch_planes_grid(g, B, ws, s);
+  launch_dense(g, B, ws, s);
+  launch_post(g, B, ws, D1, D2, status, s);
+  JN_CUDA_CHECK(cudaGetLastError());
+  return JN_OK;
+}
+
+extern "C" int jn_elas_process_batch(jn_elas* e, int n, const uint8_t* I1, const uint8_t* I2, float* D1, float* D2,
+                                     int32_t* status, const int32_t dims[3], void* stream) {
+  if (!e || n <= 0 || !I1 || !I2 || !D1 || !dims) { jn_set_error("jn_elas_process_batch: bad arguments"); return JN_ERR_ARG; }
+  int rc = ensure_workspace(e, dims, n);
+  if (rc) return rc;
+  return run_pipeline(e, n, I1, I2, D1, D2, status, (cudaStream_t)stream);
+}
+
+static int ensure_staging(jn_elas* e, const int32_t dims[3]) {
+  size_t npix = (size_t)dims[0] * dims[1], nbytes = (size_t)dims[2] * dims[1];
+  if (e->stage_pixels >= npix && e->stage_bytes >= nbytes) return JN_OK;
+  for (int k = 0; k < 2; k++) { cudaFree(e->dI[k]); cudaFree(e->dD[k]); e->dI[k] = nullptr; e->dD[k] = nullptr; }
+  cudaFree(e->dStatus);
+  e->dStatus = nullptr;
+  for (int k = 0; k < 2; k++) {
+    JN_CUDA_CHECK(cudaMalloc(&e->dI[k], nbytes));
+    JN_CUDA_CHECK(cudaMalloc(&e->dD[k], npix * sizeof(float)));
+  }
+  JN_CUDA_CHECK(cudaMalloc(&e->dStatus, sizeof(int32_t)));
+  e->stage_pixels = npix;
+  e->stage_bytes = nbytes;
+  return JN_OK;
+}
+
+extern "C" int jn_elas_process(jn_elas* e, const uint8_t* I1, const uint8_t* I2, float* D1, float* D2,
+                               const int32_t dims[3]) {
+  if (!e || !I1 || !I2 || !D1 || !D2 || !dims) { jn_set_error("jn_elas_process: bad arguments"); return JN_ERR_ARG; }
+  int rc = ensure_workspace(e, dims, 1);
+  if (rc) return rc;
+  rc = ensure_staging(e, dims);
+  if (rc) return rc;
+  const size_t npix = (size_t)dims[0] * dims[1], nbytes = (size_t)dims[2] * dims[1];
+  JN_CUDA_CHECK(cudaMemcpyAsync(e->dI[0], I1, nbytes, cudaMemcpyHostToDevice, 0));
+  JN_CUDA_CHECK(cudaMemcpyAsync(e->dI[1], I2, nbytes, cudaMemcpyHostToDevice, 0));
+  rc = run_pipeline(e, 1, e->dI[0], e->dI[1], e->dD[0], e->dD[1], e->dStatus, 0);
+  if (rc) return rc;
+  int32_t st = 0;
+  JN_CUDA_CHECK(cudaMemcpy(&st, e->dStatus, sizeof(st), cudaMemcpyDeviceToHost));
+  if (st == JN_OK) {  // "<3 support points": outputs untouched (elas.cpp:66-71)
+    JN_CUDA_CHECK(cudaMemcpy(D1, e->dD[0], npix * sizeof(float), cudaMemcpyDeviceToHost));
+    JN_CUDA_CHECK(cudaMemcpy(D2, e->dD[1], npix * sizeof(float), cudaMemcpyDeviceToHost));
+  }
+  return st;
+}
+
+// ------------------------------------------------------------------------------------------
+// stage dump
+template <typename T>
+static int d2h(T* dst, const T* src, size_t count) {
+  if (!dst) return JN_OK;
+  JN_CUDA_CHECK(cudaMemcpy(dst, src, count * sizeof(T), cudaMemcpyDeviceToHost));
+  return JN_OK;
+}
+
+static int dump_grid(const Geo& g, const uint32_t* dmask, int32_t* out) {
+  if (!out) return JN_OK;
+  size_t cells = (size_t)g.gw * g.gh;
+  std::vector<uint32_t> m(cells * g.gwords);
+  JN_CUDA_CHECK(cudaMemcpy(m.data(), dmask, m.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  const int stride = g.p.disp_max + 2;
+  memset(out, 0, cells * stride * sizeof(int32_t));
+  for (size_t c = 0; c < cells; c++) {
+    int k = 0;
+    for (int d = 0; d <= g.p.disp_max; d++)
+      if (m[c * g.gwords + (d >> 5)] >> (d & 31) & 1u) out[c * stride + (++k)] = d;
+    out[c * stride] = k;
+  }
+  return JN_OK;
+}
+
+extern "C" int jn_elas_stages(jn_elas* e, const uint8_t* I1, const uint8_t* I2, const int32_t dims[3],
+                              jn_stage_dump* o) {
+  if (!e || !I1 || !I2 || !dims || !o) return JN_ERR_ARG;
+  int rc = ensure_workspace(e, dims, 1);
+  if (rc) return rc;
+  rc = ensure_staging(e, dims);
+  if (rc) return rc;
+  const Geo& g = e->g;
+  Workspace& ws = e->ws;
+  const size_t n = (size_t)g.W * g.H, np = (size_t)g.Wc * g.Hc, nbytes = (size_t)dims[2] * dims[1];
+  JN_CUDA_CHECK(cudaMemcpy(e->dI[0], I1, nbytes, cudaMemcpyHostToDevice));
+  JN_CUDA_CHECK(cudaMemcpy(e->dI[1], I2, nbytes, cudaMemcpyHostToDevice));
+  cudaStream_t s = 0;
+  launch_descriptor(g, 1, e->dI[0], e->dI[1], ws, s);
+  rc = launch_support(g, 1, ws, s);
+  if (rc) return rc;
+  JN_CUDA_CHECK(cudaDeviceSynchronize());
+  if ((rc = d2h(o->desc1, ws.desc[0], n * 16))) return rc;
+  if ((rc = d2h(o->desc2, ws.desc[1], n * 16))) return rc;
+  if ((rc = d2h(o->dcan_raw, ws.dcan, np))) return rc;
+  if ((rc = d2h(o->dcan_incon, ws.dcan_incon, np))) return rc;
+  if ((rc = d2h(o->dcan_final, ws.dcan_final, np))) return rc;
+  FrameInfo info;
+  JN_CUDA_CHECK(cudaMemcpy(&info, ws.info, sizeof(info), cudaMemcpyDeviceToHost));
+  o->n_support = info.n_support;
+  if (o->support && info.n_support <= o->cap_support) {
+    std::vector<int32_t> s4((size_t)info.n_support * 4);
+    JN_CUDA_CHECK(cudaMemcpy(s4.data(), ws.sup, s4.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < info.n_support; i++)
+      for (int k = 0; k < 3; k++) o->support[3 * i + k] = s4[4 * (size_t)i + k];
+  }
+  o->n_tri1 = o->n_tri2 = 0;
+  if (info.status != JN_OK) return JN_FEW_SUPPORT;
+
+  rc = launch_delaunay(g, 1, ws, s);
+  if (rc) return rc;
+  launch_planes_grid(g, 1, ws, s);
+  JN_CUDA_CHECK(cudaDeviceSynchronize());
+  JN_CUDA_CHECK(cudaMemcpy(&info, ws.info, sizeof(info), cudaMemcpyDeviceToHost));
+  o->n_tri1 = info.n_tri[0];
+  o->n_tri2 = info.n_tri[1];
+  for (int k = 0; k < 2; k++) {
+    int nt = info.n_tri[k];
+    if (nt > o->cap_tri) continue;
+    if ((rc = d2h(k ? o->tri2 : o->tri1, ws.tri[k], (size_t)nt * 3))) return rc;
+    if ((rc = d2h(k ? o->planes2 : o->planes1, ws.planes[k], (size_t)nt * 6))) return rc;
+  }
+  if ((rc = dump_grid(g, ws.gridmask[0], o->grid1))) return rc;
+  if ((rc = dump_grid(g, ws.gridmask[1], o->grid2))) return rc;
+
+  launch_dense(g, 1, ws, s);
+  JN_CUDA_CHECK(cudaDeviceSynchronize());
+  if ((rc = d2h(o->D1_raw, ws.Draw[0], n))) return rc;
+  if ((rc = d2h(o->D2_raw, ws.Draw[1], n))) return rc;
+
+  const int sides = g.p.postprocess_only_left ? 1 : 2;
+  post_lr(g, 1, ws, s);
+  if ((rc = d2h(o->D1_lr, ws.Dlr[0], n))) return rc;
+  if ((rc = d2h(o->D2_lr, ws.Dlr[1], n))) return rc;
+  for (int k = 0; k < sides; k++) post_segments(g, 1, ws, k, s);
+  if ((rc = d2h(o->D1_seg, ws.Dlr[0], n))) return rc;
+  if ((rc = d2h(o->D2_seg, ws.Dlr[1], n))) return rc;
+  for (int k = 0; k < sides; k++) post_gap(g, 1, ws, k, s);
+  if ((rc = d2h(o->D1_gap, ws.Dlr[0], n))) return rc;
+  if ((rc = d2h(o->D2_gap, ws.Dlr[1], n))) return rc;
+  const float* cur[2] = {ws.Dlr[0], ws.Dlr[1]};
+  if (g.p.filter_adaptive_mean)
+    for (int k = 0; k < sides; k++) {
+      post_mean(g, 1, ws, cur[k], ws.Dtmp[k], ws.Dtmp2[k], n, s);
+      cur[k] = ws.Dtmp2[k];
+    }
+  if ((rc = d2h(o->D1_mean, cur[0], n))) return rc;
+  if ((rc = d2h(o->D2_mean, cur[1], n))) return rc;
+  if (g.p.filter_median)
+    for (int k = 0; k < sides; k++) {
+      post_median(g, 1, ws, cur[k], ws.Dtmp[k], e->dD[k], n, s);
+      cur[k] = e->dD[k];
+    }
+  if ((rc = d2h(o->D1, cur[0], n))) return rc;
+  if ((rc = d2h(o->D2, cur[1], n))) return rc;
+  JN_CUDA_CHECK(cudaGetLastError());
+  return JN_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Calibration YAML (OpenCV FileStorage subset: "name: !!opencv-matrix ... data: [ ... ]" and
+// "name: [ ... ]"), point_cloud.cpp:530-538.
+static bool yaml_numbers(const std::string& txt, const char* key, std::vector<double>& out) {
+  out.clear();
+  std::string k = std::string(key) + ":";
+  size_t pos = 0;
+  while (true) {
+    pos = txt.find(k, pos);
+    if (pos == std::string::npos) return false;
+    if (pos == 0 || txt[pos - 1] == '\n') break;   // key must start a line
+    pos += k.size();
+  }
+  size_t next_key = txt.size();
+  // the block ends at the next top-level key (a line that starts with a letter)
+  for (size_t i = txt.find('\n', pos); i != std::string::npos && i + 1 < txt.size(); i = txt.find('\n', i + 1))
+    if (isalpha((unsigned char)txt[i + 1])) { next_key = i + 1; break; }
+  std::string block = txt.substr(pos + k.size(), next_key - pos - k.size());
+  size_t dpos = block.find("data:");
+  size_t lb = block.find('[', dpos == std::string::npos ? 0 : dpos);
+  size_t rb = block.find(']', lb == std::string::npos ? 0 : lb);
+  if (lb == std::string::npos || rb == std::string::npos) return false;
+  std::string nums = block.substr(lb + 1, rb - lb - 1);
+  const char* c = nums.c_str();
+  while (*c) {
+    while (*c && (*c == ',' || isspace((unsigned char)*c))) c++;
+    if (!*c) break;
+    char* end = nullptr;
+    double v = strtod(c, &end);
+    if (end == c) return false;
+    out.push_back(v);
+    c = end;
+  }
+  return true;
+}
+
+extern "C" int jn_calib_load_yaml(const char* path, jn_calib* c) {
+  if (!path || !c) return JN_ERR_ARG;
+  FILE* f = fopen(path, "rb");
+  if (!f) { jn_set_error("cannot open %s", path); return JN_ERR_IO; }
+  std::string txt;
+  char buf[4096];
+  size_t r;
+  while ((r = fread(buf, 1, sizeof(buf), f)) > 0) txt.append(buf, r);
+  fclose(f);
+  memset(c, 0, sizeof(*c));
+  struct { const char* key; double* dst; size_t n; } items[] = {
+      {"K1", c->K1, 9}, {"K2", c->K2, 9}, {"D1", c->D1, 5}, {"D2", c->D2, 5},
+      {"R", c->R, 9},   {"T", c->T, 3},   {"XR", c->XR, 9}, {"XT", c->XT, 3}};
+  std::vector<double> v;
+  for (auto& it : items) {
+    if (!yaml_numbers(txt, it.key, v) || v.size() != it.n) {
+      jn_set_error("calibration file %s: key %s missing or wrong size", path, it.key);
+      return JN_ERR_IO;
+    }
+    for (size_t i = 0; i < it.n; i++) it.dst[i] = v[i];
+  }
+  return JN_OK;
+}
+
+extern "C" void jn_calib_set_q(jn_calib* c, double cx, double cy, double f, double tx) {
+  memset(c->Q, 0, sizeof(c->Q));
+  c->Q[0] = 1;  c->Q[3] = -cx;
+  c->Q[5] = 1;  c->Q[7] = -cy;
+  c->Q[11] = f;
+  c->Q[14] = -1.0 / tx;
+  c->has_q = 1;
+}

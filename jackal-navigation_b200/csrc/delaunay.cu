@@ -1,0 +1,496 @@
+// delaunay.cu -- Delaunay triangulation of the support points on the GPU.
+//
+// Replaces computeDelaunayTriangulation (elas.cpp:445-505), i.e. Triangle 1.6
+// run as triangulate("zQB") (triangle.cpp: divconqdelaunay 6160-6217,
+// alternateaxes 5582-5601, divconqrecurse 5953-6103, mergehulls 5638-5934,
+// writeelements 7800-7862).  Support points sit on a 5-px lattice, so
+// cocircular quadruples are the rule and the Delaunay triangulation is not
+// unique; the plane prior of the dense matcher depends on which diagonal is
+// chosen.  To give the reference's triangles this kernel follows the same
+// divide-and-conquer with alternating cuts and the same strict tie rules, but
+// organised for a GPU:
+//
+//   * one CTA per (frame, image side); frames of a batch run concurrently;
+//   * ordering: points are ranked by prefix sums over an occupancy grid instead
+//     of a quicksort, and the alternating-axis median partition (a k-d tree
+//     build) is done level by level with stable CTA-wide partitions of two
+//     presorted lists;
+//   * the recursion is unrolled into levels: all subproblems of one depth are
+//     merged in parallel (one thread per merge), deepest level first;
+//   * a subproblem of n points allocates exactly 2n-2 table rows in depth-first
+//     order, so every thread knows its rows up front and the final row order
+//     (= Triangle's allocation order = its output order) needs no atomics;
+//   * predicates are exact 64-bit integer determinants (coordinates < 2^13).
+//
+// Known deviation: among duplicate right-image points (u-d,v) Triangle keeps
+// the one its randomized quicksort happens to put first; this kernel keeps the
+// lowest support index.
+#include "common.cuh"
+#include "blockutil.cuh"
+
+namespace {
+
+constexpr int DT = 512;
+constexpr int OCC_EMPTY = 0x7f7f7f7f;   // cudaMemset(0x7f) pattern
+
+struct Ot { int t, o; };
+
+struct Mesh {
+  int* nb;
+  int* vx;
+  const int* x;
+  const int* y;
+};
+
+__device__ __forceinline__ int p1(int o) { return o == 2 ? 0 : o + 1; }
+__device__ __forceinline__ int m1(int o) { return o == 0 ? 2 : o - 1; }
+__device__ __forceinline__ int enc(Ot a) { return a.t * 4 + a.o; }
+__device__ __forceinline__ Ot dec(int e) { Ot r; r.t = e >> 2; r.o = e & 3; return r; }
+__device__ __forceinline__ Ot sym(const Mesh& m, Ot a) { return dec(m.nb[3 * a.t + a.o]); }
+__device__ __forceinline__ Ot lnext(Ot a) { a.o = p1(a.o); return a; }
+__device__ __forceinline__ Ot lprev(Ot a) { a.o = m1(a.o); return a; }
+__device__ __forceinline__ int org(const Mesh& m, Ot a) { return m.vx[3 * a.t + p1(a.o)]; }
+__device__ __forceinline__ int dest(const Mesh& m, Ot a) { return m.vx[3 * a.t + m1(a.o)]; }
+__device__ __forceinline__ int apex(const Mesh& m, Ot a) { return m.vx[3 * a.t + a.o]; }
+__device__ __forceinline__ void setorg(const Mesh& m, Ot a, int v) { m.vx[3 * a.t + p1(a.o)] = v; }
+__device__ __forceinline__ void setdest(const Mesh& m, Ot a, int v) { m.vx[3 * a.t + m1(a.o)] = v; }
+__device__ __forceinline__ void setapex(const Mesh& m, Ot a, int v) { m.vx[3 * a.t + a.o] = v; }
+__device__ __forceinline__ void bond(const Mesh& m, Ot a, Ot b) {
+  m.nb[3 * a.t + a.o] = enc(b);
+  m.nb[3 * b.t + b.o] = enc(a);
+}
+__device__ __forceinline__ Ot newtri(const Mesh& m, int row) {
+  Ot r; r.t = row; r.o = 0;
+#pragma unroll
+  for (int k = 0; k < 3; k++) { m.nb[3 * row + k] = -1; m.vx[3 * row + k] = -1; }
+  return r;
+}
+
+__device__ __forceinline__ long long ccw(const Mesh& m, int a, int b, int c) {
+  long long ax = m.x[a] - m.x[c], ay = m.y[a] - m.y[c];
+  long long bx = m.x[b] - m.x[c], by = m.y[b] - m.y[c];
+  return ax * by - ay * bx;
+}
+__device__ __forceinline__ bool incircle_pos(const Mesh& m, int a, int b, int c, int d) {
+  long long dx = m.x[d], dy = m.y[d];
+  long long adx = m.x[a] - dx, ady = m.y[a] - dy;
+  long long bdx = m.x[b] - dx, bdy = m.y[b] - dy;
+  long long cdx = m.x[c] - dx, cdy = m.y[c] - dy;
+  long long al = adx * adx + ady * ady, bl = bdx * bdx + bdy * bdy, cl = cdx * cdx + cdy * cdy;
+  long long det = al * (bdx * cdy - cdx * bdy) + bl * (cdx * ady - adx * cdy) + cl * (adx * bdy - bdx * ady);
+  return det > 0;
+}
+
+// Knit the triangulations of two adjacent point sets (mergehulls).  row0/row1 are
+// the table rows of the bottom and top ghost this merge creates.
+__device__ void merge_hulls(const Mesh& m, Ot& farleft, Ot innerleft, Ot innerright, Ot& farright, int axis,
+                            int row0, int row1) {
+  const int* X = m.x; const int* Y = m.y;
+  int ild = dest(m, innerleft), ila = apex(m, innerleft);
+  int iro = org(m, innerright), ira = apex(m, innerright);
+  Ot check; int cv;
+  if (axis == 1) {
+    int flp = org(m, farleft), fla = apex(m, farleft);
+    int frp = dest(m, farright);
+    while (Y[fla] < Y[flp]) {
+      farleft = sym(m, lnext(farleft));
+      flp = fla;
+      fla = apex(m, farleft);
+    }
+    check = sym(m, innerleft);
+    cv = apex(m, check);
+    while (Y[cv] > Y[ild]) {
+      innerleft = lnext(check);
+      ila = ild;
+      ild = cv;
+      check = sym(m, innerleft);
+      cv = apex(m, check);
+    }
+    while (Y[ira] < Y[iro]) {
+      innerright = sym(m, lnext(innerright));
+      iro = ira;
+      ira = apex(m, innerright);
+    }
+    check = sym(m, farright);
+    cv = apex(m, check);
+    while (Y[cv] > Y[frp]) {
+      farright = lnext(check);
+      frp = cv;
+      check = sym(m, farright);
+      cv = apex(m, check);
+    }
+  }
+  bool changed;
+  do {
+    changed = false;
+    if (ccw(m, ild, ila, iro) > 0) {
+      innerleft = sym(m, lprev(innerleft));
+      ild = ila;
+      ila = apex(m, innerleft);
+      changed = true;
+    }
+    if (ccw(m, ira, iro, ild) > 0) {
+      innerright = sym(m, lnext(innerright));
+      iro = ira;
+      ira = apex(m, innerright);
+      changed = true;
+    }
+  } while (changed);
+  Ot leftcand = sym(m, innerleft), rightcand = sym(m, innerright);
+  Ot base = newtri(m, row0);
+  bond(m, base, innerleft);
+  base = lnext(base);
+  bond(m, base, innerright);
+  base = lnext(base);
+  setorg(m, base, iro);
+  setdest(m, base, ild);
+  if (ild == org(m, farleft)) farleft = lnext(base);
+  if (iro == dest(m, farright)) farright = lprev(base);
+  int ll = ild, lr = iro;
+  int ul = apex(m, leftcand), ur = apex(m, rightcand);
+  for (;;) {
+    bool leftdone = ccw(m, ul, ll, lr) <= 0;
+    bool rightdone = ccw(m, ur, ll, lr) <= 0;
+    if (leftdone && rightdone) {
+      Ot top = newtri(m, row1);
+      setorg(m, top, ll);
+      setdest(m, top, lr);
+      bond(m, top, base);
+      top = lnext(top);
+      bond(m, top, rightcand);
+      top = lnext(top);
+      bond(m, top, leftcand);
+      if (axis == 1) {
+        int flp = org(m, farleft), frp = dest(m, farright), fra = apex(m, farright);
+        check = sym(m, farleft);
+        cv = apex(m, check);
+        while (X[cv] < X[flp]) {
+          farleft = lprev(check);
+          flp = cv;
+          check = sym(m, farleft);
+          cv = apex(m, check);
+        }
+        while (X[fra] > X[frp]) {
+          farright = sym(m, lprev(farright));
+          frp = fra;
+          fra = apex(m, farright);
+        }
+      }
+      return;
+    }
+    if (!leftdone) {
+      Ot nxt = sym(m, lprev(leftcand));
+      int na = apex(m, nxt);
+      if (na != -1) {
+        bool bad = incircle_pos(m, ll, lr, ul, na);
+        while (bad) {
+          nxt = lnext(nxt);
+          Ot topc = sym(m, nxt);
+          nxt = lnext(nxt);
+          Ot sidec = sym(m, nxt);
+          bond(m, nxt, topc);
+          bond(m, leftcand, sidec);
+          leftcand = lnext(leftcand);
+          Ot outerc = sym(m, leftcand);
+          nxt = lprev(nxt);
+          bond(m, nxt, outerc);
+          setorg(m, leftcand, ll);
+          setdest(m, leftcand, -1);
+          setapex(m, leftcand, na);
+          setorg(m, nxt, -1);
+          setdest(m, nxt, ul);
+          setapex(m, nxt, na);
+          ul = na;
+          nxt = sidec;
+          na = apex(m, nxt);
+          bad = (na != -1) ? incircle_pos(m, ll, lr, ul, na) : false;
+        }
+      }
+    }
+    if (!rightdone) {
+      Ot nxt = sym(m, lnext(rightcand));
+      int na = apex(m, nxt);
+      if (na != -1) {
+        bool bad = incircle_pos(m, ll, lr, ur, na);
+        while (bad) {
+          nxt = lprev(nxt);
+          Ot topc = sym(m, nxt);
+          nxt = lprev(nxt);
+          Ot sidec = sym(m, nxt);
+          bond(m, nxt, topc);
+          bond(m, rightcand, sidec);
+          rightcand = lprev(rightcand);
+          Ot outerc = sym(m, rightcand);
+          nxt = lnext(nxt);
+          bond(m, nxt, outerc);
+          setorg(m, rightcand, -1);
+          setdest(m, rightcand, lr);
+          setapex(m, rightcand, na);
+          setorg(m, nxt, ur);
+          setdest(m, nxt, -1);
+          setapex(m, nxt, na);
+          ur = na;
+          nxt = sidec;
+          na = apex(m, nxt);
+          bad = (na != -1) ? incircle_pos(m, ll, lr, ur, na) : false;
+        }
+      }
+    }
+    if (leftdone || (!rightdone && incircle_pos(m, ul, ll, lr, ur))) {
+      bond(m, base, rightcand);
+      base = lprev(rightcand);
+      setdest(m, base, ll);
+      lr = ur;
+      rightcand = sym(m, base);
+      ur = apex(m, rightcand);
+    } else {
+      bond(m, base, leftcand);
+      base = lnext(leftcand);
+      setorg(m, base, lr);
+      ll = ul;
+      leftcand = sym(m, base);
+      ul = apex(m, leftcand);
+    }
+  }
+}
+
+// Base cases of divconqrecurse: 2 points = an edge (2 ghosts), 3 points = a
+// triangle + 3 ghosts or two edges (4 ghosts).
+__device__ void leaf_case(const Mesh& m, const int* sa, int n, int row, Ot& farleft, Ot& farright) {
+  if (n == 2) {
+    Ot a = newtri(m, row);
+    setorg(m, a, sa[0]);
+    setdest(m, a, sa[1]);
+    Ot b = newtri(m, row + 1);
+    setorg(m, b, sa[1]);
+    setdest(m, b, sa[0]);
+    bond(m, a, b);
+    a = lprev(a); b = lnext(b);
+    bond(m, a, b);
+    a = lprev(a); b = lnext(b);
+    bond(m, a, b);
+    farright = b;
+    farleft = lprev(b);
+    return;
+  }
+  Ot mid = newtri(m, row), t1 = newtri(m, row + 1), t2 = newtri(m, row + 2), t3 = newtri(m, row + 3);
+  long long area = ccw(m, sa[0], sa[1], sa[2]);
+  if (area == 0) {
+    setorg(m, mid, sa[0]); setdest(m, mid, sa[1]);
+    setorg(m, t1, sa[1]);  setdest(m, t1, sa[0]);
+    setorg(m, t2, sa[2]);  setdest(m, t2, sa[1]);
+    setorg(m, t3, sa[1]);  setdest(m, t3, sa[2]);
+    bond(m, mid, t1);
+    bond(m, t2, t3);
+    mid = lnext(mid); t1 = lprev(t1); t2 = lnext(t2); t3 = lprev(t3);
+    bond(m, mid, t3);
+    bond(m, t1, t2);
+    mid = lnext(mid); t1 = lprev(t1); t2 = lnext(t2); t3 = lprev(t3);
+    bond(m, mid, t1);
+    bond(m, t2, t3);
+    farleft = t1;
+    farright = t2;
+  } else {
+    setorg(m, mid, sa[0]);
+    setdest(m, t1, sa[0]);
+    setorg(m, t3, sa[0]);
+    if (area > 0) {
+      setdest(m, mid, sa[1]); setorg(m, t1, sa[1]); setdest(m, t2, sa[1]);
+      setapex(m, mid, sa[2]); setorg(m, t2, sa[2]); setdest(m, t3, sa[2]);
+    } else {
+      setdest(m, mid, sa[2]); setorg(m, t1, sa[2]); setdest(m, t2, sa[2]);
+      setapex(m, mid, sa[1]); setorg(m, t2, sa[1]); setdest(m, t3, sa[1]);
+    }
+    bond(m, mid, t1);
+    mid = lnext(mid);
+    bond(m, mid, t2);
+    mid = lnext(mid);
+    bond(m, mid, t3);
+    t1 = lprev(t1); t2 = lnext(t2);
+    bond(m, t1, t2);
+    t1 = lprev(t1); t3 = lprev(t3);
+    bond(m, t1, t3);
+    t2 = lnext(t2); t3 = lprev(t3);
+    bond(m, t2, t3);
+    farleft = t1;
+    farright = (area > 0) ? t2 : lnext(farleft);
+  }
+}
+
+struct SideBuffers {
+  const int* px; const int* py;
+  int* occ;
+  int* listA; int* listB; int* listC;   // x list, y list, spare
+  int* seglo; int* segn; int* flag; int* scan;
+  int* nb; int* vx; int* nodeL; int* nodeR;
+  int* tri;
+};
+
+__global__ void __launch_bounds__(DT, 1)
+delaunay_kernel(Geo g, Workspace ws) {
+  __shared__ int s_part[DT + 1];
+  __shared__ int s_flag;
+  const int side = blockIdx.x, frame = blockIdx.y, tid = threadIdx.x;
+  FrameInfo* info = ws.info + frame;
+  if (info->status != JN_OK) return;
+  const int n = info->n_support;
+  const size_t fo = (size_t)frame * g.cap_s;
+  const int* px = ws.px[side] + fo;
+  const int* py = ws.py + fo;
+  const int step = g.p.candidate_stepsize;
+  const int xdim = side ? g.W : g.Wc, xdiv = side ? 1 : step, Hc = g.Hc;
+  const int cells = xdim * Hc;
+  int* occ = ws.occ + ((size_t)frame * 2 + side) * ((size_t)g.W * Hc);
+  int* xl = ws.xlist[side] + fo;
+  int* yl = ws.ylist[side] + fo;
+  int* sp = ws.tmpA[side] + fo;
+  int* seglo = ws.tmpB[side] + fo;
+  int* segn = ws.tmpC[side] + fo;
+  int* flag = ws.tmpD[side] + (size_t)frame * g.cap_t;          // cap_t ints
+  int* scan = ws.nodeL[side] + (size_t)frame * g.cap_t;         // reused before the merge phase
+  int* scanbig = ws.trimap[side] + (size_t)frame * g.W * g.H;   // >= cells ints, free at this point
+
+  // ---- 1. ranks by (x,y) and (y,x) through the occupancy grid (occ preset to OCC_EMPTY) ----
+  for (int i = tid; i < n; i += DT) {
+    int cx = px[i] / xdiv, cy = py[i] / step;
+    atomicMin(&occ[cx * Hc + cy], i);   // duplicates: lowest support index survives
+  }
+  __syncthreads();
+  for (int c = tid; c < cells; c += DT) scanbig[c] = occ[c] != OCC_EMPTY;
+  __syncthreads();
+  const int nu = block_exclusive_scan(scanbig, cells, s_part);   // unique points
+  for (int c = tid; c < cells; c += DT) {
+    int id = occ[c];
+    if (id != OCC_EMPTY) xl[scanbig[c]] = id;
+  }
+  __syncthreads();
+  for (int j = tid; j < cells; j += DT) {   // y-major traversal: j = cy*xdim + cx
+    int cy = j / xdim, cx = j - cy * xdim;
+    scanbig[j] = occ[cx * Hc + cy] != OCC_EMPTY;
+  }
+  __syncthreads();
+  block_exclusive_scan(scanbig, cells, s_part);
+  for (int j = tid; j < cells; j += DT) {
+    int cy = j / xdim, cx = j - cy * xdim;
+    int id = occ[cx * Hc + cy];
+    if (id != OCC_EMPTY) yl[scanbig[j]] = id;
+  }
+  __syncthreads();
+  if (nu < 2) {
+    if (tid == 0) info->n_tri[side] = 0;
+    return;
+  }
+
+  // ---- 2. alternating-axis median partition (alternateaxes), level by level -------------
+  for (int i = tid; i < nu; i += DT) { seglo[i] = 0; segn[i] = nu; }
+  __syncthreads();
+  int depth = 0;   // number of levels that split something = depth of the deepest leaves
+  for (;; depth++) {
+    if (tid == 0) s_flag = 0;
+    __syncthreads();
+    int* prim = (depth & 1) ? yl : xl;
+    int* sec = (depth & 1) ? xl : yl;
+    for (int i = tid; i < nu; i += DT) {
+      int ns = segn[i];
+      int r = 0;
+      if (ns >= 4) { r = (i - seglo[i]) >= (ns >> 1); s_flag = 1; }
+      flag[prim[i]] = r;
+    }
+    __syncthreads();
+    if (!s_flag) break;
+    for (int i = tid; i < nu; i += DT) scan[i] = flag[sec[i]];
+    __syncthreads();
+    block_exclusive_scan(scan, nu, s_part);
+    for (int i = tid; i < nu; i += DT) {
+      int ns = segn[i], lo = seglo[i], id = sec[i];
+      int pos = i;
+      if (ns >= 4) {
+        int rb = scan[i] - scan[lo];
+        pos = flag[id] ? lo + (ns >> 1) + rb : lo + (i - lo - rb);
+      }
+      sp[pos] = id;
+    }
+    __syncthreads();
+    for (int i = tid; i < nu; i += DT) {
+      int ns = segn[i], lo = seglo[i];
+      if (ns >= 4) {
+        int dv = ns >> 1;
+        if (i - lo < dv) segn[i] = dv;
+        else { seglo[i] = lo + dv; segn[i] = ns - dv; }
+      }
+    }
+    // the partitioned copy becomes the secondary list
+    if (depth & 1) { int* t = xl; xl = sp; sp = t; } else { int* t = yl; yl = sp; sp = t; }
+    __syncthreads();
+  }
+  const int* sa = xl;   // Triangle's final sortarray
+
+  // ---- 3. merges, deepest level first -----------------------------------------------------
+  Mesh m;
+  m.nb = ws.nb[side] + (size_t)frame * g.cap_t * 3;
+  m.vx = ws.vx[side] + (size_t)frame * g.cap_t * 3;
+  m.x = px; m.y = py;
+  int* nodeL = ws.nodeL[side] + (size_t)frame * g.cap_t;
+  int* nodeR = ws.nodeR[side] + (size_t)frame * g.cap_t;
+  __syncthreads();
+  for (int d = depth; d >= 0; d--) {
+    const int nodes = 1 << d;
+    for (int k = tid; k < nodes; k += DT) {
+      // locate node (d,k): follow the bits of k from the root
+      int lo = 0, cnt = nu, row = 0;
+      bool exists = true;
+      for (int b = d - 1; b >= 0; b--) {
+        if (cnt <= 3) { exists = false; break; }
+        int dv = cnt >> 1;
+        if ((k >> b) & 1) { lo += dv; row += 2 * dv - 2; cnt -= dv; }
+        else cnt = dv;
+      }
+      if (!exists) continue;
+      Ot fl, fr;
+      if (cnt <= 3) {
+        leaf_case(m, sa + lo, cnt, row, fl, fr);
+      } else {
+        int c0 = (1 << (d + 1)) + 2 * k;
+        fl = dec(nodeL[c0]);
+        Ot il = dec(nodeR[c0]);
+        Ot ir = dec(nodeL[c0 + 1]);
+        fr = dec(nodeR[c0 + 1]);
+        merge_hulls(m, fl, il, ir, fr, d & 1, row + 2 * cnt - 4, row + 2 * cnt - 3);
+      }
+      nodeL[nodes + k] = enc(fl);
+      nodeR[nodes + k] = enc(fr);
+    }
+    __syncthreads();
+  }
+
+  // ---- 4. emit the non-ghost rows in row order (writeelements) ----------------------------
+  const int rows = 2 * nu - 2;
+  for (int t = tid; t < rows; t += DT) {
+    const int* v = m.vx + 3 * t;
+    flag[t] = (v[0] >= 0 && v[1] >= 0 && v[2] >= 0);
+  }
+  __syncthreads();
+  int* tri = ws.tri[side] + (size_t)frame * g.cap_t * 3;
+  // flag[] is overwritten by the scan; test the vertices again when writing
+  const int nt = block_exclusive_scan(flag, rows, s_part);
+  for (int t = tid; t < rows; t += DT) {
+    const int* v = m.vx + 3 * t;
+    if (v[0] >= 0 && v[1] >= 0 && v[2] >= 0) {
+      int k = flag[t];
+      tri[3 * k] = v[1];       // org
+      tri[3 * k + 1] = v[2];   // dest
+      tri[3 * k + 2] = v[0];   // apex
+    }
+  }
+  if (tid == 0) info->n_tri[side] = nt;
+}
+
+}  // namespace
+
+int launch_delaunay(const Geo& g, int B, Workspace& ws, cudaStream_t s) {
+  // occupancy grids start "empty" = 0x7f7f7f7f
+  JN_CUDA_CHECK(cudaMemsetAsync(ws.occ, 0x7f, (size_t)B * 2 * g.W * g.Hc * sizeof(int32_t), s));
+  delaunay_kernel<<<dim3(2, B), DT, 0, s>>>(g, ws);
+  g_jn_launches += 1;
+  return JN_OK;
+}

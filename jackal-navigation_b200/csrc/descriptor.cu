@@ -1,0 +1,93 @@
+// descriptor.cu -- Sobel du/dv + 16-byte descriptor, one fused tiled kernel.
+//
+// Replaces Descriptor::Descriptor (descriptor.cpp:28-36), filter::sobel3x3
+// (filter.cpp:408-416 with 372-405, 227-267, 176-222) and createDescriptor
+// (descriptor.cpp:80-112).  Output layout = Descriptor::I_desc: 16 bytes per
+// pixel at ((v*W+u)*16); pixels outside u in [3,W-4], v in [3,H-4] are 0
+// (the reference leaves them unwritten).
+//
+// Roofline: HBM.  Algorithmic bytes per image = 1*N read + 16*N written; the
+// image tile (+3 px halo) is staged once in shared memory, du/dv never touch
+// HBM, and every warp stores 32 consecutive descriptors = 512 contiguous bytes
+// (one 128-bit store per lane).
+#include "common.cuh"
+
+namespace {
+
+constexpr int TW = 64, TH = 16;          // output tile
+constexpr int IW = TW + 6, IH = TH + 6;  // image tile with 3-px halo
+constexpr int GW_ = TW + 4, GH_ = TH + 4; // gradient tile with 2-px halo
+constexpr int IWP = 72;                  // padded row pitches (bytes)
+constexpr int GWP = 68;
+
+__device__ __forceinline__ int sat8(int x) { return min(max(x, 0), 255); }
+
+__global__ void __launch_bounds__(256) descriptor_kernel(Geo g, const uint8_t* __restrict__ I1,
+                                                         const uint8_t* __restrict__ I2,
+                                                         uint8_t* __restrict__ D1, uint8_t* __restrict__ D2) {
+  __shared__ uint8_t sI[IH * IWP];
+  __shared__ uint8_t sU[GH_ * GWP];
+  __shared__ uint8_t sV[GH_ * GWP];
+
+  const int W = g.W, H = g.H;
+  const int frame = blockIdx.z >> 1, side = blockIdx.z & 1;
+  const uint8_t* I = (side ? I2 : I1) + (size_t)frame * g.bpl * H;
+  uint8_t* D = (side ? D2 : D1) + (size_t)frame * W * H * 16;
+  const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+  const int tid = threadIdx.x;
+
+  // 1. image tile, zero outside the image
+  for (int i = tid; i < IH * IW; i += 256) {
+    int r = i / IW, c = i - r * IW;
+    int y = y0 - 3 + r, x = x0 - 3 + c;
+    uint8_t v = 0;
+    if (x >= 0 && x < W && y >= 0 && y < H) v = __ldg(I + (size_t)y * g.bpl + x);
+    sI[r * IWP + c] = v;
+  }
+  __syncthreads();
+
+  // 2. Sobel responses on the gradient tile (origin x0-2, y0-2)
+  for (int i = tid; i < GH_ * GW_; i += 256) {
+    int r = i / GW_, c = i - r * GW_;
+    const uint8_t* p = sI + (r + 1) * IWP + (c + 1);  // centre pixel in sI
+    int a0 = p[-IWP - 1], a1 = p[-IWP], a2 = p[-IWP + 1];
+    int b0 = p[-1], b2 = p[1];
+    int c0 = p[IWP - 1], c1 = p[IWP], c2 = p[IWP + 1];
+    int Sl = a0 + 2 * b0 + c0, Sr = a2 + 2 * b2 + c2;
+    int Tl = a0 - c0, Tc = a1 - c1, Tr = a2 - c2;
+    sU[r * GWP + c] = (uint8_t)sat8(((Sl - Sr) >> 2) + 128);
+    sV[r * GWP + c] = (uint8_t)sat8(((Tl + 2 * Tc + Tr) >> 2) + 128);
+  }
+  __syncthreads();
+
+  // 3. gather 16 samples per pixel, one 128-bit store per pixel
+  const int tx = tid & 63, ty = tid >> 6;
+#pragma unroll
+  for (int k = 0; k < TH / 4; k++) {
+    int ly = ty + 4 * k;
+    int x = x0 + tx, y = y0 + ly;
+    if (x >= W || y >= H) continue;
+    uint4 out = make_uint4(0, 0, 0, 0);
+    if (x >= 3 && x <= W - 4 && y >= 3 && y <= H - 4) {
+      const uint8_t* u = sU + (ly + 2) * GWP + (tx + 2);
+      const uint8_t* v = sV + (ly + 2) * GWP + (tx + 2);
+      unsigned b0 = u[-2 * GWP], b1 = u[-GWP - 2], b2 = u[-GWP], b3 = u[-GWP + 2];
+      unsigned b4 = u[-1], b5 = u[0], b7 = u[1];
+      unsigned b8 = u[GWP - 2], b9 = u[GWP], b10 = u[GWP + 2], b11 = u[2 * GWP];
+      unsigned b12 = v[-GWP], b13 = v[-1], b14 = v[1], b15 = v[GWP];
+      out.x = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+      out.y = b4 | (b5 << 8) | (b5 << 16) | (b7 << 24);
+      out.z = b8 | (b9 << 8) | (b10 << 16) | (b11 << 24);
+      out.w = b12 | (b13 << 8) | (b14 << 16) | (b15 << 24);
+    }
+    *reinterpret_cast<uint4*>(D + ((size_t)y * W + x) * 16) = out;
+  }
+}
+
+}  // namespace
+
+void launch_descriptor(const Geo& g, int B, const uint8_t* I1, const uint8_t* I2, Workspace& ws, cudaStream_t s) {
+  dim3 grid((g.W + TW - 1) / TW, (g.H + TH - 1) / TH, 2 * B);
+  descriptor_kernel<<<grid, 256, 0, s>>>(g, I1, I2, ws.desc[0], ws.desc[1]);
+  g_jn_launches += 1;
+}

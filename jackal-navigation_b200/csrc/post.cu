@@ -1,0 +1,467 @@
+// post.cu -- post-processing of the raw disparity maps (elas.cpp:909-1560):
+// leftRightConsistencyCheck, removeSmallSegments, gapInterpolation,
+// adaptiveMean, median.  Full-resolution branches (subsampling = 0).
+//
+// All five are HBM-bound streaming passes over H*W floats.
+//   L/R check        one thread per pixel, out of place (the reference copies both maps first).
+//   small segments   4-connected components by union-find: rows are pre-linked to
+//                    their run start by a CTA-wide max-scan (depth-1 trees), vertical
+//                    unions use atomicMin with path halving, component sizes are
+//                    counted with warp-aggregated atomics.  At this stage every
+//                    invalid pixel is exactly -10 and similarity is symmetric, so the
+//                    components equal the reference's breadth-first segments.
+//   gap interpolation rows: one CTA per row (previous/next valid index by scans, any
+//                    gap width); columns: one thread per column walking down, lanes =
+//                    adjacent columns so every step is a coalesced row access.
+//   adaptive mean    the reference's 8-tap filter including its bit-mask "abs"
+//                     and its exact summation order, so results are
+//                    bit-identical; horizontal then vertical.
+//   median           7-tap horizontal then vertical selection.
+#include "common.cuh"
+#include "blockutil.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------ L/R check
+__global__ void lr_kernel(Geo g, Workspace ws) {
+  const int frame = blockIdx.z;
+  if (ws.info[frame].status != JN_OK) return;
+  const int W = g.W, H = g.H;
+  const int u = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y;
+  if (u >= W) return;
+  const size_t fp = (size_t)frame * W * H, a = fp + (size_t)v * W + u;
+  const float* D1 = ws.Draw[0];
+  const float* D2 = ws.Draw[1];
+  const float thr = (float)g.p.lr_threshold;
+  float d1 = D1[a], d2 = D2[a];
+  float o1 = -10.f, o2 = -10.f;
+  float uw1 = (float)u - d1, uw2 = (float)u + d2;
+  if (d1 >= 0 && uw1 >= 0 && uw1 < (float)W) {
+    o1 = (fabsf(D2[fp + (size_t)v * W + (int)uw1] - d1) > thr) ? -10.f : d1;
+  }
+  if (d2 >= 0 && uw2 >= 0 && uw2 < (float)W) {
+    o2 = (fabsf(D1[fp + (size_t)v * W + (int)uw2] - d2) > thr) ? -10.f : d2;
+  }
+  ws.Dlr[0][a] = o1;
+  ws.Dlr[1][a] = o2;
+}
+
+// ------------------------------------------------------------ small segments
+constexpr int ROW_THREADS = 256;
+
+// label[i] = index of the first pixel of i's horizontal run of similar valid pixels; -1 if invalid
+__global__ void __launch_bounds__(ROW_THREADS) seg_rows_kernel(Geo g, Workspace ws, int side) {
+  __shared__ int s_part[ROW_THREADS];
+  const int frame = blockIdx.y, v = blockIdx.x;
+  if (ws.info[frame].status != JN_OK) return;
+  const int W = g.W, H = g.H, tid = threadIdx.x;
+  const size_t base = (size_t)frame * W * H + (size_t)v * W;
+  const float* D = ws.Dlr[side] + base;
+  int* label = ws.label + base;
+  const float thr = g.p.speckle_sim_threshold;
+  const int chunk = (W + ROW_THREADS - 1) / ROW_THREADS;
+  const int lo = min(tid * chunk, W), hi = min(lo + chunk, W);
+  // A valid pixel's run starts at the nearest run start at or left of it (an invalid pixel
+  // is always followed by a start), so a max-scan over start positions is enough.
+  int last = -1;
+  for (int u = lo; u < hi; u++) {
+    float d = D[u];
+    if (d >= 0 && (u == 0 || !(D[u - 1] >= 0) || fabsf(d - D[u - 1]) > thr)) last = u;
+  }
+  s_part[tid] = last;
+  __syncthreads();
+  for (int off = 1; off < ROW_THREADS; off <<= 1) {
+    int o = (tid >= off) ? s_part[tid - off] : -1;
+    __syncthreads();
+    s_part[tid] = max(s_part[tid], o);
+    __syncthreads();
+  }
+  int cur = (tid == 0) ? -1 : s_part[tid - 1];
+  for (int u = lo; u < hi; u++) {
+    float d = D[u];
+    if (d < 0) { label[u] = -1; continue; }
+    if (u == 0 || !(D[u - 1] >= 0) || fabsf(d - D[u - 1]) > thr) cur = u;
+    label[u] = v * W + cur;
+  }
+}
+
+__device__ __forceinline__ int uf_find(int* label, int x) {
+  int p = __ldcg(label + x);   // L2 reads: other SMs update labels with atomics
+  while (p != x) {
+    int gp = __ldcg(label + p);
+    if (gp != p) label[x] = gp;  // path halving; labels only ever decrease toward an ancestor
+    x = p;
+    p = gp;
+  }
+  return x;
+}
+__device__ __forceinline__ void uf_union(int* label, int a, int b) {
+  while (true) {
+    a = uf_find(label, a);
+    b = uf_find(label, b);
+    if (a == b) return;
+    if (a < b) { int t = a; a = b; b = t; }
+    int old = atomicMin(&label[a], b);
+    if (old == a) return;
+    a = old;
+  }
+}
+
+__global__ void seg_merge_kernel(Geo g, Workspace ws, int side) {
+  const int frame = blockIdx.z;
+  if (ws.info[frame].status != JN_OK) return;
+  const int W = g.W, H = g.H;
+  const int u = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y;
+  if (u >= W || v + 1 >= H) return;
+  const size_t fp = (size_t)frame * W * H;
+  const float* D = ws.Dlr[side] + fp;
+  int* label = ws.label + fp;
+  const int i = v * W + u;
+  float d = D[i], e = D[i + W];
+  if (d >= 0 && e >= 0 && fabsf(d - e) <= g.p.speckle_sim_threshold) {
+    // only one thread per pair of horizontal runs needs to do the union: skip if my left
+    // neighbour makes the same vertical link between the same two runs
+    if (u > 0 && label[i - 1] >= 0 && label[i + W - 1] >= 0) {
+      float dl = D[i - 1], el = D[i + W - 1];
+      if (fabsf(d - dl) <= g.p.speckle_sim_threshold && fabsf(e - el) <= g.p.speckle_sim_threshold &&
+          fabsf(dl - el) <= g.p.speckle_sim_threshold)
+        return;
+    }
+    uf_union(label, i, i + W);
+  }
+}
+
+__global__ void seg_count_kernel(Geo g, Workspace ws) {
+  const int frame = blockIdx.z;
+  if (ws.info[frame].status != JN_OK) return;
+  const int W = g.W, H = g.H;
+  const int u = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y;
+  const size_t fp = (size_t)frame * W * H;
+  int* label = ws.label + fp;
+  int* size = ws.segsize + fp;
+  int root = -1;
+  if (u < W) {
+    const int i = v * W + u;
+    if (label[i] >= 0) {
+      root = uf_find(label, i);
+      label[i] = root;
+    }
+  }
+  // warp-aggregated count: one atomic per distinct root per warp
+  unsigned peers = __match_any_sync(0xffffffffu, root);
+  if (root >= 0 && (int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&size[root], __popc(peers));
+}
+
+__global__ void seg_apply_kernel(Geo g, Workspace ws, int side) {
+  const int frame = blockIdx.z;
+  if (ws.info[frame].status != JN_OK) return;
+  const int W = g.W, H = g.H;
+  const int u = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y;
+  if (u >= W) return;
+  const size_t a = (size_t)frame * W * H + (size_t)v * W + u;
+  int l = ws.label[a];
+  if (l >= 0 && ws.segsize[(size_t)frame * W * H + l] < g.p.speckle_size) ws.Dlr[side][a] = -10.f;
+}
+
+// ------------------------------------------------------------ gap interpolation
+__device__ __forceinline__ float ipol(float d1, float d2) {
+  return (fabsf(d1 - d2) < 3.0f) ? (d1 + d2) / 2 : fminf(d1, d2);
+}
+
+__global__ void __launch_bounds__(ROW_THREADS) gap_rows_kernel(Geo g, Workspace ws, int side) {
+  extern __shared__ float s_row[];           // W floats
+  __shared__ int s_prev[ROW_THREADS], s_next[ROW_THREADS];
+  const int frame = blockIdx.y, v = blockIdx.x;
+  if (ws.info[frame].status != JN_OK) return;
+  const int W = g.W, H = g.H, tid = threadIdx.x, gap = g.p.ipol_gap_width;
+  float* D = ws.Dlr[side] + (size_t)frame * W * H + (size_t)v * W;
+  for (int u = tid; u < W; u += ROW_THREADS) s_row[u] = D[u];
+  __syncthreads();
+  const int chunk = (W + ROW_THREADS - 1) / ROW_THREADS;
+  const int lo = min(tid * chunk, W), hi = min(lo + chunk, W);
+  int lastv = -1, firstv = W;
+  for (int u = lo; u < hi; u++)
+    if (s_row[u] >= 0) { lastv = u; if (firstv == W) firstv = u; }
+  s_prev[tid] = lastv;
+  s_next[tid] = firstv;
+  __syncthreads();
+  for (int off = 1; off < ROW_THREADS; off <<= 1) {
+    int a = (tid >= off) ? s_prev[tid - off] : -1;
+    int b = (tid + off < ROW_THREADS) ? s_next[tid + off] : W;
+    __syncthreads();
+    s_prev[tid] = max(s_prev[tid], a);
+    s_next[tid] = min(s_next[tid], b);
+    __syncthreads();
+  }
+  const int first_all = s_next[0], last_all = s_prev[ROW_THREADS - 1];
+  int prev = (tid == 0) ? -1 : s_prev[tid - 1];
+  for (int u = lo; u < hi; u++) {
+    if (s_row[u] >= 0) { prev = u; continue; }
+    // next valid at or after u: inside my chunk or from the suffix scan
+    int next = W;
+    for (int k = u + 1; k < hi; k++)
+      if (s_row[k] >= 0) { next = k; break; }
+    if (next == W && tid + 1 < ROW_THREADS) next = s_next[tid + 1];
+    if (prev >= 0 && next < W) {
+      if (next - prev - 1 <= gap) D[u] = ipol(s_row[prev], s_row[next]);
+    } else if (g.p.add_corners) {
+      if (prev < 0 && first_all < W && first_all - u <= gap) D[u] = s_row[first_all];
+      if (next >= W && last_all >= 0 && u - last_all <= gap) D[u] = s_row[last_all];
+    }
+  }
+}
+
+__global__ void gap_cols_kernel(Geo g, Workspace ws, int side) {
+  const int frame = blockIdx.y;
+  if (ws.info[frame].status != JN_OK) return;
+  const int W = g.W, H = g.H, gap = g.p.ipol_gap_width;
+  const int u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= W) return;
+  float* D = ws.Dlr[side] + (size_t)frame * W * H + u;
+  int count = 0;
+  float dprev = 0.f;  // value of the last valid pixel
+  bool have_prev = false;
+  for (int v = 0; v < H; v++) {
+    float d = D[(size_t)v * W];
+    if (d >= 0) {
+      if (count >= 1 && count <= gap && have_prev) {
+        float f = ipol(dprev, d);
+        for (int k = v - count; k < v; k++) D[(size_t)k * W] = f;
+      }
+      count = 0;
+      dprev = d;
+      have_prev = true;
+    } else {
+      count++;
+    }
+  }
+  if (g.p.add_corners) {
+    for (int v = 0; v < H; v++) {
+      float d = D[(size_t)v * W];
+      if (d >= 0) {
+        for (int k = max(v - gap, 0); k < v; k++) D[(size_t)k * W] = d;
+        break;
+      }
+    }
+    for (int v = H - 1; v >= 0; v--) {
+      float d = D[(size_t)v * W];
+      if (d >= 0) {
+        for (int k = v; k <= min(v + gap, H - 1); k++) D[(size_t)k * W] = d;
+        break;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------ adaptive mean
+__device__ __forceinline__ float buggy_abs(float x) { return __uint_as_float(__float_as_uint(x) & 0x4F000000u); }
+
+// One output of the 8-tap filter.  x[k] = sample at coordinate c-4+k; the reference keeps
+// samples in a ring indexed by coordinate mod 8 and adds lanes (s, s+4) first, then
+// ((l0+l1)+l2)+l3 (elas.cpp:1425-1432); `rot` = (c-4) & 3 restores that order.
+__device__ __forceinline__ bool mean8(const float x[8], float centre, int rot, float& out) {
+  float w[8], f[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    float t = 4.0f - buggy_abs(x[k] - centre);
+    w[k] = fmaxf(0.0f, t);
+    f[k] = x[k] * w[k];
+  }
+  float wq[4], fq[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) { wq[k] = w[k] + w[k + 4]; fq[k] = f[k] + f[k + 4]; }
+  // lane s holds pair k with (rot + k) & 3 == s  ->  k = (s - rot) & 3
+  float ws, fs;
+  switch (rot) {
+    case 0: ws = ((wq[0] + wq[1]) + wq[2]) + wq[3]; fs = ((fq[0] + fq[1]) + fq[2]) + fq[3]; break;
+    case 1: ws = ((wq[3] + wq[0]) + wq[1]) + wq[2]; fs = ((fq[3] + fq[0]) + fq[1]) + fq[2]; break;
+    case 2: ws = ((wq[2] + wq[3]) + wq[0]) + wq[1]; fs = ((fq[2] + fq[3]) + fq[0]) + fq[1]; break;
+    default: ws = ((wq[1] + wq[2]) + wq[3]) + wq[0]; fs = ((fq[1] + fq[2]) + fq[3]) + fq[0]; break;
+  }
+  if (ws > 0) {
+    float d = fs / ws;
+    if (d >= 0) { out = d; return true; }
+  }
+  return false;
+}
+
+// horizontal: in = post-gap map; tmp = filtered rows 3..H-4, centres 4..W-4; elsewhere -10 if
+// the input is invalid, 0 otherwise (the reference leaves those floats unwritten, H1)
+__global__ void mean_h_kernel(Geo g, Workspace ws, const float* __restrict__ in, float* __restrict__ tmp) {
+  const int frame = blockIdx.z;
+  if (ws.info[frame].status != JN_OK) return;
+  const int W = g.W, H = g.H;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y;
+  if (c >= W) return;
+  const float* row = in + (size_t)frame * W * H + (size_t)v * W;
+  float d = row[c];
+  float o = (d < 0) ? -10.f : 0.f;
+  if (W >= 8 && v >= 3 && v <= H - 4 && c >= 4 && c <= W - 4) {
+    float x[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) { float t = row[c - 4 + k]; x[k] = (t < 0) ? -10.f : t; }
+    float m;
+    if (mean8(x, x[4], (c - 4) & 3, m)) o = m;
+  }
+  tmp[(size_t)frame * W * H + (size_t)v * W + c] = o;
+}
+
+// vertical: tmp -> out for columns 3..W-4, centres 4..H-4; every other pixel keeps `in`
+__global__ void mean_v_kernel(Geo g, Workspace ws, const float* __restrict__ in, const float* __restrict__ tmp,
+                              float* __restrict__ out, size_t out_frame_stride) {
+  const int frame = blockIdx.z;
+  if (ws.info[frame].status != JN_OK) return;
+  const int W = g.W, H = g.H;
+  const int u = blockIdx.x * blockDim.x + threadIdx.x, c = blockIdx.y;
+  if (u >= W) return;
+  const size_t fp = (size_t)frame * W * H;
+  float o = in[fp + (size_t)c * W + u];
+  if (H >= 8 && u >= 3 && u <= W - 4 && c >= 4 && c <= H - 4) {
+    const float* col = tmp + fp + u;
+    float x[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) x[k] = col[(size_t)(c - 4 + k) * W];
+    float m;
+    if (mean8(x, x[4], (c - 4) & 3, m)) o = m;
+  }
+  out[(size_t)frame * out_frame_stride + (size_t)c * W + u] = o;
+}
+
+// ------------------------------------------------------------ median
+__device__ __forceinline__ float median7(float v[7]) {
+  // insertion sort, as elas.cpp:1518-1527 (NaNs cannot occur)
+#pragma unroll
+  for (int j = 1; j < 7; j++) {
+    float t = v[j];
+    int i = j - 1;
+    while (i >= 0 && v[i] > t) { v[i + 1] = v[i]; i--; }
+    v[i + 1] = t;
+  }
+  return v[3];
+}
+
+// horizontal pass into a zero-initialised temporary (calloc, elas.cpp:1505)
+__global__ void median_h_kernel(Geo g, Workspace ws, const float* __restrict__ in, float* __restrict__ tmp) {
+  const int frame = blockIdx.z;
+  if (ws.info[frame].status != JN_OK) return;
+  const int W = g.W, H = g.H;
+  const int u = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y;
+  if (u >= W) return;
+  const size_t a = (size_t)frame * W * H + (size_t)v * W + u;
+  float o = 0.f;
+  if (u >= 3 && u <= W - 4 && v >= 3 && v <= H - 4) {
+    float d = in[a];
+    o = d;
+    if (d >= 0) {
+      float x[7];
+#pragma unroll
+      for (int k = 0; k < 7; k++) x[k] = in[a - 3 + k];
+      o = median7(x);
+    }
+  }
+  tmp[a] = o;
+}
+
+__global__ void median_v_kernel(Geo g, Workspace ws, const float* __restrict__ in, const float* __restrict__ tmp,
+                                float* __restrict__ out, size_t out_frame_stride) {
+  const int frame = blockIdx.z;
+  if (ws.info[frame].status != JN_OK) return;
+  const int W = g.W, H = g.H;
+  const int u = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y;
+  if (u >= W) return;
+  const size_t a = (size_t)frame * W * H + (size_t)v * W + u;
+  float o = in[a];
+  if (u >= 3 && u <= W - 4 && v >= 3 && v <= H - 4 && o >= 0) {
+    float x[7];
+#pragma unroll
+    for (int k = 0; k < 7; k++) x[k] = tmp[a + (ptrdiff_t)(k - 3) * W];
+    o = median7(x);
+  }
+  out[(size_t)frame * out_frame_stride + (size_t)v * W + u] = o;
+}
+
+__global__ void copy_out_kernel(Geo g, Workspace ws, const float* __restrict__ in, float* __restrict__ out,
+                                int32_t* __restrict__ status) {
+  const int frame = blockIdx.y;
+  const int st = ws.info[frame].status;
+  const size_t n = (size_t)g.W * g.H;
+  if (status && blockIdx.x == 0 && threadIdx.x == 0) status[frame] = st;
+  if (st != JN_OK || out == nullptr) return;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[(size_t)frame * n + i] = in[(size_t)frame * n + i];
+}
+
+}  // namespace
+
+// Step-wise entry points (the debug dump calls them one at a time).
+void post_lr(const Geo& g, int B, Workspace& ws, cudaStream_t s) {
+  lr_kernel<<<dim3((g.W + 255) / 256, g.H, B), 256, 0, s>>>(g, ws);
+  g_jn_launches += 1;
+}
+
+void post_segments(const Geo& g, int B, Workspace& ws, int side, cudaStream_t s) {
+  dim3 pg((g.W + 255) / 256, g.H, B);
+  cudaMemsetAsync(ws.segsize, 0, (size_t)B * g.W * g.H * sizeof(int32_t), s);
+  seg_rows_kernel<<<dim3(g.H, B), ROW_THREADS, 0, s>>>(g, ws, side);
+  seg_merge_kernel<<<pg, 256, 0, s>>>(g, ws, side);
+  seg_count_kernel<<<pg, 256, 0, s>>>(g, ws);
+  seg_apply_kernel<<<pg, 256, 0, s>>>(g, ws, side);
+  g_jn_launches += 4;
+}
+
+void post_gap(const Geo& g, int B, Workspace& ws, int side, cudaStream_t s) {
+  gap_rows_kernel<<<dim3(g.H, B), ROW_THREADS, g.W * sizeof(float), s>>>(g, ws, side);
+  gap_cols_kernel<<<dim3((g.W + 63) / 64, B), 64, 0, s>>>(g, ws, side);
+  g_jn_launches += 2;
+}
+
+// in -> out (frame stride of out given in floats); tmp = scratch
+void post_mean(const Geo& g, int B, Workspace& ws, const float* in, float* tmp, float* out, size_t ostride,
+               cudaStream_t s) {
+  dim3 pg((g.W + 255) / 256, g.H, B);
+  mean_h_kernel<<<pg, 256, 0, s>>>(g, ws, in, tmp);
+  mean_v_kernel<<<pg, 256, 0, s>>>(g, ws, in, tmp, out, ostride);
+  g_jn_launches += 2;
+}
+
+void post_median(const Geo& g, int B, Workspace& ws, const float* in, float* tmp, float* out, size_t ostride,
+                 cudaStream_t s) {
+  dim3 pg((g.W + 255) / 256, g.H, B);
+  median_h_kernel<<<pg, 256, 0, s>>>(g, ws, in, tmp);
+  median_v_kernel<<<pg, 256, 0, s>>>(g, ws, in, tmp, out, ostride);
+  g_jn_launches += 2;
+}
+
+void post_copy(const Geo& g, int B, Workspace& ws, const float* in, float* out, int32_t* status, cudaStream_t s) {
+  copy_out_kernel<<<dim3(148, B), 256, 0, s>>>(g, ws, in, out, status);
+  g_jn_launches += 1;
+}
+
+// The whole chain for a batch.  D1out/D2out: user buffers (B * W*H floats); D2out may be NULL.
+void launch_post(const Geo& g, int B, Workspace& ws, float* D1out, float* D2out, int32_t* status, cudaStream_t s) {
+  const size_t n = (size_t)g.W * g.H;
+  post_lr(g, B, ws, s);
+  const int sides = g.p.postprocess_only_left ? 1 : 2;
+  for (int side = 0; side < sides; side++) {
+    post_segments(g, B, ws, side, s);
+    post_gap(g, B, ws, side, s);
+  }
+  for (int side = 0; side < 2; side++) {
+    float* out = side ? D2out : D1out;
+    if (out == nullptr) continue;
+    const float* cur = ws.Dlr[side];
+    const bool filt = side < sides;
+    const bool do_mean = filt && g.p.filter_adaptive_mean, do_med = filt && g.p.filter_median;
+    if (do_mean && do_med) {
+      post_mean(g, B, ws, cur, ws.Dtmp[side], ws.Dtmp2[side], n, s);
+      post_median(g, B, ws, ws.Dtmp2[side], ws.Dtmp[side], out, n, s);
+    } else if (do_mean) {
+      post_mean(g, B, ws, cur, ws.Dtmp[side], out, n, s);
+    } else if (do_med) {
+      post_median(g, B, ws, cur, ws.Dtmp[side], out, n, s);
+    } else {
+      post_copy(g, B, ws, cur, out, nullptr, s);
+    }
+  }
+  if (status) post_copy(g, B, ws, ws.Dlr[0], nullptr, status, s);
+}
