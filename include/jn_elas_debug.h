@@ -53,6 +53,13 @@ typedef struct jn_stage_dump {
 int jn_elas_stages(jn_elas* e, const uint8_t* I1, const uint8_t* I2, const int32_t dims[3],
                    jn_stage_dump* out);
 
+/* Per-stage device timing of a batch call, CUDA events on the launching stream.
+ * Stage order: descriptor, support (match+filter), delaunay, planes+grid, raster,
+ * dense match, post-processing. */
+#define JN_PROFILE_STAGES 7
+int jn_elas_profile(jn_elas* e, int enable);
+int jn_elas_profile_read(jn_elas* e, float ms[JN_PROFILE_STAGES]);
+
 /* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
 long long jn_launch_count(void);
 

@@ -43,6 +43,9 @@ struct jn_elas {
   float* dD[2];
   int32_t* dStatus;
   size_t stage_pixels, stage_bytes;
+  // optional per-stage timing with CUDA events on the launching stream
+  int profile;
+  cudaEvent_t ev[JN_PROFILE_STAGES + 1];
 };
 
 extern "C" const char* jn_last_error(void) { return g_err; }
@@ -113,6 +116,8 @@ extern "C" void jn_elas_destroy(jn_elas* e) {
   free_workspace(e);
   for (int k = 0; k < 2; k++) { cudaFree(e->dI[k]); cudaFree(e->dD[k]); }
   cudaFree(e->dStatus);
+  if (e->ev[0])
+    for (int i = 0; i <= JN_PROFILE_STAGES; i++) cudaEventDestroy(e->ev[i]);
   delete e;
 }
 
@@ -222,15 +227,43 @@ static int run_pipeline(jn_elas* e, int B, const uint8_t* I1, const uint8_t* I2,
                         int32_t* status, cudaStream_t s) {
   const Geo& g = e->g;
   Workspace& ws = e->ws;
+  const bool prof = e->profile != 0;
+  int k = 0;
+  if (prof) cudaEventRecord(e->ev[k++], s);
   launch_descriptor(g, B, I1, I2, ws, s);
+  if (prof) cudaEventRecord(e->ev[k++], s);
   int rc = launch_support(g, B, ws, s);
   if (rc) return rc;
+  if (prof) cudaEventRecord(e->ev[k++], s);
   rc = launch_delaunay(g, B, ws, s);
   if (rc) return rc;
+  if (prof) cudaEventRecord(e->ev[k++], s);
   launch_planes_grid(g, B, ws, s);
-  launch_dense(g, B, ws, s);
+  if (prof) cudaEventRecord(e->ev[k++], s);
+  launch_raster(g, B, ws, s);
+  if (prof) cudaEventRecord(e->ev[k++], s);
+  launch_dense_match(g, B, ws, s);
+  if (prof) cudaEventRecord(e->ev[k++], s);
   launch_post(g, B, ws, D1, D2, status, s);
+  if (prof) cudaEventRecord(e->ev[k++], s);
   JN_CUDA_CHECK(cudaGetLastError());
+  return JN_OK;
+}
+
+// Per-stage device times of the LAST profiled batch call (ms): descriptor, support,
+// delaunay, planes+grid, raster, dense match, post-processing.  The caller synchronises.
+extern "C" int jn_elas_profile(jn_elas* e, int enable) {
+  if (!e) return JN_ERR_ARG;
+  JN_CUDA_CHECK(cudaSetDevice(e->device));
+  if (enable && !e->ev[0])
+    for (int i = 0; i <= JN_PROFILE_STAGES; i++) JN_CUDA_CHECK(cudaEventCreate(&e->ev[i]));
+  e->profile = enable;
+  return JN_OK;
+}
+extern "C" int jn_elas_profile_read(jn_elas* e, float ms[JN_PROFILE_STAGES]) {
+  if (!e || !e->ev[0]) return JN_ERR_ARG;
+  JN_CUDA_CHECK(cudaEventSynchronize(e->ev[JN_PROFILE_STAGES]));
+  for (int i = 0; i < JN_PROFILE_STAGES; i++) JN_CUDA_CHECK(cudaEventElapsedTime(&ms[i], e->ev[i], e->ev[i + 1]));
   return JN_OK;
 }
 

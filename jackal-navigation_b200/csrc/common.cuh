@@ -116,4 +116,6 @@ int  launch_support(const Geo& g, int B, Workspace& ws, cudaStream_t s);
 int  launch_delaunay(const Geo& g, int B, Workspace& ws, cudaStream_t s);
 void launch_planes_grid(const Geo& g, int B, Workspace& ws, cudaStream_t s);
 void launch_dense(const Geo& g, int B, Workspace& ws, cudaStream_t s);
+void launch_raster(const Geo& g, int B, Workspace& ws, cudaStream_t s);
+void launch_dense_match(const Geo& g, int B, Workspace& ws, cudaStream_t s);
 void launch_post(const Geo& g, int B, Workspace& ws, float* D1out, float* D2out, int32_t* status, cudaStream_t s);

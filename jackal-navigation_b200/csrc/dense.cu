@@ -139,11 +139,20 @@ dense_kernel(Geo g, Workspace ws) {
 
 }  // namespace
 
-void launch_dense(const Geo& g, int B, Workspace& ws, cudaStream_t s) {
+void launch_raster(const Geo& g, int B, Workspace& ws, cudaStream_t s) {
   size_t mbytes = (size_t)B * g.W * g.H * sizeof(int32_t);
   cudaMemsetAsync(ws.trimap[0], 0xff, mbytes, s);   // -1 = no triangle
   cudaMemsetAsync(ws.trimap[1], 0xff, mbytes, s);
   raster_kernel<<<dim3(64, 2, B), 256, 0, s>>>(g, ws);
+  g_jn_launches += 1;
+}
+
+void launch_dense_match(const Geo& g, int B, Workspace& ws, cudaStream_t s) {
   dense_kernel<<<dim3((g.W + DENSE_THREADS - 1) / DENSE_THREADS, g.H, 2 * B), DENSE_THREADS, 0, s>>>(g, ws);
-  g_jn_launches += 2;
+  g_jn_launches += 1;
+}
+
+void launch_dense(const Geo& g, int B, Workspace& ws, cudaStream_t s) {
+  launch_raster(g, B, ws, s);
+  launch_dense_match(g, B, ws, s);
 }

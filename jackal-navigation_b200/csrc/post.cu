@@ -143,7 +143,11 @@ __global__ void seg_count_kernel(Geo g, Workspace ws) {
   if (u < W) {
     const int i = v * W + u;
     if (label[i] >= 0) {
-      root = uf_find(label, i);
+      // read-only walk: a path-halving store from another thread could land after this
+      // thread's `label[i] = root` and leave a non-root ancestor there
+      int x = i, p = __ldcg(label + x);
+      while (p != x) { x = p; p = __ldcg(label + x); }
+      root = x;
       label[i] = root;
     }
   }

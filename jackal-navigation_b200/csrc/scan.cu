@@ -97,6 +97,8 @@ __device__ __forceinline__ void lacc_init(LocalAcc& l) {
 __device__ __forceinline__ void lacc_add(LocalAcc& l, BlockAcc& a, double X, double Y) {
   double th = atan2(Y, X);
   double deg = th * 180. / 3.1415;
+  // defined here: a NaN reprojection (d = 0 through a wrapped gate divides by W = 0, H8) is skipped
+  if (th != th || X != X || Y != Y) return;
   double r = sqrt(Y * Y + X * X);
   unsigned long long kt = okey(th), kr = okey(r);
   l.amin = min(l.amin, kt);

@@ -745,3 +745,9 @@ int port_elas_process(const jn_elas_params* p, const uint8_t* I1, const uint8_t*
   free(b);
   return rc;
 }
+
+/* single post-processing filters, exported for unit tests */
+void port_adaptive_mean(int w, int h, float* D) { adaptive_mean(w, h, D); }
+void port_median(int w, int h, float* D) { median_filter(w, h, D); }
+void port_gap_interpolation(const jn_elas_params* p, int w, int h, float* D) { gap_interpolation(p, w, h, D); }
+void port_remove_small_segments(const jn_elas_params* p, int w, int h, float* D) { remove_small_segments(p, w, h, D); }

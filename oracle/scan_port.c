@@ -79,6 +79,9 @@ static void scan_init(double* scan, oracle_scan_meta* m) {
 static void scan_add(double X, double Y, double* scan, oracle_scan_meta* m) {
   double th = atan2(Y, X);
   double deg = th * 180. / 3.1415;
+  /* DEFINED here: a pixel whose reprojection is NaN (d = 0 passing a wrapped gate divides by
+   * W = 0, H8) is skipped; the reference would index scan[] with an undefined integer. */
+  if (th != th || X != X || Y != Y) return;
   if (th < m->angle_min) m->angle_min = th;
   if (th > m->angle_max) m->angle_max = th;
   double r = sqrt(Y * Y + X * X);
@@ -86,7 +89,7 @@ static void scan_add(double X, double Y, double* scan, oracle_scan_meta* m) {
   if (r < m->range_min) m->range_min = r;
   m->n_points++;
   double kf = floor((double)BINS * (90. / 2. - deg) / 90.);
-  if (kf < 0 || kf >= BINS) return; /* H8: defined as skip */
+  if (!(kf >= 0 && kf < BINS)) return; /* H8: defined as skip */
   int k = (int)kf;
   if (r < scan[k]) scan[k] = r;
 }

@@ -1,0 +1,204 @@
+"""Parity of the CUDA path with the oracle, through the C ABI (run with -m gpu on a B200).
+
+Integer stages (descriptors, support points, triangles, grid, SAD argmin disparities, L/R,
+segments) must be bit-exact; with identical arithmetic order and no FMA the float stages
+(planes, gap interpolation, adaptive mean, median) are bit-exact too, so every comparison
+below is exact unless a tolerance is written next to it."""
+import numpy as np
+import pytest
+import golden_util as gu
+import oracle_lib as ol
+import scan_lib
+
+pytestmark = pytest.mark.gpu
+
+STAGES = ["desc1", "desc2", "dcan_raw", "dcan_incon", "dcan_final", "support", "tri1", "tri2", "planes1", "planes2",
+          "grid1", "grid2", "D1_raw", "D2_raw", "D1_lr", "D2_lr", "D1_seg", "D2_seg", "D1_gap", "D2_gap",
+          "D1_mean", "D2_mean", "D1", "D2"]
+
+
+def assert_stages_equal(a, b, keys=STAGES):
+    assert a["rc"] == b["rc"]
+    for k in keys:
+        x, y = np.asarray(a[k]), np.asarray(b[k])
+        assert x.shape == y.shape, (k, x.shape, y.shape)
+        assert np.array_equal(x, y), "%s: %d of %d elements differ" % (k, int((x != y).sum()), x.size)
+
+
+@pytest.mark.parametrize("name,H", [("elas_robotics_160x120.npz", 120), ("elas_c5_200x150.npz", 150)])
+def test_cuda_matches_golden(jn, name, H):
+    z, p = gu.load(name)
+    pj = jn.parameters.from_buffer_copy(bytes(p))
+    e = jn.Elas(pj)
+    o = e.stages(z["I1"], z["I2"])
+    assert o["rc"] == 0
+    gu.check(o, z, H)
+    e.close()
+
+
+@pytest.mark.parametrize("W,H,dm,seed,kw", [
+    (320, 240, 64, 1, {}),
+    (333, 251, 100, 7, {}),                                            # ragged width/height
+    (640, 480, 64, 1, {}),                                             # BASELINE C1
+    (640, 480, 255, 5, {"filter_median": 1, "postprocess_only_left": 0}),
+    (256, 192, 255, 9, {"ipol_gap_width": 7, "speckle_size": 50, "lr_threshold": 1}),
+    (320, 240, 64, 3, {"filter_adaptive_mean": 0}),
+    (1920, 600, 255, 1001, {}),                                        # C3 with -h 600 crop
+])
+def test_every_stage_matches_oracle(jn, oracle, synth, W, H, dm, seed, kw):
+    I1, I2, _ = synth.synth_pair(W, H, dm, seed)
+    a = oracle.stages(ol.robotics(dm, **kw), I1, I2)
+    e = jn.Elas(jn.parameters(jn.ROBOTICS, disp_max=dm, **kw))
+    b = e.stages(I1, I2)
+    assert_stages_equal(a, b)
+    e.close()
+
+
+def test_full_size_1920x1200_matches_oracle(jn, oracle, synth):
+    """BASELINE config C3 / the bench workload, ROBOTICS and C5 (median + both images)."""
+    W, H, dm = 1920, 1200, 255
+    I1, I2, gt = synth.synth_pair(W, H, dm, 1000)
+    for kw in ({}, {"filter_median": 1, "postprocess_only_left": 0}):
+        a = oracle.stages(ol.robotics(dm, **kw), I1, I2, want_desc=False, want_grid=False)
+        e = jn.Elas(jn.parameters(jn.ROBOTICS, disp_max=dm, **kw))
+        b = e.stages(I1, I2, want_desc=False, want_grid=False)
+        assert_stages_equal(a, b, [k for k in STAGES if not k.startswith(("desc", "grid"))])
+        valid = b["D1"] >= 0
+        assert valid.mean() > 0.85
+        assert (np.abs(b["D1"] - gt)[valid] <= 1).mean() > 0.999
+        e.close()
+
+
+def test_process_is_a_drop_in(jn, oracle, synth):
+    """Elas::process semantics: same maps, caller-owned buffers, bytes_per_line honoured."""
+    W, H, dm = 333, 251, 64
+    I1, I2, _ = synth.synth_pair(W, H, dm, 21)
+    R1, R2 = oracle.process(ol.robotics(dm), I1, I2)
+    e = jn.Elas(jn.parameters(jn.ROBOTICS, disp_max=dm))
+    D1 = np.zeros((H, W), np.float32); D2 = np.zeros((H, W), np.float32)
+    assert e.process(I1, I2, D1, D2, (W, H, W)) == 0
+    assert np.array_equal(D1, R1) and np.array_equal(D2, R2)
+    # padded rows (bytes_per_line > width), elas.cpp:44-52
+    bpl = 352
+    P1 = np.full((H, bpl), 255, np.uint8); P2 = np.full((H, bpl), 255, np.uint8)
+    P1[:, :W] = I1; P2[:, :W] = I2
+    D1b = np.zeros((H, W), np.float32); D2b = np.zeros((H, W), np.float32)
+    assert e.process(P1, P2, D1b, D2b, (W, H, bpl)) == 0
+    assert np.array_equal(D1b, R1) and np.array_equal(D2b, R2)
+    e.close()
+
+
+def test_few_support_points_leave_outputs_untouched(jn, capsys):
+    """elas.cpp:66-71."""
+    I = np.full((120, 160), 77, np.uint8)
+    e = jn.Elas(jn.parameters(jn.ROBOTICS, disp_max=32))
+    D1 = np.full((120, 160), 5.0, np.float32); D2 = D1.copy()
+    assert e.process(I, I, D1, D2, (160, 120, 160)) == jn.JN_FEW_SUPPORT
+    assert (D1 == 5.0).all() and (D2 == 5.0).all()
+    assert "Need at least 3 support points" in capsys.readouterr().out
+    e.close()
+
+
+def test_unsupported_parameters_fail_loudly(jn):
+    I = np.zeros((120, 160), np.uint8); D = np.zeros((120, 160), np.float32)
+    for kw in ({"subsampling": 1}, {"add_corners": 1}):
+        e = jn.Elas(jn.parameters(jn.ROBOTICS, **kw))
+        with pytest.raises(jn.JnError):
+            e.process(I, I, D, D.copy(), (160, 120, 160))
+        e.close()
+
+
+def test_batch_equals_single_frames(jn, oracle, synth):
+    """Frames of a batch are independent: a batch (with one textureless frame in the middle)
+    gives exactly the per-frame results, in order."""
+    import torch
+    W, H, dm, B = 320, 240, 64, 5
+    L, R = synth.synth_batch(W, H, dm, [31, 32, 33, 34, 35])
+    L[2] = 9; R[2] = 9                      # frame 2 has no support points
+    dev = torch.device("cuda", 0)
+    dL = torch.from_numpy(L).to(dev); dR = torch.from_numpy(R).to(dev)
+    dD1 = torch.full((B, H, W), 7.0, dtype=torch.float32, device=dev)
+    dD2 = torch.full((B, H, W), 7.0, dtype=torch.float32, device=dev)
+    st = torch.full((B,), -9, dtype=torch.int32, device=dev)
+    e = jn.Elas(jn.parameters(jn.ROBOTICS, disp_max=dm))
+    s = torch.cuda.Stream()
+    e.process_batch(dL.data_ptr(), dR.data_ptr(), dD1.data_ptr(), dD2.data_ptr(), st.data_ptr(), (W, H, W), B,
+                    s.cuda_stream)
+    torch.cuda.synchronize()
+    assert list(st.cpu().numpy()) == [0, 0, 1, 0, 0]
+    D1 = dD1.cpu().numpy(); D2 = dD2.cpu().numpy()
+    assert (D1[2] == 7.0).all() and (D2[2] == 7.0).all()      # untouched
+    for f in (0, 1, 3, 4):
+        R1, R2 = oracle.process(ol.robotics(dm), L[f], R[f])
+        assert np.array_equal(D1[f], R1) and np.array_equal(D2[f], R2), f
+    e.close()
+
+
+def test_batch_is_deterministic_and_order_independent(jn, synth):
+    """Size-independent property at the bench size: permuting the frames of a batch permutes
+    the outputs, and two runs agree bit for bit (the segment labelling uses atomics)."""
+    import torch
+    W, H, dm, B = 1920, 1200, 255, 3
+    L, R = synth.synth_batch(W, H, dm, [1000, 1001, 1002])
+    dev = torch.device("cuda", 0)
+    e = jn.Elas(jn.parameters(jn.ROBOTICS, disp_max=dm))
+
+    def run(order):
+        dL = torch.from_numpy(L[order]).to(dev); dR = torch.from_numpy(R[order]).to(dev)
+        dD = torch.zeros((B, H, W), dtype=torch.float32, device=dev)
+        e.process_batch(dL.data_ptr(), dR.data_ptr(), dD.data_ptr(), 0, 0, (W, H, W), B, 0)
+        torch.cuda.synchronize()
+        return dD.cpu().numpy()
+
+    a = run([0, 1, 2]); b = run([0, 1, 2]); c = run([2, 0, 1])
+    assert np.array_equal(a, b)
+    assert np.array_equal(c[0], a[2]) and np.array_equal(c[1], a[0]) and np.array_equal(c[2], a[1])
+    e.close()
+
+
+@pytest.mark.parametrize("qname,W,H,dm,seed", [("640x480", 640, 480, 64, 1), ("1920x1200_Kx3", 1920, 1200, 255, 1000)])
+def test_obstacle_scan_matches_port(jn, oracle, synth, qname, W, H, dm, seed):
+    """BASELINE C2: gate cache, u8 conversion, reprojection, XR/XT, 90-bin scan, both paths.
+    Gate / u8 / bin occupancy exact; ranges and angles within 1e-9 (device atan2 is 2-ulp)."""
+    sp = scan_lib.ScanPort()
+    fx = scan_lib.fixtures()
+    cal = jn.Calibration(scan_lib.CALIB_YML)
+    cal.set_q_matrix(fx["Q"][qname])
+    A = cal.arrays()
+    I1, I2, _ = synth.synth_pair(W, H, dm, seed)
+    D1, _ = oracle.process(ol.robotics(dm), I1, I2)
+    sc = jn.ObstacleScan(cal, W, H)
+    gate_ref = sp.gate(A["Q"], A["XR"], A["XT"], W, H)
+    assert np.array_equal(sc.gate_cache(), gate_ref)
+    u8_ref = sp.convert_u8(D1)
+    r_ref, m_ref = sp.scan(A["Q"], A["XR"], A["XT"], gate_ref, u8_ref)
+    r, m, u8 = sc.from_disparity(D1, want_u8=True)
+    assert np.array_equal(u8, u8_ref)
+    assert np.array_equal(r < 1e9 - 1, r_ref < 1e9 - 1) and m.n_finite == m_ref.n_finite
+    assert m.n_points == m_ref.n_points
+    assert np.allclose(r, r_ref, rtol=0, atol=1e-9)
+    for k in ("angle_min", "angle_max", "range_min", "range_max"):
+        assert abs(getattr(m, k) - getattr(m_ref, k)) <= 1e-9, k
+    assert np.array_equal(jn.scan_compact(r), sp.compact(r))
+    # -g path: full point cloud (<= 1 mm is the stated tolerance; observed exact) + scan from points
+    pts_ref = sp.points(A["Q"], A["XR"], A["XT"], u8_ref)
+    pts, r2, m2 = sc.points(D1)
+    assert pts.shape == pts_ref.shape
+    assert np.abs(pts - pts_ref).max() <= 1e-3
+    r2_ref, m2_ref = sp.scan_points(pts_ref)
+    assert np.array_equal(r2 < 1e9 - 1, r2_ref < 1e9 - 1)
+    assert np.allclose(r2, r2_ref, rtol=0, atol=1e-9)
+    sc.close()
+
+
+def test_scan_batch_and_empty_map(jn):
+    import torch
+    fx = scan_lib.fixtures()
+    cal = jn.Calibration(scan_lib.CALIB_YML)
+    cal.set_q_matrix(fx["Q"]["640x480"])
+    W, H = 640, 480
+    sc = jn.ObstacleScan(cal, W, H)
+    r, m, _ = sc.from_disparity(np.full((H, W), -10, np.float32))   # nothing valid
+    assert (r == 1e9).all() and m.n_finite == 0 and m.n_points == 0
+    assert m.angle_min == 400 and m.angle_max == -400 and m.range_min == 1e9 and m.range_max == -500
+    sc.close()

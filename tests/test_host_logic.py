@@ -1,0 +1,113 @@
+"""CPU-only checks of the host side: the C ABI library loads and exports every declared
+symbol, presets equal the reference's, the YAML reader, loud failure without a GPU."""
+import ctypes as C
+import os
+import re
+import numpy as np
+import pytest
+import oracle_lib as ol
+import scan_lib
+
+ROOT = ol.ROOT
+
+
+def declared_functions():
+    names = set()
+    for h in ("jn_elas.h", "jn_elas_debug.h"):
+        txt = open(os.path.join(ROOT, "include", h)).read()
+        txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+        for m in re.finditer(r"\b(jn_[a-z0-9_]+)\s*\(", txt):
+            names.add(m.group(1))
+    return sorted(names)
+
+
+def test_library_exports_every_declared_symbol(jn):
+    lib = jn.lib()
+    names = declared_functions()
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(lib, n), "libjn_elas.so does not export %s" % n
+
+
+def test_presets_equal_reference_parameters(jn):
+    """Elas::parameters(ROBOTICS / MIDDLEBURY), elas.h:87-144."""
+    for setting, mk in ((jn.ROBOTICS, ol.robotics), (jn.MIDDLEBURY, ol.middlebury)):
+        a, b = jn.parameters(setting), mk()
+        for f, _ in ol.Params._fields_:
+            assert getattr(a, f) == getattr(b, f), f
+
+
+def test_presets_equal_compiled_reference(jn, ref):
+    for setting in (0, 1):
+        b = ol.Params()
+        ref.lib.ref_params_default(C.byref(b), setting)
+        a = jn.parameters(setting)
+        for f, _ in ol.Params._fields_:
+            assert getattr(a, f) == getattr(b, f), f
+
+
+def test_calibration_yaml(jn):
+    c = jn.Calibration(scan_lib.CALIB_YML).arrays()
+    fx = scan_lib.fixtures()["calib"]
+    for k in ("K1", "K2", "D1", "D2", "R", "T", "XR", "XT"):
+        assert np.array_equal(c[k].reshape(-1), np.array(fx[k], np.float64).reshape(-1)), k
+    with pytest.raises(jn.JnError):
+        jn.Calibration("/nonexistent/calib.yml")
+
+
+def test_calibration_yaml_missing_key(jn, tmp_path):
+    p = tmp_path / "bad.yml"
+    p.write_text("%YAML:1.0\nK1: !!opencv-matrix\n   rows: 3\n   cols: 3\n   dt: d\n   data: [ 1., 0., 0., 0., 1., 0., 0., 0., 1. ]\n")
+    with pytest.raises(jn.JnError):
+        jn.Calibration(str(p))
+
+
+def test_set_q(jn):
+    c = jn.Calibration()
+    c.set_q(338.27, 240.56, 679.54, -0.094)
+    Q = c.arrays()["Q"]
+    assert Q[0, 3] == -338.27 and Q[1, 3] == -240.56 and Q[2, 3] == 679.54 and Q[3, 2] == 1.0 / 0.094
+    assert Q[3, 3] == 0 and Q[0, 0] == 1 and Q[1, 1] == 1
+
+
+def test_no_cpu_fallback(jn):
+    """Without a CUDA device the product refuses to run instead of computing on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(jn.JnError, match="no CPU path"):
+        jn.Elas(jn.parameters())
+
+
+def test_product_does_not_reference_the_oracle():
+    pkg = os.path.join(ROOT, "jackal-navigation_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dp, f)).read()
+                assert "oracle/" not in txt and "oracle_lib" not in txt and "libelas_ref" not in txt, f
+
+
+def test_prior_table_matches_port(jn, port):
+    """P and plane_radius (elas.cpp:802-806) for both presets: ROBOTICS gives {-14,-9,-2}, radius 2."""
+    p = ol.robotics()
+    P = np.zeros(256, np.int32); r = C.c_int32(0)
+    port.lib.port_prior(C.byref(p), P.ctypes.data_as(C.c_void_p), C.byref(r))
+    assert r.value == 2 and list(P[:3]) == [-14, -9, -2]
+
+
+def test_scan_compact_order(jn, port):
+    ranges = np.full(90, 1e9)
+    ranges[[3, 10, 80]] = [1.5, 2.5, 3.5]
+    got = jn.scan_compact(ranges)
+    assert list(got) == [3.5, 2.5, 1.5]            # k = 89..0, finite bins only
+    assert list(scan_lib.ScanPort().compact(ranges)) == [3.5, 2.5, 1.5]
+
+
+def test_synth_ground_truth(synth):
+    I1, I2, gt = synth.synth_pair(320, 240, 64, 5)
+    v, u = 200, 300
+    d = gt[v, u]
+    assert d == int(0.10 * 64 + 0.50 * 64 * v / 240)
+    assert I2[v, u - d] == I1[v, u]
+    assert gt[120, 160] == int(0.6 * 64)

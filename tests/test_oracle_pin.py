@@ -1,0 +1,111 @@
+"""Pins the plain-C oracle port (oracle/elas_port.c, delaunay_port.c) to the reference:
+against the committed golden vectors (generated from the unmodified reference, see
+tests/golden/make_elas_golden.py) and, where oracle/_ref is built, against the compiled
+reference itself.  CPU only."""
+import numpy as np
+import pytest
+import golden_util as gu
+import oracle_lib as ol
+
+STAGE_KEYS = gu.EXACT + ["desc1", "desc2", "grid1", "grid2"]
+
+
+@pytest.mark.parametrize("name,H", [("elas_robotics_160x120.npz", 120), ("elas_c5_200x150.npz", 150)])
+def test_port_matches_golden(port, name, H):
+    z, p = gu.load(name)
+    o = port.stages(p, z["I1"], z["I2"])
+    assert o["rc"] == 0
+    gu.check(o, z, H)
+
+
+def test_port_delaunay_matches_golden_triangle_output(port):
+    z = np.load(gu.GOLD + "/delaunay_cases.npz")
+    names = [k[4:] for k in z.files if k.startswith("pts_")]
+    assert len(names) >= 8
+    for n in names:
+        got = port.triangulate(z["pts_" + n])
+        assert np.array_equal(got, z["tri_" + n]), n
+
+
+@pytest.mark.parametrize("W,H,dm,seed,kw", [
+    (320, 240, 64, 1, {}),
+    (333, 251, 100, 7, {}),                                           # width not a multiple of 16
+    (640, 480, 64, 1, {}),                                            # BASELINE config C1
+    (320, 240, 64, 3, {"filter_median": 1, "postprocess_only_left": 0}),
+    (256, 192, 255, 9, {"ipol_gap_width": 7, "speckle_size": 50, "lr_threshold": 1}),
+])
+def test_port_matches_compiled_reference_every_stage(ref, port, synth, W, H, dm, seed, kw):
+    I1, I2, _ = synth.synth_pair(W, H, dm, seed)
+    p = ol.robotics(dm, **kw)
+    a, b = ref.stages(p, I1, I2), port.stages(p, I1, I2)
+    assert a["rc"] == b["rc"] == 0
+    for k in STAGE_KEYS:
+        assert a[k].shape == b[k].shape, k
+        assert np.array_equal(a[k], b[k]), "%s: %d mismatches" % (k, int((a[k] != b[k]).sum()))
+
+
+def test_port_middlebury_matches_reference(ref, port, synth):
+    I1, I2, _ = synth.synth_pair(320, 240, 64, 3)
+    p = ol.middlebury(64)
+    a, b = ref.stages(p, I1, I2), port.stages(p, I1, I2)
+    for k in STAGE_KEYS:
+        assert np.array_equal(a[k], b[k]), k
+
+
+def test_port_delaunay_matches_triangle_random(ref, port):
+    rng = np.random.default_rng(0)
+    for it in range(300):
+        n = int(rng.integers(3, 300))
+        mode = it % 5
+        if mode == 0:
+            pts = rng.integers(0, rng.integers(2, 30), size=(n, 2)) * 5
+        elif mode == 1:
+            pts = rng.integers(0, 2000, size=(n, 2))
+        elif mode == 2:
+            pts = rng.integers(0, 6, size=(n, 2)) * 5          # many duplicates
+        elif mode == 3:
+            pts = np.stack([rng.integers(0, 50, size=n) * 5, np.full(n, 10)], 1)   # collinear
+        else:
+            u = rng.integers(1, 380, size=n) * 5; v = rng.integers(1, 240, size=n) * 5
+            pts = np.stack([u - rng.integers(0, 60, size=n), v], 1)
+        if mode in (0, 1, 4):
+            pts = np.unique(pts, axis=0)
+            rng.shuffle(pts)
+        if len(pts) < 3:
+            continue
+        assert np.array_equal(ref.triangulate(pts), port.triangulate(pts)), (it, mode)
+
+
+def test_few_support_points_leave_outputs_untouched(port):
+    """elas.cpp:66-71: a textureless pair has no support point; D1/D2 keep the caller's values."""
+    I = np.full((120, 160), 77, np.uint8)
+    p = ol.robotics(32)
+    D1 = np.full((120, 160), 5.0, np.float32); D2 = D1.copy()
+    import ctypes as C
+    dims = (C.c_int32 * 3)(160, 120, 160)
+    f = port.fn("elas_process"); f.restype = C.c_int
+    rc = f(C.byref(p), I.ctypes.data_as(C.c_void_p), I.ctypes.data_as(C.c_void_p),
+           D1.ctypes.data_as(C.c_void_p), D2.ctypes.data_as(C.c_void_p), dims)
+    assert rc == 1 and (D1 == 5.0).all() and (D2 == 5.0).all()
+
+
+def test_adaptive_mean_step_weights(port):
+    """the reference's mask turns the bilateral weight into a step function:
+    4 for |delta| < 2, 2 for 2 <= |delta| < 8, 0 for |delta| >= 8 (elas.cpp:1320, 1411-1436)."""
+    import ctypes as C
+    H, W = 16, 32
+
+    def weight(delta):
+        a = abs(delta)
+        return 4.0 if a < 2 else (2.0 if a < 8 else 0.0)
+
+    for delta in (0.5, 1.0, 1.99, 2.0, 3.0, 7.9, 8.0, 10.0, 31.0, 32.0, 60.0, -1.5, -7.0):
+        D = np.full((H, W), 20.0, np.float32)
+        D[:, 16] = 20.0 + delta                       # one outlier column -> vertical pass is neutral
+        ref_row = D[8].copy()
+        port.lib.port_adaptive_mean(W, H, D.ctypes.data_as(C.c_void_p))
+        # centre 14 sees columns 10..17 (offsets -4..+3): seven samples of 20 and the outlier
+        w = weight(delta)
+        expect = np.float32((7 * 4.0 * 20.0 + w * (20.0 + delta)) / (7 * 4.0 + w))
+        assert abs(D[8, 14] - expect) < 1e-4, (delta, D[8, 14], expect)
+        assert D[8, 5] == 20.0 and ref_row[5] == 20.0

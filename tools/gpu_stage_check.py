@@ -40,6 +40,40 @@ def compare(a, b):
     return res
 
 
+def scan_check(oracle, full):
+    import scan_lib
+    sp = scan_lib.ScanPort()
+    fx = scan_lib.fixtures()
+    cal = jn.Calibration(scan_lib.CALIB_YML)
+    A = cal.arrays()
+    for name, (W, H, dm, seed) in (("640x480", (640, 480, 64, 1)),) + ((("1920x1200_Kx3", (1920, 1200, 255, 1000)),) if full else ()):
+        Q = np.array(fx["Q"][name])
+        cal.set_q_matrix(Q)
+        I1, I2, gt = synth.synth_pair(W, H, dm, seed)
+        D1, _ = oracle.process(ol.robotics(dm), I1, I2)
+        t = time.time(); gate_ref = sp.gate(Q, A["XR"], A["XT"], W, H); tg = time.time() - t
+        sc = jn.ObstacleScan(cal, W, H)
+        gate = sc.gate_cache()
+        u8_ref = sp.convert_u8(D1)
+        r_ref, m_ref = sp.scan(Q, A["XR"], A["XT"], gate_ref, u8_ref)
+        r, m, u8 = sc.from_disparity(D1, want_u8=True)
+        fin = r_ref < 1e9 - 1
+        print("scan %s: gate mismatches %d (cpu gate %.1fs)  u8 mismatches %d  bins finite %d/%d same-set %s  max|dr| %.3e  n_points %d/%d" % (
+            name, int((gate != gate_ref).sum()), tg, int((u8 != u8_ref).sum()), int(fin.sum()), m.n_finite,
+            np.array_equal(fin, r < 1e9 - 1), float(np.abs(r[fin] - r_ref[fin]).max()) if fin.any() else 0.0, m.n_points, m_ref.n_points))
+        print("   meta ours  %.12f %.12f %.9f %.9f" % (m.angle_min, m.angle_max, m.range_min, m.range_max))
+        print("   meta port  %.12f %.12f %.9f %.9f" % (m_ref.angle_min, m_ref.angle_max, m_ref.range_min, m_ref.range_max))
+        pts_ref = sp.points(Q, A["XR"], A["XT"], u8_ref)
+        r2_ref, m2_ref = sp.scan_points(pts_ref)
+        pts, r2, m2 = sc.points(D1)
+        same = pts.shape == pts_ref.shape
+        print("   -g path: points %d/%d  max|dp| %.3e  bins same-set %s max|dr| %.3e" % (
+            len(pts), len(pts_ref), float(np.abs(pts - pts_ref).max()) if same and len(pts) else -1,
+            np.array_equal(r2 < 1e9 - 1, r2_ref < 1e9 - 1),
+            float(np.abs(r2[r2_ref < 1e9 - 1] - r2_ref[r2_ref < 1e9 - 1]).max()) if (r2_ref < 1e9 - 1).any() else 0.0))
+        sc.close()
+
+
 def main():
     full = "--full" in sys.argv
     oracle = ol.load("ref") or ol.load("port")
@@ -70,6 +104,7 @@ def main():
         summary.append({"cfg": [W, H, dm, seed, kw], "stage_mismatch": {k: str(v) for k, v in bad.items()},
                         "process_mismatch": [d1bad, d2bad]})
         e.close()
+    scan_check(oracle, full)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(summary, open(os.path.join(ROOT, "gpurun_out", "stage_check.json"), "w"), indent=1)
 
