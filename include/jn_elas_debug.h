@@ -60,6 +60,13 @@ int jn_elas_stages(jn_elas* e, const uint8_t* I1, const uint8_t* I2, const int32
 int jn_elas_profile(jn_elas* e, int enable);
 int jn_elas_profile_read(jn_elas* e, float ms[JN_PROFILE_STAGES]);
 
+/* Diagnostics: copies the device-side per-frame record (counts, status, phase timestamps). */
+int jn_elas_frameinfo(jn_elas* e, int frame, void* out, int bytes);
+
+/* Test hook: point-count limits of the Delaunay kernel's shared-memory paths (-1 = default);
+ * 0,0 forces the occupancy-grid ranking and the global-memory triangle tables. */
+void jn_debug_delaunay_limits(int sort_max, int smem_max);
+
 /* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
 long long jn_launch_count(void);
 

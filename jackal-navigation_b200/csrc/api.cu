@@ -337,6 +337,13 @@ static int dump_grid(const Geo& g, const uint32_t* dmask, int32_t* out) {
   return JN_OK;
 }
 
+// diagnostics: raw FrameInfo of frame slot `frame` after the last call (caller synchronises)
+extern "C" int jn_elas_frameinfo(jn_elas* e, int frame, void* out, int bytes) {
+  if (!e || !e->arena || frame < 0 || frame >= e->ws.B || bytes > (int)sizeof(FrameInfo)) return JN_ERR_ARG;
+  JN_CUDA_CHECK(cudaMemcpy(out, e->ws.info + frame, bytes, cudaMemcpyDeviceToHost));
+  return JN_OK;
+}
+
 extern "C" int jn_elas_stages(jn_elas* e, const uint8_t* I1, const uint8_t* I2, const int32_t dims[3],
                               jn_stage_dump* o) {
   if (!e || !I1 || !I2 || !dims || !o) return JN_ERR_ARG;

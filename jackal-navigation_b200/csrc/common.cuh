@@ -39,6 +39,7 @@ struct Geo {
   int cap_t;            // triangle-table rows per side (2*cap_s)
   int plane_radius;     // elas.cpp:806
   int P[8];             // prior table entries 0..plane_radius (elas.cpp:802-805)
+  int dl_sort_max, dl_smem_max;   // Delaunay: point-count limits of the shared-memory paths
   jn_elas_params p;
 };
 
@@ -48,7 +49,9 @@ struct FrameInfo {
   int n_tri[2];
   int status;           // JN_OK or JN_FEW_SUPPORT
   int incon_rounds;     // diagnostics
-  int pad[3];
+  int dmerge_depth;     // diagnostics: levels of the D&C tree
+  int pad[2];
+  long long dt[2][6];   // diagnostics: globaltimer at the Delaunay phase boundaries, per side
 };
 
 // All per-batch device buffers.  Index [f] = frame slot.

@@ -11,15 +11,21 @@
 // organised for a GPU:
 //
 //   * one CTA per (frame, image side); frames of a batch run concurrently;
-//   * ordering: points are ranked by prefix sums over an occupancy grid instead
-//     of a quicksort, and the alternating-axis median partition (a k-d tree
-//     build) is done level by level with stable CTA-wide partitions of two
-//     presorted lists;
+//   * ordering: a bitonic sort of 64-bit (coordinate, coordinate, index) keys in
+//     shared memory gives the (x,y) and (y,x) orders and drops duplicates; the
+//     alternating-axis median partition (a k-d tree build) is done level by
+//     level with stable CTA-wide partitions of the two presorted lists;
 //   * the recursion is unrolled into levels: all subproblems of one depth are
 //     merged in parallel (one thread per merge), deepest level first;
 //   * a subproblem of n points allocates exactly 2n-2 table rows in depth-first
 //     order, so every thread knows its rows up front and the final row order
 //     (= Triangle's allocation order = its output order) needs no atomics;
+//   * the triangle table (3 neighbour handles + 3 vertex ids per row) lives in
+//     shared memory as 6 x u16 per row (a handle = 4*row + orientation < 65536
+//     for up to 16384 rows): the merges are serial pointer chasing, and a shared
+//     memory access costs ~30 cycles against several hundred for L2.  Point
+//     sets too large for that (> SMEM_MAX_POINTS) use the same code on 32-bit
+//     tables in global memory;
 //   * predicates are exact 64-bit integer determinants (coordinates < 2^13).
 //
 // Known deviation: among duplicate right-image points (u-d,v) Triangle keeps
@@ -31,51 +37,69 @@
 namespace {
 
 constexpr int DT = 512;
-constexpr int OCC_EMPTY = 0x7f7f7f7f;   // cudaMemset(0x7f) pattern
+constexpr int SMEM_MAX_POINTS = 7680;                      // 2n-2 rows * 12 B + n * 4 B <= ~210 KB
+constexpr int SORT_MAX = 8192;                             // bitonic sort capacity (64 KB of keys)
+constexpr size_t DELAUNAY_SMEM = (size_t)(2 * SMEM_MAX_POINTS) * 12 + (size_t)SMEM_MAX_POINTS * 4;
 
 struct Ot { int t, o; };
-
-struct Mesh {
-  int* nb;
-  int* vx;
-  const int* x;
-  const int* y;
-};
 
 __device__ __forceinline__ int p1(int o) { return o == 2 ? 0 : o + 1; }
 __device__ __forceinline__ int m1(int o) { return o == 0 ? 2 : o - 1; }
 __device__ __forceinline__ int enc(Ot a) { return a.t * 4 + a.o; }
 __device__ __forceinline__ Ot dec(int e) { Ot r; r.t = e >> 2; r.o = e & 3; return r; }
-__device__ __forceinline__ Ot sym(const Mesh& m, Ot a) { return dec(m.nb[3 * a.t + a.o]); }
 __device__ __forceinline__ Ot lnext(Ot a) { a.o = p1(a.o); return a; }
 __device__ __forceinline__ Ot lprev(Ot a) { a.o = m1(a.o); return a; }
-__device__ __forceinline__ int org(const Mesh& m, Ot a) { return m.vx[3 * a.t + p1(a.o)]; }
-__device__ __forceinline__ int dest(const Mesh& m, Ot a) { return m.vx[3 * a.t + m1(a.o)]; }
-__device__ __forceinline__ int apex(const Mesh& m, Ot a) { return m.vx[3 * a.t + a.o]; }
-__device__ __forceinline__ void setorg(const Mesh& m, Ot a, int v) { m.vx[3 * a.t + p1(a.o)] = v; }
-__device__ __forceinline__ void setdest(const Mesh& m, Ot a, int v) { m.vx[3 * a.t + m1(a.o)] = v; }
-__device__ __forceinline__ void setapex(const Mesh& m, Ot a, int v) { m.vx[3 * a.t + a.o] = v; }
-__device__ __forceinline__ void bond(const Mesh& m, Ot a, Ot b) {
-  m.nb[3 * a.t + a.o] = enc(b);
-  m.nb[3 * b.t + b.o] = enc(a);
+
+// Triangle table in global memory, 32-bit entries.
+struct MeshG {
+  int* nb; int* vx; const int* x; const int* y;
+  __device__ __forceinline__ int getnb(int t, int o) const { return nb[3 * t + o]; }
+  __device__ __forceinline__ void setnb(int t, int o, int e) const { nb[3 * t + o] = e; }
+  __device__ __forceinline__ int getvx(int t, int o) const { return vx[3 * t + o]; }
+  __device__ __forceinline__ void setvx(int t, int o, int v) const { vx[3 * t + o] = v; }
+  __device__ __forceinline__ int X(int v) const { return x[v]; }
+  __device__ __forceinline__ int Y(int v) const { return y[v]; }
+};
+// Triangle table in shared memory: row = {nb0,nb1,nb2,vx0,vx1,vx2} as u16; 0xFFFF = ghost vertex.
+struct MeshS {
+  unsigned short* rows; const unsigned* xy;   // xy[v] = x << 16 | y
+  __device__ __forceinline__ int getnb(int t, int o) const { return rows[6 * t + o]; }
+  __device__ __forceinline__ void setnb(int t, int o, int e) const { rows[6 * t + o] = (unsigned short)e; }
+  __device__ __forceinline__ int getvx(int t, int o) const { int v = rows[6 * t + 3 + o]; return v == 0xFFFF ? -1 : v; }
+  __device__ __forceinline__ void setvx(int t, int o, int v) const { rows[6 * t + 3 + o] = (unsigned short)v; }
+  __device__ __forceinline__ int X(int v) const { return (int)(xy[v] >> 16); }
+  __device__ __forceinline__ int Y(int v) const { return (int)(xy[v] & 0xFFFFu); }
+};
+
+template <class M> __device__ __forceinline__ Ot sym(const M& m, Ot a) { return dec(m.getnb(a.t, a.o)); }
+template <class M> __device__ __forceinline__ int org(const M& m, Ot a) { return m.getvx(a.t, p1(a.o)); }
+template <class M> __device__ __forceinline__ int dest(const M& m, Ot a) { return m.getvx(a.t, m1(a.o)); }
+template <class M> __device__ __forceinline__ int apex(const M& m, Ot a) { return m.getvx(a.t, a.o); }
+template <class M> __device__ __forceinline__ void setorg(const M& m, Ot a, int v) { m.setvx(a.t, p1(a.o), v); }
+template <class M> __device__ __forceinline__ void setdest(const M& m, Ot a, int v) { m.setvx(a.t, m1(a.o), v); }
+template <class M> __device__ __forceinline__ void setapex(const M& m, Ot a, int v) { m.setvx(a.t, a.o, v); }
+template <class M> __device__ __forceinline__ void bond(const M& m, Ot a, Ot b) {
+  m.setnb(a.t, a.o, enc(b));
+  m.setnb(b.t, b.o, enc(a));
 }
-__device__ __forceinline__ Ot newtri(const Mesh& m, int row) {
+template <class M> __device__ __forceinline__ Ot newtri(const M& m, int row) {
   Ot r; r.t = row; r.o = 0;
 #pragma unroll
-  for (int k = 0; k < 3; k++) { m.nb[3 * row + k] = -1; m.vx[3 * row + k] = -1; }
+  for (int k = 0; k < 3; k++) { m.setnb(row, k, 0); m.setvx(row, k, -1); }
   return r;
 }
 
-__device__ __forceinline__ long long ccw(const Mesh& m, int a, int b, int c) {
-  long long ax = m.x[a] - m.x[c], ay = m.y[a] - m.y[c];
-  long long bx = m.x[b] - m.x[c], by = m.y[b] - m.y[c];
+template <class M> __device__ __forceinline__ long long ccw(const M& m, int a, int b, int c) {
+  long long cx = m.X(c), cy = m.Y(c);
+  long long ax = m.X(a) - cx, ay = m.Y(a) - cy;
+  long long bx = m.X(b) - cx, by = m.Y(b) - cy;
   return ax * by - ay * bx;
 }
-__device__ __forceinline__ bool incircle_pos(const Mesh& m, int a, int b, int c, int d) {
-  long long dx = m.x[d], dy = m.y[d];
-  long long adx = m.x[a] - dx, ady = m.y[a] - dy;
-  long long bdx = m.x[b] - dx, bdy = m.y[b] - dy;
-  long long cdx = m.x[c] - dx, cdy = m.y[c] - dy;
+template <class M> __device__ __forceinline__ bool incircle_pos(const M& m, int a, int b, int c, int d) {
+  long long dx = m.X(d), dy = m.Y(d);
+  long long adx = m.X(a) - dx, ady = m.Y(a) - dy;
+  long long bdx = m.X(b) - dx, bdy = m.Y(b) - dy;
+  long long cdx = m.X(c) - dx, cdy = m.Y(c) - dy;
   long long al = adx * adx + ady * ady, bl = bdx * bdx + bdy * bdy, cl = cdx * cdx + cdy * cdy;
   long long det = al * (bdx * cdy - cdx * bdy) + bl * (cdx * ady - adx * cdy) + cl * (adx * bdy - bdx * ady);
   return det > 0;
@@ -83,37 +107,37 @@ __device__ __forceinline__ bool incircle_pos(const Mesh& m, int a, int b, int c,
 
 // Knit the triangulations of two adjacent point sets (mergehulls).  row0/row1 are
 // the table rows of the bottom and top ghost this merge creates.
-__device__ void merge_hulls(const Mesh& m, Ot& farleft, Ot innerleft, Ot innerright, Ot& farright, int axis,
+template <class M>
+__device__ void merge_hulls(const M& m, Ot& farleft, Ot innerleft, Ot innerright, Ot& farright, int axis,
                             int row0, int row1) {
-  const int* X = m.x; const int* Y = m.y;
   int ild = dest(m, innerleft), ila = apex(m, innerleft);
   int iro = org(m, innerright), ira = apex(m, innerright);
   Ot check; int cv;
   if (axis == 1) {
     int flp = org(m, farleft), fla = apex(m, farleft);
     int frp = dest(m, farright);
-    while (Y[fla] < Y[flp]) {
+    while (m.Y(fla) < m.Y(flp)) {
       farleft = sym(m, lnext(farleft));
       flp = fla;
       fla = apex(m, farleft);
     }
     check = sym(m, innerleft);
     cv = apex(m, check);
-    while (Y[cv] > Y[ild]) {
+    while (m.Y(cv) > m.Y(ild)) {
       innerleft = lnext(check);
       ila = ild;
       ild = cv;
       check = sym(m, innerleft);
       cv = apex(m, check);
     }
-    while (Y[ira] < Y[iro]) {
+    while (m.Y(ira) < m.Y(iro)) {
       innerright = sym(m, lnext(innerright));
       iro = ira;
       ira = apex(m, innerright);
     }
     check = sym(m, farright);
     cv = apex(m, check);
-    while (Y[cv] > Y[frp]) {
+    while (m.Y(cv) > m.Y(frp)) {
       farright = lnext(check);
       frp = cv;
       check = sym(m, farright);
@@ -164,13 +188,13 @@ __device__ void merge_hulls(const Mesh& m, Ot& farleft, Ot innerleft, Ot innerri
         int flp = org(m, farleft), frp = dest(m, farright), fra = apex(m, farright);
         check = sym(m, farleft);
         cv = apex(m, check);
-        while (X[cv] < X[flp]) {
+        while (m.X(cv) < m.X(flp)) {
           farleft = lprev(check);
           flp = cv;
           check = sym(m, farleft);
           cv = apex(m, check);
         }
-        while (X[fra] > X[frp]) {
+        while (m.X(fra) > m.X(frp)) {
           farright = sym(m, lprev(farright));
           frp = fra;
           fra = apex(m, farright);
@@ -256,7 +280,8 @@ __device__ void merge_hulls(const Mesh& m, Ot& farleft, Ot innerleft, Ot innerri
 
 // Base cases of divconqrecurse: 2 points = an edge (2 ghosts), 3 points = a
 // triangle + 3 ghosts or two edges (4 ghosts).
-__device__ void leaf_case(const Mesh& m, const int* sa, int n, int row, Ot& farleft, Ot& farright) {
+template <class M>
+__device__ void leaf_case(const M& m, const int* sa, int n, int row, Ot& farleft, Ot& farright) {
   if (n == 2) {
     Ot a = newtri(m, row);
     setorg(m, a, sa[0]);
@@ -317,17 +342,86 @@ __device__ void leaf_case(const Mesh& m, const int* sa, int n, int row, Ot& farl
   }
 }
 
-struct SideBuffers {
-  const int* px; const int* py;
-  int* occ;
-  int* listA; int* listB; int* listC;   // x list, y list, spare
-  int* seglo; int* segn; int* flag; int* scan;
-  int* nb; int* vx; int* nodeL; int* nodeR;
-  int* tri;
-};
+// All merges of one triangulation, deepest level first, then the non-ghost rows in row
+// order (writeelements).  Returns the triangle count.
+template <class M>
+__device__ int build_and_emit(const M& m, const int* sa, int nu, int depth, int* nodeL, int* nodeR, int* flag,
+                              int* tri, int* s_part) {
+  const int tid = threadIdx.x;
+  for (int d = depth; d >= 0; d--) {
+    const int nodes = 1 << d;
+    for (int k = tid; k < nodes; k += DT) {
+      // locate node (d,k): follow the bits of k from the root
+      int lo = 0, cnt = nu, row = 0;
+      bool exists = true;
+      for (int b = d - 1; b >= 0; b--) {
+        if (cnt <= 3) { exists = false; break; }
+        int dv = cnt >> 1;
+        if ((k >> b) & 1) { lo += dv; row += 2 * dv - 2; cnt -= dv; }
+        else cnt = dv;
+      }
+      if (!exists) continue;
+      Ot fl, fr;
+      if (cnt <= 3) {
+        leaf_case(m, sa + lo, cnt, row, fl, fr);
+      } else {
+        int c0 = (1 << (d + 1)) + 2 * k;
+        fl = dec(nodeL[c0]);
+        Ot il = dec(nodeR[c0]);
+        Ot ir = dec(nodeL[c0 + 1]);
+        fr = dec(nodeR[c0 + 1]);
+        merge_hulls(m, fl, il, ir, fr, d & 1, row + 2 * cnt - 4, row + 2 * cnt - 3);
+      }
+      nodeL[nodes + k] = enc(fl);
+      nodeR[nodes + k] = enc(fr);
+    }
+    __syncthreads();
+  }
+  const int rows = 2 * nu - 2;
+  for (int t = tid; t < rows; t += DT)
+    flag[t] = (m.getvx(t, 0) >= 0 && m.getvx(t, 1) >= 0 && m.getvx(t, 2) >= 0);
+  __syncthreads();
+  const int nt = block_exclusive_scan(flag, rows, s_part);
+  for (int t = tid; t < rows; t += DT) {
+    int v0 = m.getvx(t, 0), v1 = m.getvx(t, 1), v2 = m.getvx(t, 2);
+    if (v0 >= 0 && v1 >= 0 && v2 >= 0) {
+      int k = flag[t];
+      tri[3 * k] = v1;       // org
+      tri[3 * k + 1] = v2;   // dest
+      tri[3 * k + 2] = v0;   // apex
+    }
+  }
+  return nt;
+}
+
+// ascending bitonic sort of N (power of two) 64-bit keys in shared memory
+__device__ void bitonic_sort(unsigned long long* key, int N) {
+  const int tid = threadIdx.x;
+  for (int k = 2; k <= N; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < N; i += DT) {
+        int ixj = i ^ j;
+        if (ixj > i) {
+          unsigned long long a = key[i], b = key[ixj];
+          bool asc = (i & k) == 0;
+          if ((a > b) == asc) { key[i] = b; key[ixj] = a; }
+        }
+      }
+      __syncthreads();
+    }
+}
+
+__device__ __forceinline__ long long gtime() {
+  long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+constexpr int OCC_EMPTY = 0x7f7f7f7f;   // cudaMemset(0x7f) pattern
 
 __global__ void __launch_bounds__(DT, 1)
 delaunay_kernel(Geo g, Workspace ws) {
+  extern __shared__ __align__(16) unsigned char dsm[];
   __shared__ int s_part[DT + 1];
   __shared__ int s_flag;
   const int side = blockIdx.x, frame = blockIdx.y, tid = threadIdx.x;
@@ -337,10 +431,6 @@ delaunay_kernel(Geo g, Workspace ws) {
   const size_t fo = (size_t)frame * g.cap_s;
   const int* px = ws.px[side] + fo;
   const int* py = ws.py + fo;
-  const int step = g.p.candidate_stepsize;
-  const int xdim = side ? g.W : g.Wc, xdiv = side ? 1 : step, Hc = g.Hc;
-  const int cells = xdim * Hc;
-  int* occ = ws.occ + ((size_t)frame * 2 + side) * ((size_t)g.W * Hc);
   int* xl = ws.xlist[side] + fo;
   int* yl = ws.ylist[side] + fo;
   int* sp = ws.tmpA[side] + fo;
@@ -348,38 +438,75 @@ delaunay_kernel(Geo g, Workspace ws) {
   int* segn = ws.tmpC[side] + fo;
   int* flag = ws.tmpD[side] + (size_t)frame * g.cap_t;          // cap_t ints
   int* scan = ws.nodeL[side] + (size_t)frame * g.cap_t;         // reused before the merge phase
-  int* scanbig = ws.trimap[side] + (size_t)frame * g.W * g.H;   // >= cells ints, free at this point
+  if (tid == 0) info->dt[side][0] = gtime();
 
-  // ---- 1. ranks by (x,y) and (y,x) through the occupancy grid (occ preset to OCC_EMPTY) ----
-  for (int i = tid; i < n; i += DT) {
-    int cx = px[i] / xdiv, cy = py[i] / step;
-    atomicMin(&occ[cx * Hc + cy], i);   // duplicates: lowest support index survives
+  // ---- 1. (x,y) order without duplicates, then (y,x) order ------------------------------------
+  int nu;
+  if (n <= g.dl_sort_max) {
+    unsigned long long* key = reinterpret_cast<unsigned long long*>(dsm);
+    int N = 2;
+    while (N < n) N <<= 1;
+    for (int i = tid; i < N; i += DT)
+      key[i] = (i < n) ? (((unsigned long long)px[i] << 48) | ((unsigned long long)py[i] << 32) | (unsigned)i)
+                       : ~0ull;
+    __syncthreads();
+    bitonic_sort(key, N);
+    // first of every (x,y) run survives = lowest support index
+    for (int i = tid; i < n; i += DT) scan[i] = (i == 0) || ((key[i] >> 32) != (key[i - 1] >> 32));
+    __syncthreads();
+    nu = block_exclusive_scan(scan, n, s_part);
+    for (int i = tid; i < n; i += DT) {
+      bool first = (i == 0) || ((key[i] >> 32) != (key[i - 1] >> 32));
+      if (first) xl[scan[i]] = (int)(key[i] & 0xFFFFFFFFu);
+    }
+    __syncthreads();
+    for (int i = tid; i < N; i += DT) {
+      unsigned long long k = ~0ull;
+      if (i < nu) {
+        int id = xl[i];
+        k = ((unsigned long long)py[id] << 48) | ((unsigned long long)px[id] << 32) | (unsigned)id;
+      }
+      key[i] = k;
+    }
+    __syncthreads();
+    bitonic_sort(key, N);
+    for (int i = tid; i < nu; i += DT) yl[i] = (int)(key[i] & 0xFFFFFFFFu);
+    __syncthreads();
+  } else {
+    // large point sets: ranks by prefix sums over an occupancy grid (preset to OCC_EMPTY)
+    const int step = g.p.candidate_stepsize;
+    const int xdim = side ? g.W : g.Wc, xdiv = side ? 1 : step, Hc = g.Hc;
+    const int cells = xdim * Hc;
+    int* occ = ws.occ + ((size_t)frame * 2 + side) * ((size_t)g.W * Hc);
+    int* scanbig = ws.trimap[side] + (size_t)frame * g.W * g.H;   // >= cells ints, free at this point
+    for (int i = tid; i < n; i += DT) atomicMin(&occ[(px[i] / xdiv) * Hc + py[i] / step], i);
+    __syncthreads();
+    for (int c = tid; c < cells; c += DT) scanbig[c] = occ[c] != OCC_EMPTY;
+    __syncthreads();
+    nu = block_exclusive_scan(scanbig, cells, s_part);
+    for (int c = tid; c < cells; c += DT) {
+      int id = occ[c];
+      if (id != OCC_EMPTY) xl[scanbig[c]] = id;
+    }
+    __syncthreads();
+    for (int j = tid; j < cells; j += DT) {   // y-major traversal: j = cy*xdim + cx
+      int cy = j / xdim, cx = j - cy * xdim;
+      scanbig[j] = occ[cx * Hc + cy] != OCC_EMPTY;
+    }
+    __syncthreads();
+    block_exclusive_scan(scanbig, cells, s_part);
+    for (int j = tid; j < cells; j += DT) {
+      int cy = j / xdim, cx = j - cy * xdim;
+      int id = occ[cx * Hc + cy];
+      if (id != OCC_EMPTY) yl[scanbig[j]] = id;
+    }
+    __syncthreads();
   }
-  __syncthreads();
-  for (int c = tid; c < cells; c += DT) scanbig[c] = occ[c] != OCC_EMPTY;
-  __syncthreads();
-  const int nu = block_exclusive_scan(scanbig, cells, s_part);   // unique points
-  for (int c = tid; c < cells; c += DT) {
-    int id = occ[c];
-    if (id != OCC_EMPTY) xl[scanbig[c]] = id;
-  }
-  __syncthreads();
-  for (int j = tid; j < cells; j += DT) {   // y-major traversal: j = cy*xdim + cx
-    int cy = j / xdim, cx = j - cy * xdim;
-    scanbig[j] = occ[cx * Hc + cy] != OCC_EMPTY;
-  }
-  __syncthreads();
-  block_exclusive_scan(scanbig, cells, s_part);
-  for (int j = tid; j < cells; j += DT) {
-    int cy = j / xdim, cx = j - cy * xdim;
-    int id = occ[cx * Hc + cy];
-    if (id != OCC_EMPTY) yl[scanbig[j]] = id;
-  }
-  __syncthreads();
   if (nu < 2) {
     if (tid == 0) info->n_tri[side] = 0;
     return;
   }
+  if (tid == 0) info->dt[side][1] = gtime();
 
   // ---- 2. alternating-axis median partition (alternateaxes), level by level -------------
   for (int i = tid; i < nu; i += DT) { seglo[i] = 0; segn[i] = nu; }
@@ -424,73 +551,55 @@ delaunay_kernel(Geo g, Workspace ws) {
     __syncthreads();
   }
   const int* sa = xl;   // Triangle's final sortarray
+  if (tid == 0) { info->dt[side][2] = gtime(); info->dmerge_depth = depth; }
 
-  // ---- 3. merges, deepest level first -----------------------------------------------------
-  Mesh m;
-  m.nb = ws.nb[side] + (size_t)frame * g.cap_t * 3;
-  m.vx = ws.vx[side] + (size_t)frame * g.cap_t * 3;
-  m.x = px; m.y = py;
+  // ---- 3. merges + emission --------------------------------------------------------------------
   int* nodeL = ws.nodeL[side] + (size_t)frame * g.cap_t;
   int* nodeR = ws.nodeR[side] + (size_t)frame * g.cap_t;
-  __syncthreads();
-  for (int d = depth; d >= 0; d--) {
-    const int nodes = 1 << d;
-    for (int k = tid; k < nodes; k += DT) {
-      // locate node (d,k): follow the bits of k from the root
-      int lo = 0, cnt = nu, row = 0;
-      bool exists = true;
-      for (int b = d - 1; b >= 0; b--) {
-        if (cnt <= 3) { exists = false; break; }
-        int dv = cnt >> 1;
-        if ((k >> b) & 1) { lo += dv; row += 2 * dv - 2; cnt -= dv; }
-        else cnt = dv;
-      }
-      if (!exists) continue;
-      Ot fl, fr;
-      if (cnt <= 3) {
-        leaf_case(m, sa + lo, cnt, row, fl, fr);
-      } else {
-        int c0 = (1 << (d + 1)) + 2 * k;
-        fl = dec(nodeL[c0]);
-        Ot il = dec(nodeR[c0]);
-        Ot ir = dec(nodeL[c0 + 1]);
-        fr = dec(nodeR[c0 + 1]);
-        merge_hulls(m, fl, il, ir, fr, d & 1, row + 2 * cnt - 4, row + 2 * cnt - 3);
-      }
-      nodeL[nodes + k] = enc(fl);
-      nodeR[nodes + k] = enc(fr);
-    }
-    __syncthreads();
-  }
-
-  // ---- 4. emit the non-ghost rows in row order (writeelements) ----------------------------
-  const int rows = 2 * nu - 2;
-  for (int t = tid; t < rows; t += DT) {
-    const int* v = m.vx + 3 * t;
-    flag[t] = (v[0] >= 0 && v[1] >= 0 && v[2] >= 0);
-  }
-  __syncthreads();
   int* tri = ws.tri[side] + (size_t)frame * g.cap_t * 3;
-  // flag[] is overwritten by the scan; test the vertices again when writing
-  const int nt = block_exclusive_scan(flag, rows, s_part);
-  for (int t = tid; t < rows; t += DT) {
-    const int* v = m.vx + 3 * t;
-    if (v[0] >= 0 && v[1] >= 0 && v[2] >= 0) {
-      int k = flag[t];
-      tri[3 * k] = v[1];       // org
-      tri[3 * k + 1] = v[2];   // dest
-      tri[3 * k + 2] = v[0];   // apex
-    }
+  int nt;
+  __syncthreads();
+  if (n <= g.dl_smem_max) {
+    MeshS m;
+    m.rows = reinterpret_cast<unsigned short*>(dsm);
+    unsigned* xy = reinterpret_cast<unsigned*>(dsm + (size_t)(2 * SMEM_MAX_POINTS) * 12);
+    for (int i = tid; i < n; i += DT) xy[i] = ((unsigned)px[i] << 16) | (unsigned)py[i];
+    m.xy = xy;
+    __syncthreads();
+    nt = build_and_emit(m, sa, nu, depth, nodeL, nodeR, flag, tri, s_part);
+  } else {
+    MeshG m;
+    m.nb = ws.nb[side] + (size_t)frame * g.cap_t * 3;
+    m.vx = ws.vx[side] + (size_t)frame * g.cap_t * 3;
+    m.x = px; m.y = py;
+    nt = build_and_emit(m, sa, nu, depth, nodeL, nodeR, flag, tri, s_part);
   }
-  if (tid == 0) info->n_tri[side] = nt;
+  if (tid == 0) { info->n_tri[side] = nt; info->dt[side][4] = gtime(); }
 }
 
 }  // namespace
 
-int launch_delaunay(const Geo& g, int B, Workspace& ws, cudaStream_t s) {
-  // occupancy grids start "empty" = 0x7f7f7f7f
-  JN_CUDA_CHECK(cudaMemsetAsync(ws.occ, 0x7f, (size_t)B * 2 * g.W * g.Hc * sizeof(int32_t), s));
-  delaunay_kernel<<<dim3(2, B), DT, 0, s>>>(g, ws);
+// test hook: force the large-point-set paths (occupancy-grid ranking, global-memory tables)
+static int g_sort_max = SORT_MAX, g_smem_max = SMEM_MAX_POINTS;
+extern "C" void jn_debug_delaunay_limits(int sort_max, int smem_max) {
+  g_sort_max = sort_max < 0 ? SORT_MAX : (sort_max < SORT_MAX ? sort_max : SORT_MAX);
+  g_smem_max = smem_max < 0 ? SMEM_MAX_POINTS : (smem_max < SMEM_MAX_POINTS ? smem_max : SMEM_MAX_POINTS);
+}
+
+int launch_delaunay(const Geo& g_in, int B, Workspace& ws, cudaStream_t s) {
+  Geo g = g_in;
+  g.dl_sort_max = g_sort_max;
+  g.dl_smem_max = g_smem_max;
+  static bool attr_set = false;
+  if (!attr_set) {
+    JN_CUDA_CHECK(cudaFuncSetAttribute(delaunay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)DELAUNAY_SMEM));
+    attr_set = true;
+  }
+  // the occupancy grids (only used above SORT_MAX points) start "empty" = 0x7f7f7f7f
+  if (g.cap_s > g.dl_sort_max)
+    JN_CUDA_CHECK(cudaMemsetAsync(ws.occ, 0x7f, (size_t)B * 2 * g.W * g.Hc * sizeof(int32_t), s));
+  delaunay_kernel<<<dim3(2, B), DT, DELAUNAY_SMEM, s>>>(g, ws);
   g_jn_launches += 1;
   return JN_OK;
 }

@@ -69,6 +69,23 @@ def test_full_size_1920x1200_matches_oracle(jn, oracle, synth):
         e.close()
 
 
+def test_delaunay_large_point_set_paths(jn, oracle, synth):
+    """The Delaunay kernel has shared-memory fast paths (bitonic sort, u16 tables) and
+    global-memory paths for large point sets; force the latter and compare again."""
+    W, H, dm = 640, 480, 255
+    I1, I2, _ = synth.synth_pair(W, H, dm, 5)
+    a = oracle.stages(ol.robotics(dm), I1, I2)
+    e = jn.Elas(jn.parameters(jn.ROBOTICS, disp_max=dm))
+    try:
+        for limits in ((0, 0), (-1, 0), (0, -1)):
+            jn.lib().jn_debug_delaunay_limits(*limits)
+            b = e.stages(I1, I2)
+            assert_stages_equal(a, b, ["support", "tri1", "tri2", "planes1", "planes2", "D1", "D2"])
+    finally:
+        jn.lib().jn_debug_delaunay_limits(-1, -1)
+    e.close()
+
+
 def test_process_is_a_drop_in(jn, oracle, synth):
     """Elas::process semantics: same maps, caller-owned buffers, bytes_per_line honoured."""
     W, H, dm = 333, 251, 64
