@@ -140,7 +140,9 @@ static int make_geo(const jn_elas_params& p, const int32_t dims[3], Geo* out) {
   g.Hc = (g.H + step - 1) / step;
   g.gw = (int)ceilf((float)g.W / (float)p.grid_size);
   g.gh = (int)ceilf((float)g.H / (float)p.grid_size);
-  g.gwords = (p.disp_max + 1 + 31) / 32;
+  g.gwords = ((p.disp_max + 1 + 127) / 128) * 4;
+  g.gs_magic = (unsigned)((0x100000000ull + (unsigned)p.grid_size - 1) / (unsigned)p.grid_size);
+  if (p.grid_size >= 32768) { jn_set_error("grid_size too large"); return JN_ERR_ARG; }
   g.cap_s = g.Wc * g.Hc + 8;
   g.cap_t = 2 * g.cap_s;
   // prior table and radius exactly as computeDisparity builds them (elas.cpp:802-806), float math

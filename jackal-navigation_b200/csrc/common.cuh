@@ -34,7 +34,8 @@ struct Geo {
   int W, H, bpl;        // image size, input stride in bytes
   int Wc, Hc;           // candidate lattice (elas.cpp:386-387)
   int gw, gh;           // disparity grid (elas.cpp:90-91)
-  int gwords;           // u32 words per grid cell bit set = ceil((disp_max+1)/32)
+  int gwords;           // u32 words per grid cell bit set, ceil((disp_max+1)/32) rounded up to 4
+  unsigned gs_magic;    // ceil(2^32 / grid_size): x / grid_size == __umulhi(x, gs_magic) for x < 2^16
   int cap_s;            // support point capacity per frame
   int cap_t;            // triangle-table rows per side (2*cap_s)
   int plane_radius;     // elas.cpp:806

@@ -79,7 +79,36 @@ __global__ void raster_kernel(Geo g, Workspace ws) {
 }
 
 constexpr int DENSE_THREADS = 128;
+constexpr unsigned KEY_NONE = 0xFFFFFFFFu;
 
+// One candidate: 16-byte SAD (+ prior), folded into a packed key
+//   (cost + 64) << 13 | class << 12 | d      class 0 = grid candidate, 1 = plane range
+// The reference keeps the FIRST minimum in its evaluation order (grid candidates outside the
+// plane range ascending, then the plane range ascending; strict '<', H7) = the smallest key.
+__device__ __forceinline__ void eval_candidate(unsigned& best, const uint4& a, const uint4* __restrict__ Brow, int u,
+                                               int dir, int d, int prior, unsigned cls, unsigned wm4) {
+  const int uw = u + dir * d;
+  if ((unsigned)(uw - 2) < wm4) {
+    const uint4 b = __ldg(Brow + (unsigned)uw);
+    const int val = (int)sad16(a, b, 0u) + prior;
+    best = min(best, ((unsigned)(val + 64) << 13) | cls | (unsigned)d);
+  }
+}
+
+__device__ __forceinline__ void eval_word(unsigned& best, unsigned bits, int w, int lo, int hi, const uint4& a,
+                                          const uint4* __restrict__ Brow, int u, int dir, unsigned wm4) {
+  if (bits == 0u) return;
+  const int l = lo - 32 * w, h = hi - 32 * w;     // plane range relative to this word
+  if (h >= 0 && l <= 31) bits &= ~((0xFFFFFFFFu << max(l, 0)) & (0xFFFFFFFFu >> (31 - min(h, 31))));
+  while (bits) {
+    const int b = __ffs(bits) - 1;
+    bits &= bits - 1;
+    eval_candidate(best, a, Brow, u, dir, 32 * w + b, 0, 0u, wm4);
+  }
+}
+
+// R = plane radius known at compile time (2: ROBOTICS, 3: MIDDLEBURY), 0 = run-time radius.
+template <int R>
 __global__ void __launch_bounds__(DENSE_THREADS)
 dense_kernel(Geo g, Workspace ws) {
   const int side = blockIdx.z & 1, frame = blockIdx.z >> 1;
@@ -88,53 +117,50 @@ dense_kernel(Geo g, Workspace ws) {
   const int u = blockIdx.x * DENSE_THREADS + threadIdx.x, v = blockIdx.y;
   if (u >= W) return;
   const size_t fpix = (size_t)frame * W * H;
-  const int t = ws.trimap[side][fpix + (size_t)v * W + u];
+  const unsigned pix = (unsigned)(v * W + u);
+  const int vl = max(min(v, H - 3), 2);
+  const uint4* Arow = reinterpret_cast<const uint4*>(ws.desc[side] + fpix * 16) + (unsigned)(vl * W);
+  const uint4* Brow = reinterpret_cast<const uint4*>(ws.desc[side ^ 1] + fpix * 16) + (unsigned)(vl * W);
+  // independent loads first: triangle id, own descriptor, grid cell bit set
+  const int t = __ldg(ws.trimap[side] + fpix + pix);
+  const uint4 a = __ldg(Arow + (unsigned)u);
+  const unsigned gx = __umulhi((unsigned)u, g.gs_magic), gy = __umulhi((unsigned)v, g.gs_magic);
+  const uint4* cell = reinterpret_cast<const uint4*>(
+      ws.gridmask[side] + ((size_t)frame * g.gw * g.gh + gy * g.gw + gx) * g.gwords);
   float out = -10.f;
-  if (t >= 0 && u >= 2 && u < W - 2) {
-    const int vl = max(min(v, H - 3), 2);
-    const uint4* A = reinterpret_cast<const uint4*>(ws.desc[side] + fpix * 16) + (size_t)vl * W;
-    const uint4* Bd = reinterpret_cast<const uint4*>(ws.desc[side ^ 1] + fpix * 16) + (size_t)vl * W;
-    const uint4 a = __ldg(A + u);
-    if ((int)texture16(a) >= g.p.match_texture) {
-      const float* pl = ws.planes[side] + ((size_t)frame * g.cap_t + t) * 6;
-      float pa, pb, pc, pd;
-      if (!side) { pa = pl[0]; pb = pl[1]; pc = pl[2]; pd = pl[3]; }
-      else { pa = pl[3]; pb = pl[4]; pc = pl[5]; pd = pl[0]; }
-      const int d_plane = (int)(pa * (float)u + pb * (float)v + pc);
-      const int r = g.plane_radius;
-      const int lo = max(d_plane - r, 0), hi = min(d_plane + r, g.p.disp_max);
-      const bool valid = (double)fabsf(pa) < 0.7 && (double)fabsf(pd) < 0.7;
-      const int gs = g.p.grid_size;
-      const uint32_t* cell = ws.gridmask[side] +
-                             ((size_t)frame * g.gw * g.gh + (size_t)(v / gs) * g.gw + (u / gs)) * g.gwords;
-      const int dir = side ? 1 : -1;
-      int min_val = 10000, min_d = -1;
-      for (int w = 0; w < g.gwords; w++) {
-        uint32_t bits = __ldg(cell + w);
-        while (bits) {
-          int b = __ffs(bits) - 1;
-          bits &= bits - 1;
-          int d = (w << 5) + b;
-          if (d < lo || d > hi) {
-            int uw = u + dir * d;
-            if (uw >= 2 && uw < W - 2) {
-              int val = (int)sad16(a, __ldg(Bd + uw), 0u);
-              if (val < min_val) { min_val = val; min_d = d; }
-            }
-          }
-        }
-      }
-      for (int d = lo; d <= hi; d++) {
-        int uw = u + dir * d;
-        if (uw >= 2 && uw < W - 2) {
-          int val = (int)sad16(a, __ldg(Bd + uw), 0u) + (valid ? g.P[abs(d - d_plane)] : 0);
-          if (val < min_val) { min_val = val; min_d = d; }
-        }
-      }
-      out = (min_d >= 0) ? (float)min_d : -1.f;
+  if (t >= 0 && u >= 2 && u < W - 2 && (int)texture16(a) >= g.p.match_texture) {
+    const float* pl = ws.planes[side] + ((size_t)frame * g.cap_t + (unsigned)t) * 6;
+    const float pa = __ldg(pl + (side ? 3 : 0)), pb = __ldg(pl + (side ? 4 : 1)), pc = __ldg(pl + (side ? 5 : 2));
+    const float pd = __ldg(pl + (side ? 0 : 3));
+    const int d_plane = (int)(pa * (float)u + pb * (float)v + pc);
+    const int r = R ? R : g.plane_radius;
+    const int lo = max(d_plane - r, 0), hi = min(d_plane + r, g.p.disp_max);
+    // (double)|x| < 0.7  <=>  |x| <= 0.7f  (0.7f is the largest float below 0.7)
+    const bool valid = fabsf(pa) <= 0.7f && fabsf(pd) <= 0.7f;
+    const int dir = side ? 1 : -1;
+    const unsigned wm4 = (unsigned)(W - 4);
+    unsigned best = KEY_NONE;
+    for (int q = 0; q < (g.gwords >> 2); q++) {
+      const uint4 m = __ldg(cell + q);
+      eval_word(best, m.x, 4 * q + 0, lo, hi, a, Brow, u, dir, wm4);
+      eval_word(best, m.y, 4 * q + 1, lo, hi, a, Brow, u, dir, wm4);
+      eval_word(best, m.z, 4 * q + 2, lo, hi, a, Brow, u, dir, wm4);
+      eval_word(best, m.w, 4 * q + 3, lo, hi, a, Brow, u, dir, wm4);
     }
+    if (R) {
+#pragma unroll
+      for (int k = -R; k <= R; k++) {
+        const int d = d_plane + k;
+        const int prior = valid ? g.P[k < 0 ? -k : k] : 0;
+        if (d >= 0 && d <= g.p.disp_max) eval_candidate(best, a, Brow, u, dir, d, prior, 1u << 12, wm4);
+      }
+    } else {
+      for (int d = lo; d <= hi; d++)
+        eval_candidate(best, a, Brow, u, dir, d, valid ? g.P[abs(d - d_plane)] : 0, 1u << 12, wm4);
+    }
+    out = (best != KEY_NONE) ? (float)(best & 0xFFFu) : -1.f;
   }
-  ws.Draw[side][fpix + (size_t)v * W + u] = out;
+  ws.Draw[side][fpix + pix] = out;
 }
 
 }  // namespace
@@ -148,7 +174,10 @@ void launch_raster(const Geo& g, int B, Workspace& ws, cudaStream_t s) {
 }
 
 void launch_dense_match(const Geo& g, int B, Workspace& ws, cudaStream_t s) {
-  dense_kernel<<<dim3((g.W + DENSE_THREADS - 1) / DENSE_THREADS, g.H, 2 * B), DENSE_THREADS, 0, s>>>(g, ws);
+  dim3 grid((g.W + DENSE_THREADS - 1) / DENSE_THREADS, g.H, 2 * B);
+  if (g.plane_radius == 2) dense_kernel<2><<<grid, DENSE_THREADS, 0, s>>>(g, ws);
+  else if (g.plane_radius == 3) dense_kernel<3><<<grid, DENSE_THREADS, 0, s>>>(g, ws);
+  else dense_kernel<0><<<grid, DENSE_THREADS, 0, s>>>(g, ws);
   g_jn_launches += 1;
 }
 
