@@ -57,41 +57,77 @@ __device__ __forceinline__ Best best_merge_warp(Best b) {
   return b;
 }
 
-// One candidate, executed by a full warp.  rowA_* = descriptor rows of the image
-// the pixel lives in, rowB_* = rows of the image searched; dir = -1 (left pixel,
-// search u-d) or +1 (right pixel, search u+d).  Returns the disparity or -1.
-__device__ __forceinline__ int match_candidate(const Geo& g, int u, int dir, const uint4* rowA_t,
-                                               const uint4* rowA_b, const uint4* rowB_t, const uint4* rowB_b,
-                                               const uint4* centre_row, int lane) {
+constexpr int KG = 4;   // candidates matched together by one warp
+
+// KG candidates, executed by a full warp.  rowA_* = descriptor rows of the image the pixels
+// live in, rowB_* = rows of the image searched; dir = -1 (left pixels, search u-d) or +1
+// (right pixels, search u+d); u[k] < 0 = empty slot.  The lanes stride POSITIONS of the
+// searched rows: every lane loads the four searched descriptors of its position once and
+// scores them against all KG candidates (disparity = distance to the candidate), so the
+// shared-memory traffic per candidate drops by KG.  res[k] = disparity or -1.
+__device__ __forceinline__ void match_group(const Geo& g, const int (&u)[KG], int dir, const uint4* rowA_t,
+                                            const uint4* rowA_b, const uint4* rowB_t, const uint4* rowB_b,
+                                            const uint4* centre_row, int lane, int (&res)[KG]) {
   const int W = g.W;
-  if (u < 5 || u > W - 6) return -1;
-  uint4 c = __ldg(centre_row + u);
-  if ((int)texture16(c) < g.p.support_texture) return -1;
-  int dmin = max(g.p.disp_min, 0);
-  int dmax = (dir < 0) ? min(g.p.disp_max, u - 5) : min(g.p.disp_max, W - u - 5);
-  if (dmax - dmin < 10) return -1;
-  const uint4 a0 = rowA_t[u - 2], a1 = rowA_t[u + 2], a2 = rowA_b[u - 2], a3 = rowA_b[u + 2];
-  Best b;
-  b.key = EMPTY_KEY;
-  b.e2 = 32767u;
-  for (int d = dmin + lane; d <= dmax; d += 32) {
-    int uw = u + dir * d;
-    unsigned e = sad16(a0, rowB_t[uw - 2], 0u);
-    e = sad16(a1, rowB_t[uw + 2], e);
-    e = sad16(a2, rowB_b[uw - 2], e);
-    e = sad16(a3, rowB_b[uw + 2], e);
-    best_update(b, e, (unsigned)d);
+  const int dmin = max(g.p.disp_min, 0);
+  uint4 a[KG][4];
+  int dmax[KG];
+  bool ok[KG];
+  Best best[KG];
+  int plo = 0x7fffffff, phi = -0x7fffffff;
+  uint4 c[KG];
+#pragma unroll
+  for (int k = 0; k < KG; k++) {
+    ok[k] = u[k] >= 5 && u[k] <= W - 6;
+    c[k] = ok[k] ? __ldg(centre_row + u[k]) : make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u);
   }
-  b = best_merge_warp(b);
-  float e1 = (float)(b.key >> 16), e2 = (float)b.e2;
-  if (e1 < __fmul_rn(g.p.support_threshold, e2)) return (int)(b.key & 0xFFFFu);
-  return -1;
+#pragma unroll
+  for (int k = 0; k < KG; k++) {
+    dmax[k] = (dir < 0) ? min(g.p.disp_max, u[k] - 5) : min(g.p.disp_max, W - u[k] - 5);
+    ok[k] = ok[k] && (int)texture16(c[k]) >= g.p.support_texture && (dmax[k] - dmin >= 10);
+    best[k].key = EMPTY_KEY;
+    best[k].e2 = 32767u;
+    res[k] = -1;
+    if (ok[k]) {
+      a[k][0] = rowA_t[u[k] - 2]; a[k][1] = rowA_t[u[k] + 2];
+      a[k][2] = rowA_b[u[k] - 2]; a[k][3] = rowA_b[u[k] + 2];
+      int p0 = (dir < 0) ? u[k] - dmax[k] : u[k] + dmin;
+      int p1 = (dir < 0) ? u[k] - dmin : u[k] + dmax[k];
+      plo = min(plo, p0);
+      phi = max(phi, p1);
+    } else {
+      a[k][0] = a[k][1] = a[k][2] = a[k][3] = make_uint4(0, 0, 0, 0);
+    }
+  }
+  if (plo > phi) return;   // no candidate of the group survives the gates
+  for (int p = plo + lane; p <= phi; p += 32) {
+    const uint4 s0 = rowB_t[p - 2], s1 = rowB_t[p + 2], s2 = rowB_b[p - 2], s3 = rowB_b[p + 2];
+#pragma unroll
+    for (int k = 0; k < KG; k++) {
+      const int d = (dir < 0) ? u[k] - p : p - u[k];
+      if (ok[k] && d >= dmin && d <= dmax[k]) {
+        unsigned e = sad16(a[k][0], s0, 0u);
+        e = sad16(a[k][1], s1, e);
+        e = sad16(a[k][2], s2, e);
+        e = sad16(a[k][3], s3, e);
+        best_update(best[k], e, (unsigned)d);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < KG; k++) {
+    if (!ok[k]) continue;
+    Best b = best_merge_warp(best[k]);
+    float e1 = (float)(b.key >> 16), e2 = (float)b.e2;
+    if (e1 < __fmul_rn(g.p.support_threshold, e2)) res[k] = (int)(b.key & 0xFFFFu);
+  }
 }
 
 __global__ void __launch_bounds__(MATCH_THREADS, 1)
 support_match_kernel(Geo g, const uint8_t* __restrict__ desc1, const uint8_t* __restrict__ desc2,
                      int16_t* __restrict__ dcan) {
   extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ int s_nvalid;
   const int W = g.W, H = g.H, Wc = g.Wc;
   const int vc = blockIdx.x, frame = blockIdx.y;
   const int step = g.p.candidate_stepsize;
@@ -107,12 +143,15 @@ support_match_kernel(Geo g, const uint8_t* __restrict__ desc1, const uint8_t* __
   }
 
   const size_t rowbytes = (size_t)W * 16;
+  const size_t wcb = (size_t)((Wc * 4 + 15) & ~15);
   uint4* L_t = reinterpret_cast<uint4*>(smem);
   uint4* L_b = reinterpret_cast<uint4*>(smem + rowbytes);
   uint4* R_t = reinterpret_cast<uint4*>(smem + 2 * rowbytes);
   uint4* R_b = reinterpret_cast<uint4*>(smem + 3 * rowbytes);
-  int* fwd = reinterpret_cast<int*>(smem + 4 * rowbytes);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 4 * rowbytes + (size_t)((Wc * 4 + 15) & ~15));
+  int* fwd = reinterpret_cast<int*>(smem + 4 * rowbytes);             // forward disparity per candidate
+  int* list = reinterpret_cast<int*>(smem + 4 * rowbytes + wcb);      // candidates that passed forward
+  int* resv = reinterpret_cast<int*>(smem + 4 * rowbytes + 2 * wcb);  // final disparity per candidate
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 4 * rowbytes + 3 * wcb);
 
   const uint8_t* d1 = desc1 + (size_t)frame * W * H * 16;
   const uint8_t* d2 = desc2 + (size_t)frame * W * H * 16;
@@ -128,28 +167,64 @@ support_match_kernel(Geo g, const uint8_t* __restrict__ desc1, const uint8_t* __
     bulk_g2s(R_t, d2 + (size_t)(v - 2) * rowbytes, (uint32_t)rowbytes, bar);
     bulk_g2s(R_b, d2 + (size_t)(v + 2) * rowbytes, (uint32_t)rowbytes, bar);
   }
+  for (int uc = tid; uc < Wc; uc += MATCH_THREADS) resv[uc] = (uc == 0) ? 0 : -1;
   mbar_wait(bar, 0);
 
   const uint4* c1 = reinterpret_cast<const uint4*>(d1 + (size_t)v * rowbytes);
   const uint4* c2 = reinterpret_cast<const uint4*>(d2 + (size_t)v * rowbytes);
 
-  // forward: left pixel (u,v) -> right image
-  for (int uc = 1 + warp; uc < Wc; uc += nwarps) {
-    int d = match_candidate(g, uc * step, -1, L_t, L_b, R_t, R_b, c1, lane);
-    if (lane == 0) fwd[uc] = d;
+  // forward: left pixels (u,v) -> right image, KG lattice neighbours per warp pass
+  const int ngroups = (Wc - 1 + KG - 1) / KG;
+  for (int gi = warp; gi < ngroups; gi += nwarps) {
+    int u[KG], r[KG];
+#pragma unroll
+    for (int k = 0; k < KG; k++) {
+      int uc = 1 + gi * KG + k;
+      u[k] = (uc < Wc) ? uc * step : -1;
+    }
+    match_group(g, u, -1, L_t, L_b, R_t, R_b, c1, lane, r);
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < KG; k++) {
+        int uc = 1 + gi * KG + k;
+        if (uc < Wc) fwd[uc] = r[k];
+      }
+    }
   }
   __syncthreads();
-  // backward: right pixel (u-d,v) -> left image, then the cross check (elas.cpp:404-411)
-  for (int uc = 1 + warp; uc < Wc; uc += nwarps) {
-    int d = fwd[uc];
-    int res = -1;
-    if (d >= 0) {
-      int d2 = match_candidate(g, uc * step - d, +1, R_t, R_b, L_t, L_b, c2, lane);
-      if (d2 >= 0 && abs(d - d2) <= g.p.lr_threshold) res = d;
+  // compact the candidates that have a forward match (order preserved: neighbours stay together)
+  if (warp == 0) {
+    int n = 0;
+    for (int base = 1; base < Wc; base += 32) {
+      int uc = base + lane;
+      bool f = uc < Wc && fwd[uc] >= 0;
+      unsigned m = __ballot_sync(0xffffffffu, f);
+      if (f) list[n + __popc(m & ((1u << lane) - 1))] = uc;
+      n += __popc(m);
     }
-    if (lane == 0) out[uc] = (int16_t)res;
+    if (lane == 0) s_nvalid = n;
   }
-  if (tid == 0) out[0] = 0;
+  __syncthreads();
+  // backward: right pixels (u-d,v) -> left image, then the cross check (elas.cpp:404-411)
+  const int nvalid = s_nvalid;
+  for (int gi = warp; gi * KG < nvalid; gi += nwarps) {
+    int u[KG], r[KG], ucs[KG], df[KG];
+#pragma unroll
+    for (int k = 0; k < KG; k++) {
+      int i = gi * KG + k;
+      ucs[k] = (i < nvalid) ? list[i] : -1;
+      df[k] = (ucs[k] >= 0) ? fwd[ucs[k]] : 0;
+      u[k] = (ucs[k] >= 0) ? ucs[k] * step - df[k] : -1;
+    }
+    match_group(g, u, +1, R_t, R_b, L_t, L_b, c2, lane, r);
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < KG; k++)
+        if (ucs[k] >= 0 && r[k] >= 0 && abs(df[k] - r[k]) <= g.p.lr_threshold) resv[ucs[k]] = df[k];
+    }
+  }
+  __syncthreads();
+  for (int uc = tid; uc < Wc; uc += MATCH_THREADS) out[uc] = (int16_t)resv[uc];
 }
 
 // c0(p) = number of lattice points q in the (2r+1)^2 window (p included) that are
@@ -315,15 +390,15 @@ support_filter_kernel(Geo g, const int16_t* __restrict__ dcan_all, int32_t* __re
 }  // namespace
 
 int launch_support(const Geo& g, int B, Workspace& ws, cudaStream_t s) {
-  size_t smem = (size_t)4 * g.W * 16 + ((g.Wc * 4 + 15) & ~15) + 16;
-  if (smem > 227 * 1024 || g.Wc > 2048) {
+  size_t smem = (size_t)4 * g.W * 16 + 3 * (size_t)((g.Wc * 4 + 15) & ~15) + 16;
+  if (smem > 226 * 1024 || g.Wc > 2048) {   // 227 KB per CTA minus the static shared memory
     jn_set_error("image width %d too large for the shared-memory support matcher", g.W);
     return JN_ERR_UNSUPPORTED;
   }
   static bool attr_set = false;
   if (!attr_set) {
     JN_CUDA_CHECK(cudaFuncSetAttribute(support_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       227 * 1024));
+                                       226 * 1024));
     attr_set = true;
   }
   support_match_kernel<<<dim3(g.Hc, B), MATCH_THREADS, smem, s>>>(g, ws.desc[0], ws.desc[1], ws.dcan);
