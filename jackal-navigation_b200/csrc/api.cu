@@ -36,8 +36,14 @@ struct jn_elas {
   jn_elas_params p;
   int device;
   Geo g;            // geometry the workspace was built for
-  Workspace ws;
+  Workspace ws;     // frame slots for a whole batch (first half-batch in split mode)
   void* arena;      // one cudaMalloc
+  Workspace ws2;    // frame slots of the second half-batch (split mode)
+  void* arena2;
+  int split;        // 1: run the two halves of a batch on two streams so that latency-bound
+                    // kernels of one half overlap the bandwidth-bound kernels of the other
+  cudaStream_t aux;
+  cudaEvent_t ev_fork, ev_join;
   // single-frame staging for the host-pointer entry point
   uint8_t* dI[2];
   float* dD[2];
@@ -101,13 +107,17 @@ extern "C" jn_elas* jn_elas_create(const jn_elas_params* p, int device) {
   memset(e, 0, sizeof(*e));
   e->p = *p;
   e->device = device;
+  const char* sp = getenv("JN_ELAS_SPLIT");
+  e->split = sp ? atoi(sp) : 1;
   return e;
 }
 
 static void free_workspace(jn_elas* e) {
   if (e->arena) cudaFree(e->arena);
-  e->arena = nullptr;
+  if (e->arena2) cudaFree(e->arena2);
+  e->arena = e->arena2 = nullptr;
   memset(&e->ws, 0, sizeof(e->ws));
+  memset(&e->ws2, 0, sizeof(e->ws2));
 }
 
 extern "C" void jn_elas_destroy(jn_elas* e) {
@@ -118,6 +128,7 @@ extern "C" void jn_elas_destroy(jn_elas* e) {
   cudaFree(e->dStatus);
   if (e->ev[0])
     for (int i = 0; i <= JN_PROFILE_STAGES; i++) cudaEventDestroy(e->ev[i]);
+  if (e->aux) { cudaStreamDestroy(e->aux); cudaEventDestroy(e->ev_fork); cudaEventDestroy(e->ev_join); }
   delete e;
 }
 
@@ -209,7 +220,8 @@ static int ensure_workspace(jn_elas* e, const int32_t dims[3], int B) {
   int rc = make_geo(e->p, dims, &g);
   if (rc) return rc;
   JN_CUDA_CHECK(cudaSetDevice(e->device));
-  if (e->arena && e->g.W == g.W && e->g.H == g.H && e->ws.B >= B) {
+  const int B2 = (e->split && B >= 2) ? B / 2 : 0;
+  if (e->arena && e->g.W == g.W && e->g.H == g.H && e->ws.B >= B && e->ws2.B >= B2) {
     e->g = g;  // stride may differ between calls
     return JN_OK;
   }
@@ -220,34 +232,63 @@ static int ensure_workspace(jn_elas* e, const int32_t dims[3], int B) {
   JN_CUDA_CHECK(cudaMalloc(&e->arena, probe.bytes));
   JN_CUDA_CHECK(cudaMemset(e->arena, 0, probe.bytes));
   layout(g, B, e->ws, (char*)e->arena);
+  if (B2 > 0) {
+    layout(g, B2, probe, nullptr);
+    JN_CUDA_CHECK(cudaMalloc(&e->arena2, probe.bytes));
+    JN_CUDA_CHECK(cudaMemset(e->arena2, 0, probe.bytes));
+    layout(g, B2, e->ws2, (char*)e->arena2);
+    if (!e->aux) {
+      JN_CUDA_CHECK(cudaStreamCreateWithFlags(&e->aux, cudaStreamNonBlocking));
+      JN_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+      JN_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
+    }
+  }
   e->g = g;
   return JN_OK;
 }
 
-// Elas::process for B frames (elas.cpp:57-140), everything enqueued on one stream.
+// One stage of Elas::process (elas.cpp:57-140) for the B frames of one workspace.
+static int run_stage(int stage, const Geo& g, int B, Workspace& ws, const uint8_t* I1, const uint8_t* I2, float* D1,
+                     float* D2, int32_t* status, cudaStream_t s) {
+  switch (stage) {
+    case 0: launch_descriptor(g, B, I1, I2, ws, s); return JN_OK;
+    case 1: return launch_support(g, B, ws, s);
+    case 2: return launch_delaunay(g, B, ws, s);
+    case 3: launch_planes_grid(g, B, ws, s); return JN_OK;
+    case 4: launch_raster(g, B, ws, s); return JN_OK;
+    case 5: launch_dense_match(g, B, ws, s); return JN_OK;
+    default: launch_post(g, B, ws, D1, D2, status, s); return JN_OK;
+  }
+}
+
+// Elas::process for B frames.  Single stream: everything on `s`.  Split mode: frames
+// [0,B-B/2) on `s` with e->ws and frames [B-B/2,B) on the auxiliary stream with e->ws2, stage
+// launches interleaved; the auxiliary stream forks from and joins back into `s`.
 static int run_pipeline(jn_elas* e, int B, const uint8_t* I1, const uint8_t* I2, float* D1, float* D2,
                         int32_t* status, cudaStream_t s) {
   const Geo& g = e->g;
-  Workspace& ws = e->ws;
   const bool prof = e->profile != 0;
-  int k = 0;
-  if (prof) cudaEventRecord(e->ev[k++], s);
-  launch_descriptor(g, B, I1, I2, ws, s);
-  if (prof) cudaEventRecord(e->ev[k++], s);
-  int rc = launch_support(g, B, ws, s);
-  if (rc) return rc;
-  if (prof) cudaEventRecord(e->ev[k++], s);
-  rc = launch_delaunay(g, B, ws, s);
-  if (rc) return rc;
-  if (prof) cudaEventRecord(e->ev[k++], s);
-  launch_planes_grid(g, B, ws, s);
-  if (prof) cudaEventRecord(e->ev[k++], s);
-  launch_raster(g, B, ws, s);
-  if (prof) cudaEventRecord(e->ev[k++], s);
-  launch_dense_match(g, B, ws, s);
-  if (prof) cudaEventRecord(e->ev[k++], s);
-  launch_post(g, B, ws, D1, D2, status, s);
-  if (prof) cudaEventRecord(e->ev[k++], s);
+  const int Bb = (e->split && !prof && B >= 2 && e->ws2.B >= B / 2) ? B / 2 : 0, Ba = B - Bb;
+  const size_t n = (size_t)g.W * g.H, ibytes = (size_t)g.bpl * g.H;
+  if (Bb) {
+    JN_CUDA_CHECK(cudaEventRecord(e->ev_fork, s));
+    JN_CUDA_CHECK(cudaStreamWaitEvent(e->aux, e->ev_fork, 0));
+  }
+  for (int stage = 0; stage < JN_PROFILE_STAGES; stage++) {
+    if (prof) cudaEventRecord(e->ev[stage], s);
+    int rc = run_stage(stage, g, Ba, e->ws, I1, I2, D1, D2, status, s);
+    if (rc) return rc;
+    if (Bb) {
+      rc = run_stage(stage, g, Bb, e->ws2, I1 + Ba * ibytes, I2 + Ba * ibytes, D1 + Ba * n, D2 ? D2 + Ba * n : nullptr,
+                     status ? status + Ba : nullptr, e->aux);
+      if (rc) return rc;
+    }
+  }
+  if (prof) cudaEventRecord(e->ev[JN_PROFILE_STAGES], s);
+  if (Bb) {
+    JN_CUDA_CHECK(cudaEventRecord(e->ev_join, e->aux));
+    JN_CUDA_CHECK(cudaStreamWaitEvent(s, e->ev_join, 0));
+  }
   JN_CUDA_CHECK(cudaGetLastError());
   return JN_OK;
 }
