@@ -77,12 +77,22 @@ __global__ void __launch_bounds__(ROW_THREADS) seg_rows_kernel(Geo g, Workspace 
     __syncthreads();
   }
   int cur = (tid == 0) ? -1 : s_part[tid - 1];
+  // run lengths: runlen[run start] += pixels of the run seen by this thread (runlen is zeroed)
+  int* runlen = ws.runlen + base;
+  int acc = 0, acc_run = -1;
   for (int u = lo; u < hi; u++) {
     float d = D[u];
     if (d < 0) { label[u] = -1; continue; }
     if (u == 0 || !(D[u - 1] >= 0) || fabsf(d - D[u - 1]) > thr) cur = u;
     label[u] = v * W + cur;
+    if (cur != acc_run) {
+      if (acc) atomicAdd(runlen + acc_run, acc);
+      acc_run = cur;
+      acc = 0;
+    }
+    acc++;
   }
+  if (acc) atomicAdd(runlen + acc_run, acc);
 }
 
 __device__ __forceinline__ int uf_find(int* label, int x) {
@@ -131,40 +141,45 @@ __global__ void seg_merge_kernel(Geo g, Workspace ws, int side) {
   }
 }
 
+// Only the first pixel of every horizontal run walks to its root (runs, not pixels, are the
+// union-find elements); it adds the run length to the root's size and leaves label[start] = root.
 __global__ void seg_count_kernel(Geo g, Workspace ws) {
   const int frame = blockIdx.z;
   if (ws.info[frame].status != JN_OK) return;
   const int W = g.W, H = g.H;
   const int u = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y;
+  if (u >= W) return;
   const size_t fp = (size_t)frame * W * H;
+  const int i = v * W + u;
+  const int len = ws.runlen[fp + i];
+  if (len == 0) return;                 // not a run start
   int* label = ws.label + fp;
-  int* size = ws.segsize + fp;
-  int root = -1;
-  if (u < W) {
-    const int i = v * W + u;
-    if (label[i] >= 0) {
-      // read-only walk: a path-halving store from another thread could land after this
-      // thread's `label[i] = root` and leave a non-root ancestor there
-      int x = i, p = __ldcg(label + x);
-      while (p != x) { x = p; p = __ldcg(label + x); }
-      root = x;
-      label[i] = root;
-    }
+  // A component's root is its smallest pixel index and labels only decrease towards it, so
+  // compressing with atomicMin can never replace a root by a larger ancestor.
+  int x = i, p = __ldcg(label + x);
+  while (p != x) {
+    int gp = __ldcg(label + p);
+    if (gp != p) atomicMin(label + x, gp);
+    x = p;
+    p = gp;
   }
-  // warp-aggregated count: one atomic per distinct root per warp
-  unsigned peers = __match_any_sync(0xffffffffu, root);
-  if (root >= 0 && (int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&size[root], __popc(peers));
+  atomicMin(label + i, x);
+  atomicAdd(ws.segsize + fp + x, len);
 }
 
+// label[i] is i's run start or one of its ancestors (always a run start), and after
+// seg_count_kernel every run start points straight at its root: two hops at most.
 __global__ void seg_apply_kernel(Geo g, Workspace ws, int side) {
   const int frame = blockIdx.z;
   if (ws.info[frame].status != JN_OK) return;
   const int W = g.W, H = g.H;
   const int u = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y;
   if (u >= W) return;
-  const size_t a = (size_t)frame * W * H + (size_t)v * W + u;
+  const size_t fp = (size_t)frame * W * H, a = fp + (size_t)v * W + u;
   int l = ws.label[a];
-  if (l >= 0 && ws.segsize[(size_t)frame * W * H + l] < g.p.speckle_size) ws.Dlr[side][a] = -10.f;
+  if (l < 0) return;
+  const int root = ws.label[fp + l];
+  if (ws.segsize[fp + root] < g.p.speckle_size) ws.Dlr[side][a] = -10.f;
 }
 
 // ------------------------------------------------------------ gap interpolation
@@ -213,6 +228,42 @@ __global__ void __launch_bounds__(ROW_THREADS) gap_rows_kernel(Geo g, Workspace 
       if (next >= W && last_all >= 0 && u - last_all <= gap) D[u] = s_row[last_all];
     }
   }
+}
+
+// Gap widths up to SMALL_GAP: one thread per pixel, out of place.  An invalid pixel looks for
+// the nearest valid pixel on both sides along the line; the run it sits in is filled iff both
+// exist and the run is at most `gap` long (elas.cpp:1137-1155).  Valid pixels never change in a
+// pass, so reading the unmodified input is exactly the reference's sequential result.
+constexpr int SMALL_GAP = 8;
+
+template <bool ROWS>
+__global__ void gap_small_kernel(Geo g, Workspace ws, const float* __restrict__ in, float* __restrict__ out) {
+  const int frame = blockIdx.z;
+  if (ws.info[frame].status != JN_OK) return;
+  const int W = g.W, H = g.H, gap = g.p.ipol_gap_width;
+  const int u = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y;
+  if (u >= W) return;
+  const size_t fp = (size_t)frame * W * H;
+  const float* D = in + fp;
+  const int i = v * W + u;
+  float d = D[i];
+  if (d < 0) {
+    const int pos = ROWS ? u : v, len = ROWS ? W : H, stride = ROWS ? 1 : W;
+    int l = 0, r = 0;
+    float dl = -1.f, dr = -1.f;
+    for (int k = 1; k <= gap && pos - k >= 0; k++) {
+      float t = D[i - k * stride];
+      if (t >= 0) { l = k; dl = t; break; }
+    }
+    if (l > 0) {
+      for (int k = 1; k <= gap + 1 - l && pos + k < len; k++) {
+        float t = D[i + k * stride];
+        if (t >= 0) { r = k; dr = t; break; }
+      }
+      if (r > 0) d = ipol(dl, dr);   // run length l + r - 1 <= gap
+    }
+  }
+  out[fp + i] = d;
 }
 
 __global__ void gap_cols_kernel(Geo g, Workspace ws, int side) {
@@ -406,6 +457,7 @@ void post_lr(const Geo& g, int B, Workspace& ws, cudaStream_t s) {
 void post_segments(const Geo& g, int B, Workspace& ws, int side, cudaStream_t s) {
   dim3 pg((g.W + 255) / 256, g.H, B);
   cudaMemsetAsync(ws.segsize, 0, (size_t)B * g.W * g.H * sizeof(int32_t), s);
+  cudaMemsetAsync(ws.runlen, 0, (size_t)B * g.W * g.H * sizeof(int32_t), s);
   seg_rows_kernel<<<dim3(g.H, B), ROW_THREADS, 0, s>>>(g, ws, side);
   seg_merge_kernel<<<pg, 256, 0, s>>>(g, ws, side);
   seg_count_kernel<<<pg, 256, 0, s>>>(g, ws);
@@ -414,8 +466,14 @@ void post_segments(const Geo& g, int B, Workspace& ws, int side, cudaStream_t s)
 }
 
 void post_gap(const Geo& g, int B, Workspace& ws, int side, cudaStream_t s) {
-  gap_rows_kernel<<<dim3(g.H, B), ROW_THREADS, g.W * sizeof(float), s>>>(g, ws, side);
-  gap_cols_kernel<<<dim3((g.W + 63) / 64, B), 64, 0, s>>>(g, ws, side);
+  if (g.p.ipol_gap_width <= SMALL_GAP && !g.p.add_corners) {
+    dim3 pg((g.W + 255) / 256, g.H, B);
+    gap_small_kernel<true><<<pg, 256, 0, s>>>(g, ws, ws.Dlr[side], ws.Dtmp[side]);
+    gap_small_kernel<false><<<pg, 256, 0, s>>>(g, ws, ws.Dtmp[side], ws.Dlr[side]);
+  } else {
+    gap_rows_kernel<<<dim3(g.H, B), ROW_THREADS, g.W * sizeof(float), s>>>(g, ws, side);
+    gap_cols_kernel<<<dim3((g.W + 63) / 64, B), 64, 0, s>>>(g, ws, side);
+  }
   g_jn_launches += 2;
 }
 
