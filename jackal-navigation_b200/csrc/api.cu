@@ -162,6 +162,8 @@ static int make_geo(const jn_elas_params& p, const int32_t dims[3], Geo* out) {
   if (g.plane_radius > 7) { jn_set_error("plane radius %d > 7 not supported", g.plane_radius); return JN_ERR_UNSUPPORTED; }
   for (int dd = 0; dd <= g.plane_radius; dd++)
     g.P[dd] = (int32_t)((-logf(p.gamma + expf(-dd * dd / two_sigma_squared)) + logf(p.gamma)) / p.beta);
+  for (int dd = 0; dd <= g.plane_radius; dd++)
+    if (g.P[dd] < -2000 || g.P[dd] > 1900) { jn_set_error("prior table out of the packed-key range"); return JN_ERR_UNSUPPORTED; }
   *out = g;
   return JN_OK;
 }

@@ -79,31 +79,35 @@ __global__ void raster_kernel(Geo g, Workspace ws) {
 }
 
 constexpr int DENSE_THREADS = 128;
+constexpr int DENSE_ROWS = 4;              // image rows per thread (amortises the per-thread setup)
 constexpr unsigned KEY_NONE = 0xFFFFFFFFu;
 
 // One candidate: 16-byte SAD (+ prior), folded into a packed key
-//   (cost + 64) << 13 | class << 12 | d      class 0 = grid candidate, 1 = plane range
+//   (cost + 2048) << 13 | class << 12 | d      class 0 = grid candidate, 1 = plane range
 // The reference keeps the FIRST minimum in its evaluation order (grid candidates outside the
 // plane range ascending, then the plane range ascending; strict '<', H7) = the smallest key.
-__device__ __forceinline__ void eval_candidate(unsigned& best, const uint4& a, const uint4* __restrict__ Brow, int u,
-                                               int dir, int d, int prior, unsigned cls, unsigned wm4) {
+// Bf = descriptors of the searched image (frame base), rowoff = first pixel of the row:
+// 32-bit index arithmetic, one IMAD.WIDE per address.
+__device__ __forceinline__ void eval_candidate(unsigned& best, const uint4& a, const uint4* __restrict__ Bf,
+                                               unsigned rowoff, int u, int dir, int d, unsigned addend,
+                                               unsigned wm4) {
   const int uw = u + dir * d;
   if ((unsigned)(uw - 2) < wm4) {
-    const uint4 b = __ldg(Brow + (unsigned)uw);
-    const int val = (int)sad16(a, b, 0u) + prior;
-    best = min(best, ((unsigned)(val + 64) << 13) | cls | (unsigned)d);
+    const uint4 b = __ldg(Bf + (rowoff + (unsigned)uw));
+    best = min(best, sad16(a, b, 0u) * 8192u + (addend + (unsigned)d));
   }
 }
 
 __device__ __forceinline__ void eval_word(unsigned& best, unsigned bits, int w, int lo, int hi, const uint4& a,
-                                          const uint4* __restrict__ Brow, int u, int dir, unsigned wm4) {
+                                          const uint4* __restrict__ Bf, unsigned rowoff, int u, int dir,
+                                          unsigned wm4) {
   if (bits == 0u) return;
   const int l = lo - 32 * w, h = hi - 32 * w;     // plane range relative to this word
   if (h >= 0 && l <= 31) bits &= ~((0xFFFFFFFFu << max(l, 0)) & (0xFFFFFFFFu >> (31 - min(h, 31))));
   while (bits) {
     const int b = __ffs(bits) - 1;
     bits &= bits - 1;
-    eval_candidate(best, a, Brow, u, dir, 32 * w + b, 0, 0u, wm4);
+    eval_candidate(best, a, Bf, rowoff, u, dir, 32 * w + b, 2048u << 13, wm4);
   }
 }
 
@@ -114,53 +118,71 @@ dense_kernel(Geo g, Workspace ws) {
   const int side = blockIdx.z & 1, frame = blockIdx.z >> 1;
   if (ws.info[frame].status != JN_OK) return;
   const int W = g.W, H = g.H;
-  const int u = blockIdx.x * DENSE_THREADS + threadIdx.x, v = blockIdx.y;
+  const int u = blockIdx.x * DENSE_THREADS + threadIdx.x;
   if (u >= W) return;
+  // frame-level bases once per thread; everything below is 32-bit offsets from them
   const size_t fpix = (size_t)frame * W * H;
-  const unsigned pix = (unsigned)(v * W + u);
-  const int vl = max(min(v, H - 3), 2);
-  const uint4* Arow = reinterpret_cast<const uint4*>(ws.desc[side] + fpix * 16) + (unsigned)(vl * W);
-  const uint4* Brow = reinterpret_cast<const uint4*>(ws.desc[side ^ 1] + fpix * 16) + (unsigned)(vl * W);
-  // independent loads first: triangle id, own descriptor, grid cell bit set
-  const int t = __ldg(ws.trimap[side] + fpix + pix);
-  const uint4 a = __ldg(Arow + (unsigned)u);
-  const unsigned gx = __umulhi((unsigned)u, g.gs_magic), gy = __umulhi((unsigned)v, g.gs_magic);
-  const uint4* cell = reinterpret_cast<const uint4*>(
-      ws.gridmask[side] + ((size_t)frame * g.gw * g.gh + gy * g.gw + gx) * g.gwords);
-  float out = -10.f;
-  if (t >= 0 && u >= 2 && u < W - 2 && (int)texture16(a) >= g.p.match_texture) {
-    const float* pl = ws.planes[side] + ((size_t)frame * g.cap_t + (unsigned)t) * 6;
-    const float pa = __ldg(pl + (side ? 3 : 0)), pb = __ldg(pl + (side ? 4 : 1)), pc = __ldg(pl + (side ? 5 : 2));
-    const float pd = __ldg(pl + (side ? 0 : 3));
-    const int d_plane = (int)(pa * (float)u + pb * (float)v + pc);
-    const int r = R ? R : g.plane_radius;
-    const int lo = max(d_plane - r, 0), hi = min(d_plane + r, g.p.disp_max);
-    // (double)|x| < 0.7  <=>  |x| <= 0.7f  (0.7f is the largest float below 0.7)
-    const bool valid = fabsf(pa) <= 0.7f && fabsf(pd) <= 0.7f;
-    const int dir = side ? 1 : -1;
-    const unsigned wm4 = (unsigned)(W - 4);
-    unsigned best = KEY_NONE;
-    for (int q = 0; q < (g.gwords >> 2); q++) {
-      const uint4 m = __ldg(cell + q);
-      eval_word(best, m.x, 4 * q + 0, lo, hi, a, Brow, u, dir, wm4);
-      eval_word(best, m.y, 4 * q + 1, lo, hi, a, Brow, u, dir, wm4);
-      eval_word(best, m.z, 4 * q + 2, lo, hi, a, Brow, u, dir, wm4);
-      eval_word(best, m.w, 4 * q + 3, lo, hi, a, Brow, u, dir, wm4);
-    }
-    if (R) {
-#pragma unroll
-      for (int k = -R; k <= R; k++) {
-        const int d = d_plane + k;
-        const int prior = valid ? g.P[k < 0 ? -k : k] : 0;
-        if (d >= 0 && d <= g.p.disp_max) eval_candidate(best, a, Brow, u, dir, d, prior, 1u << 12, wm4);
+  const uint4* __restrict__ Af = reinterpret_cast<const uint4*>(ws.desc[side] + fpix * 16);
+  const uint4* __restrict__ Bf = reinterpret_cast<const uint4*>(ws.desc[side ^ 1] + fpix * 16);
+  const int* __restrict__ tmap = ws.trimap[side] + fpix;
+  float* __restrict__ outp = ws.Draw[side] + fpix;
+  const float* __restrict__ planes = ws.planes[side] + (size_t)frame * g.cap_t * 6;
+  const uint32_t* __restrict__ masks = ws.gridmask[side] + (size_t)frame * g.gw * g.gh * g.gwords;
+  const unsigned gx = __umulhi((unsigned)u, g.gs_magic);
+  const int dir = side ? 1 : -1;
+  const unsigned wm4 = (unsigned)(W - 4);
+  const bool u_ok = u >= 2 && u < W - 2;
+  const int po = side ? 3 : 0;              // this image's plane, the other image's slope
+  const int P0 = g.P[0], P1 = g.P[1], P2 = g.P[2], P3 = g.P[3];
+  const int v0 = blockIdx.y * DENSE_ROWS;
+#pragma unroll 1
+  for (int v = v0; v < min(v0 + DENSE_ROWS, H); v++) {
+    const unsigned pix = (unsigned)(v * W + u);
+    const unsigned rowoff = (unsigned)(max(min(v, H - 3), 2) * W);
+    // independent loads first: triangle id, own descriptor
+    const int t = __ldg(tmap + pix);
+    const uint4 a = __ldg(Af + (rowoff + (unsigned)u));
+    float out = -10.f;
+    if (t >= 0 && u_ok && (int)texture16(a) >= g.p.match_texture) {
+      const float* pl = planes + (unsigned)t * 6u;
+      const float pa = __ldg(pl + po), pb = __ldg(pl + po + 1), pc = __ldg(pl + po + 2), pd = __ldg(pl + 3 - po);
+      const unsigned gy = __umulhi((unsigned)v, g.gs_magic);
+      const uint4* cell = reinterpret_cast<const uint4*>(masks + (gy * (unsigned)g.gw + gx) * (unsigned)g.gwords);
+      const int d_plane = (int)(pa * (float)u + pb * (float)v + pc);
+      const int r = R ? R : g.plane_radius;
+      const int lo = max(d_plane - r, 0), hi = min(d_plane + r, g.p.disp_max);
+      // (double)|x| < 0.7  <=>  |x| <= 0.7f  (0.7f is the largest float below 0.7)
+      const bool valid = fabsf(pa) <= 0.7f && fabsf(pd) <= 0.7f;
+      unsigned best = KEY_NONE;
+      for (int q = 0; q < (g.gwords >> 2); q++) {
+        const uint4 m = __ldg(cell + q);
+        eval_word(best, m.x, 4 * q + 0, lo, hi, a, Bf, rowoff, u, dir, wm4);
+        eval_word(best, m.y, 4 * q + 1, lo, hi, a, Bf, rowoff, u, dir, wm4);
+        eval_word(best, m.z, 4 * q + 2, lo, hi, a, Bf, rowoff, u, dir, wm4);
+        eval_word(best, m.w, 4 * q + 3, lo, hi, a, Bf, rowoff, u, dir, wm4);
       }
-    } else {
-      for (int d = lo; d <= hi; d++)
-        eval_candidate(best, a, Brow, u, dir, d, valid ? g.P[abs(d - d_plane)] : 0, 1u << 12, wm4);
+      if (R) {
+        // key addend per |k|: (2048 + prior) << 13 | class bit
+        const unsigned a0 = ((unsigned)(2048 + (valid ? P0 : 0)) << 13) | (1u << 12);
+        const unsigned a1 = ((unsigned)(2048 + (valid ? P1 : 0)) << 13) | (1u << 12);
+        const unsigned a2 = ((unsigned)(2048 + (valid ? P2 : 0)) << 13) | (1u << 12);
+        const unsigned a3 = ((unsigned)(2048 + (valid ? P3 : 0)) << 13) | (1u << 12);
+#pragma unroll
+        for (int k = -R; k <= R; k++) {
+          const int d = d_plane + k;
+          const int ak = k < 0 ? -k : k;
+          const unsigned add = ak == 0 ? a0 : (ak == 1 ? a1 : (ak == 2 ? a2 : a3));
+          if (d >= 0 && d <= g.p.disp_max) eval_candidate(best, a, Bf, rowoff, u, dir, d, add, wm4);
+        }
+      } else {
+        for (int d = lo; d <= hi; d++)
+          eval_candidate(best, a, Bf, rowoff, u, dir, d,
+                         ((unsigned)(2048 + (valid ? g.P[abs(d - d_plane)] : 0)) << 13) | (1u << 12), wm4);
+      }
+      out = (best != KEY_NONE) ? (float)(best & 0xFFFu) : -1.f;
     }
-    out = (best != KEY_NONE) ? (float)(best & 0xFFFu) : -1.f;
+    outp[pix] = out;
   }
-  ws.Draw[side][fpix + pix] = out;
 }
 
 }  // namespace
@@ -174,7 +196,7 @@ void launch_raster(const Geo& g, int B, Workspace& ws, cudaStream_t s) {
 }
 
 void launch_dense_match(const Geo& g, int B, Workspace& ws, cudaStream_t s) {
-  dim3 grid((g.W + DENSE_THREADS - 1) / DENSE_THREADS, g.H, 2 * B);
+  dim3 grid((g.W + DENSE_THREADS - 1) / DENSE_THREADS, (g.H + DENSE_ROWS - 1) / DENSE_ROWS, 2 * B);
   if (g.plane_radius == 2) dense_kernel<2><<<grid, DENSE_THREADS, 0, s>>>(g, ws);
   else if (g.plane_radius == 3) dense_kernel<3><<<grid, DENSE_THREADS, 0, s>>>(g, ws);
   else dense_kernel<0><<<grid, DENSE_THREADS, 0, s>>>(g, ws);
