@@ -67,6 +67,10 @@ int jn_elas_frameinfo(jn_elas* e, int frame, void* out, int bytes);
  * 0,0 forces the occupancy-grid ranking and the global-memory triangle tables. */
 void jn_debug_delaunay_limits(int sort_max, int smem_max);
 
+/* Test hook: grid cells with more than `limit` candidates are decoded from the bit set by the
+ * dense matcher instead of the compact list (-1 = default 16; 0 = always the bit set). */
+void jn_debug_grid_list_limit(int limit);
+
 /* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
 long long jn_launch_count(void);
 

@@ -205,6 +205,7 @@ static void layout(const Geo& g, int B, Workspace& ws, char* base) {
     carve(cur, ws.planes[k], b * g.cap_t * 6);
     carve(cur, ws.gridtmp[k], b * gcw);
     carve(cur, ws.gridmask[k], b * gcw);
+    carve(cur, ws.gridlist[k], b * (size_t)g.gw * g.gh * GRID_LIST);
     carve(cur, ws.trimap[k], b * n);
     carve(cur, ws.Draw[k], b * n);
     carve(cur, ws.Dlr[k], b * n);

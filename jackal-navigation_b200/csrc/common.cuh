@@ -29,6 +29,8 @@
 void jn_set_error(const char* fmt, ...);
 extern long long g_jn_launches;   // kernels launched by this library (bench.py gpu_launches)
 
+constexpr int GRID_LIST = 16;    // entries of the compact per-cell candidate list
+
 // Per-call geometry + parameters, passed to kernels by value.
 struct Geo {
   int W, H, bpl;        // image size, input stride in bytes
@@ -40,6 +42,7 @@ struct Geo {
   int cap_t;            // triangle-table rows per side (2*cap_s)
   int plane_radius;     // elas.cpp:806
   int P[8];             // prior table entries 0..plane_radius (elas.cpp:802-805)
+  int grid_list_limit;  // cells with more candidates than this use the bit-set path (<= GRID_LIST)
   int dl_sort_max, dl_smem_max;   // Delaunay: point-count limits of the shared-memory paths
   jn_elas_params p;
 };
@@ -82,6 +85,7 @@ struct Workspace {
   float*   planes[2];          // B * cap_t*6
   uint32_t* gridtmp[2];        // B * gh*gw*gwords
   uint32_t* gridmask[2];
+  uint16_t* gridlist[2];       // B * gh*gw*GRID_LIST  sorted candidate list per cell (0xFFFF padded)
   int32_t* trimap[2];          // B * H*W
   float* Draw[2];              // B * H*W
   float* Dlr[2];

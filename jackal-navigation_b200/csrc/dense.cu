@@ -128,6 +128,7 @@ dense_kernel(Geo g, Workspace ws) {
   float* __restrict__ outp = ws.Draw[side] + fpix;
   const float* __restrict__ planes = ws.planes[side] + (size_t)frame * g.cap_t * 6;
   const uint32_t* __restrict__ masks = ws.gridmask[side] + (size_t)frame * g.gw * g.gh * g.gwords;
+  const uint16_t* __restrict__ lists = ws.gridlist[side] + (size_t)frame * g.gw * g.gh * GRID_LIST;
   const unsigned gx = __umulhi((unsigned)u, g.gs_magic);
   const int dir = side ? 1 : -1;
   const unsigned wm4 = (unsigned)(W - 4);
@@ -147,19 +148,41 @@ dense_kernel(Geo g, Workspace ws) {
       const float* pl = planes + (unsigned)t * 6u;
       const float pa = __ldg(pl + po), pb = __ldg(pl + po + 1), pc = __ldg(pl + po + 2), pd = __ldg(pl + 3 - po);
       const unsigned gy = __umulhi((unsigned)v, g.gs_magic);
-      const uint4* cell = reinterpret_cast<const uint4*>(masks + (gy * (unsigned)g.gw + gx) * (unsigned)g.gwords);
       const int d_plane = (int)(pa * (float)u + pb * (float)v + pc);
       const int r = R ? R : g.plane_radius;
       const int lo = max(d_plane - r, 0), hi = min(d_plane + r, g.p.disp_max);
       // (double)|x| < 0.7  <=>  |x| <= 0.7f  (0.7f is the largest float below 0.7)
       const bool valid = fabsf(pa) <= 0.7f && fabsf(pd) <= 0.7f;
       unsigned best = KEY_NONE;
-      for (int q = 0; q < (g.gwords >> 2); q++) {
-        const uint4 m = __ldg(cell + q);
-        eval_word(best, m.x, 4 * q + 0, lo, hi, a, Bf, rowoff, u, dir, wm4);
-        eval_word(best, m.y, 4 * q + 1, lo, hi, a, Bf, rowoff, u, dir, wm4);
-        eval_word(best, m.z, 4 * q + 2, lo, hi, a, Bf, rowoff, u, dir, wm4);
-        eval_word(best, m.w, 4 * q + 3, lo, hi, a, Bf, rowoff, u, dir, wm4);
+      // grid candidates outside the plane range: compact sorted list, 2 x 128-bit loads
+      const unsigned ci = gy * (unsigned)g.gw + gx;
+      const uint4* lst = reinterpret_cast<const uint4*>(lists + ci * GRID_LIST);
+      const uint4 l0 = __ldg(lst);
+      if (l0.x != 0xFFFEFFFEu) {
+        const uint4 l1 = __ldg(lst + 1);
+        const unsigned wv[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+        // "d < lo || d > hi" as one unsigned compare; an empty plane range (hi < lo: the plane
+        // extrapolates outside [0, disp_max]) excludes nothing
+        const int lo2 = (hi < lo) ? 0x7fffffff : lo;
+        const unsigned span = (hi < lo) ? 0u : (unsigned)(hi - lo);
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          if (wv[k] == 0xFFFFFFFFu) break;          // sorted: only padding follows
+          const int d0 = (int)(wv[k] & 0xFFFFu), d1 = (int)(wv[k] >> 16);
+          if ((unsigned)(d0 - lo2) > span) eval_candidate(best, a, Bf, rowoff, u, dir, d0, 2048u << 13, wm4);
+          // a 0xFFFF pad in the upper half fails the image-bounds test inside eval_candidate
+          if ((unsigned)(d1 - lo2) > span) eval_candidate(best, a, Bf, rowoff, u, dir, d1, 2048u << 13, wm4);
+        }
+      } else {
+        // overflowing cell: decode the bit set
+        const uint4* cell = reinterpret_cast<const uint4*>(masks + ci * (unsigned)g.gwords);
+        for (int q = 0; q < (g.gwords >> 2); q++) {
+          const uint4 m = __ldg(cell + q);
+          eval_word(best, m.x, 4 * q + 0, lo, hi, a, Bf, rowoff, u, dir, wm4);
+          eval_word(best, m.y, 4 * q + 1, lo, hi, a, Bf, rowoff, u, dir, wm4);
+          eval_word(best, m.z, 4 * q + 2, lo, hi, a, Bf, rowoff, u, dir, wm4);
+          eval_word(best, m.w, 4 * q + 3, lo, hi, a, Bf, rowoff, u, dir, wm4);
+        }
       }
       if (R) {
         // key addend per |k|: (2048 + prior) << 13 | class bit

@@ -114,9 +114,50 @@ __global__ void grid_dilate_kernel(Geo g, Workspace ws) {
   }
 }
 
+// Compact form of a cell's bit set for the dense matcher: up to GRID_LIST disparities as sorted
+// u16 (= the reference's candidate list, elas.cpp:642-652), padded with 0xFFFF.  A cell with
+// more candidates stores the overflow marker 0xFFFE everywhere and is decoded from the bit set.
+__global__ void grid_list_kernel(Geo g, Workspace ws) {
+  const int side = blockIdx.y, frame = blockIdx.z;
+  const int cells = g.gw * g.gh, gwords = g.gwords;
+  const uint32_t* mask = ws.gridmask[side] + (size_t)frame * cells * gwords;
+  uint16_t* list = ws.gridlist[side] + (size_t)frame * cells * GRID_LIST;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < cells; c += gridDim.x * blockDim.x) {
+    uint16_t e[GRID_LIST];
+    int n = 0;
+    for (int w = 0; w < gwords; w++) {
+      uint32_t bits = mask[(size_t)c * gwords + w];
+      while (bits) {
+        int b = __ffs(bits) - 1;
+        bits &= bits - 1;
+        if (n < GRID_LIST) e[n] = (uint16_t)(32 * w + b);
+        n++;
+      }
+    }
+    uint4* out = reinterpret_cast<uint4*>(list + (size_t)c * GRID_LIST);
+    uint32_t words[GRID_LIST / 2];
+#pragma unroll
+    for (int k = 0; k < GRID_LIST / 2; k++) {
+      uint32_t lo = (n > g.grid_list_limit) ? 0xFFFEu : (2 * k < n ? e[2 * k] : 0xFFFFu);
+      uint32_t hi = (n > g.grid_list_limit) ? 0xFFFEu : (2 * k + 1 < n ? e[2 * k + 1] : 0xFFFFu);
+      words[k] = lo | (hi << 16);
+    }
+    out[0] = make_uint4(words[0], words[1], words[2], words[3]);
+    out[1] = make_uint4(words[4], words[5], words[6], words[7]);
+  }
+}
+
 }  // namespace
 
-void launch_planes_grid(const Geo& g, int B, Workspace& ws, cudaStream_t s) {
+// test hook: cells with more than `limit` candidates take the bit-set path of the dense matcher
+static int g_list_limit = GRID_LIST;
+extern "C" void jn_debug_grid_list_limit(int limit) {
+  g_list_limit = (limit < 0 || limit > GRID_LIST) ? GRID_LIST : limit;
+}
+
+void launch_planes_grid(const Geo& g_in, int B, Workspace& ws, cudaStream_t s) {
+  Geo g = g_in;
+  g.grid_list_limit = g_list_limit;
   size_t gbytes = (size_t)B * g.gw * g.gh * g.gwords * sizeof(uint32_t);
   cudaMemsetAsync(ws.gridtmp[0], 0, gbytes, s);
   cudaMemsetAsync(ws.gridtmp[1], 0, gbytes, s);
@@ -124,5 +165,6 @@ void launch_planes_grid(const Geo& g, int B, Workspace& ws, cudaStream_t s) {
   grid_scatter_kernel<<<dim3(16, 2, B), 256, 0, s>>>(g, ws);
   int cw = g.gw * g.gh * g.gwords;
   grid_dilate_kernel<<<dim3((cw + 255) / 256, 2, B), 256, 0, s>>>(g, ws);
-  g_jn_launches += 3;
+  grid_list_kernel<<<dim3((g.gw * g.gh + 127) / 128, 2, B), 128, 0, s>>>(g, ws);
+  g_jn_launches += 4;
 }

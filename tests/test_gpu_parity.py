@@ -86,6 +86,23 @@ def test_delaunay_large_point_set_paths(jn, oracle, synth):
     e.close()
 
 
+def test_dense_grid_list_overflow_path(jn, oracle, synth):
+    """The dense matcher reads a compact candidate list per grid cell and falls back to the
+    bit set for cells with more than 16 candidates; force the fallback and compare again."""
+    W, H, dm = 640, 480, 255
+    I1, I2, _ = synth.synth_pair(W, H, dm, 5)
+    a = oracle.stages(ol.robotics(dm), I1, I2)
+    e = jn.Elas(jn.parameters(jn.ROBOTICS, disp_max=dm))
+    try:
+        for limit in (0, 3):
+            jn.lib().jn_debug_grid_list_limit(limit)
+            b = e.stages(I1, I2)
+            assert_stages_equal(a, b, ["grid1", "grid2", "D1_raw", "D2_raw", "D1", "D2"])
+    finally:
+        jn.lib().jn_debug_grid_list_limit(-1)
+    e.close()
+
+
 def test_process_is_a_drop_in(jn, oracle, synth):
     """Elas::process semantics: same maps, caller-owned buffers, bytes_per_line honoured."""
     W, H, dm = 333, 251, 64
