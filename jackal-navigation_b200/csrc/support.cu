@@ -254,7 +254,8 @@ __global__ void __launch_bounds__(FILT_THREADS, 1)
 support_filter_kernel(Geo g, const int16_t* __restrict__ dcan_all, int32_t* __restrict__ cnt_all,
                       int32_t* __restrict__ frontier_all, int16_t* __restrict__ incon_all,
                       int16_t* __restrict__ final_all, int32_t* __restrict__ sup_all, int32_t* __restrict__ px0,
-                      int32_t* __restrict__ px1, int32_t* __restrict__ py_all, FrameInfo* __restrict__ info) {
+                      int32_t* __restrict__ px1, int32_t* __restrict__ py_all, FrameInfo* __restrict__ info,
+                      int use_smem) {
   __shared__ int s_n[2];
   __shared__ int s_part[FILT_THREADS + 1];
   __shared__ int s_col[2048];
@@ -267,6 +268,10 @@ support_filter_kernel(Geo g, const int16_t* __restrict__ dcan_all, int32_t* __re
   int16_t* st1 = incon_all + (size_t)frame * NP;
   int16_t* st2 = final_all + (size_t)frame * NP;
   const int r = g.p.incon_window_size, thr = g.p.incon_threshold, minsup = g.p.incon_min_support;
+  // Working copy of the candidate image for the redundancy passes and the compaction: shared
+  // memory when it fits (their accesses are serial, data dependent and strided), else global.
+  extern __shared__ int16_t s_wk[];
+  int16_t* wk = use_smem ? s_wk : st2;
 
   // ---- inconsistent points: frontier propagation -----------------------------
   if (tid == 0) { s_n[0] = 0; s_n[1] = 0; }
@@ -307,7 +312,7 @@ support_filter_kernel(Geo g, const int16_t* __restrict__ dcan_all, int32_t* __re
     int d = dc[p];
     int16_t o = (d >= 0 && cnt[p] >= minsup) ? (int16_t)d : (int16_t)-1;
     st1[p] = o;
-    st2[p] = o;
+    wk[p] = o;
   }
   __syncthreads();
 
@@ -315,38 +320,38 @@ support_filter_kernel(Geo g, const int16_t* __restrict__ dcan_all, int32_t* __re
   const int md = 5, rt = 1;  // redun_max_dist, redun_threshold (elas.cpp:421-422)
   for (int u = tid; u < Wc; u += T) {
     for (int v = 0; v < Hc; v++) {
-      int d = st2[v * Wc + u];
+      int d = wk[v * Wc + u];
       if (d < 0) continue;
       bool up = false, down = false;
       for (int j = 1; j <= md && v - j >= 0; j++) {
-        int d2 = st2[(v - j) * Wc + u];
+        int d2 = wk[(v - j) * Wc + u];
         if (d2 >= 0 && abs(d - d2) <= rt) { up = true; break; }
       }
       if (!up) continue;
       for (int j = 1; j <= md && v + j < Hc; j++) {
-        int d2 = st2[(v + j) * Wc + u];
+        int d2 = wk[(v + j) * Wc + u];
         if (d2 >= 0 && abs(d - d2) <= rt) { down = true; break; }
       }
-      if (down) st2[v * Wc + u] = -1;
+      if (down) wk[v * Wc + u] = -1;
     }
   }
   __syncthreads();
   // ---- horizontal pass (dependencies along a row only) --------------------------
   for (int v = tid; v < Hc; v += T) {
     for (int u = 0; u < Wc; u++) {
-      int d = st2[v * Wc + u];
+      int d = wk[v * Wc + u];
       if (d < 0) continue;
       bool lft = false, rgt = false;
       for (int j = 1; j <= md && u - j >= 0; j++) {
-        int d2 = st2[v * Wc + u - j];
+        int d2 = wk[v * Wc + u - j];
         if (d2 >= 0 && abs(d - d2) <= rt) { lft = true; break; }
       }
       if (!lft) continue;
       for (int j = 1; j <= md && u + j < Wc; j++) {
-        int d2 = st2[v * Wc + u + j];
+        int d2 = wk[v * Wc + u + j];
         if (d2 >= 0 && abs(d - d2) <= rt) { rgt = true; break; }
       }
-      if (rgt) st2[v * Wc + u] = -1;
+      if (rgt) wk[v * Wc + u] = -1;
     }
   }
   __syncthreads();
@@ -355,11 +360,13 @@ support_filter_kernel(Geo g, const int16_t* __restrict__ dcan_all, int32_t* __re
   for (int u = tid; u < Wc; u += T) {
     int c = 0;
     if (u >= 1)
-      for (int v = 1; v < Hc; v++) c += st2[v * Wc + u] >= 0;
+      for (int v = 1; v < Hc; v++) c += wk[v * Wc + u] >= 0;
     s_col[u] = c;
   }
   __syncthreads();
   int total = block_exclusive_scan(s_col, Wc, s_part);
+  if (wk != st2)
+    for (int p = tid; p < NP; p += T) st2[p] = wk[p];   // final candidate image, kept for the stage dump
   const int step = g.p.candidate_stepsize;
   int4* sup = reinterpret_cast<int4*>(sup_all) + (size_t)frame * g.cap_s;
   int32_t* x0 = px0 + (size_t)frame * g.cap_s;
@@ -368,7 +375,7 @@ support_filter_kernel(Geo g, const int16_t* __restrict__ dcan_all, int32_t* __re
   for (int u = 1 + tid; u < Wc; u += T) {
     int k = s_col[u];
     for (int v = 1; v < Hc; v++) {
-      int d = st2[v * Wc + u];
+      int d = wk[v * Wc + u];
       if (d >= 0) {
         sup[k] = make_int4(u * step, v * step, d, 0);
         x0[k] = u * step;
@@ -404,8 +411,17 @@ int launch_support(const Geo& g, int B, Workspace& ws, cudaStream_t s) {
   support_match_kernel<<<dim3(g.Hc, B), MATCH_THREADS, smem, s>>>(g, ws.desc[0], ws.desc[1], ws.dcan);
   dim3 cb(32, 8), cg((g.Wc + 31) / 32, (g.Hc + 7) / 8, B);
   incon_count_kernel<<<cg, cb, 0, s>>>(g, ws.dcan, ws.cnt);
-  support_filter_kernel<<<B, FILT_THREADS, 0, s>>>(g, ws.dcan, ws.cnt, ws.frontier, ws.dcan_incon, ws.dcan_final,
-                                                   ws.sup, ws.px[0], ws.px[1], ws.py, ws.info);
+  const size_t wk_bytes = (size_t)g.Wc * g.Hc * sizeof(int16_t);
+  const int use_smem = wk_bytes <= 212 * 1024;
+  static bool attr2_set = false;
+  if (!attr2_set) {
+    JN_CUDA_CHECK(cudaFuncSetAttribute(support_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       212 * 1024));
+    attr2_set = true;
+  }
+  support_filter_kernel<<<B, FILT_THREADS, use_smem ? wk_bytes : 0, s>>>(
+      g, ws.dcan, ws.cnt, ws.frontier, ws.dcan_incon, ws.dcan_final, ws.sup, ws.px[0], ws.px[1], ws.py, ws.info,
+      use_smem);
   g_jn_launches += 3;
   return JN_OK;
 }
