@@ -59,22 +59,49 @@ __device__ __forceinline__ Best best_merge_warp(Best b) {
 
 constexpr int KG = 4;   // candidates matched together by one warp
 
+// (best, second best) as two packed keys (energy << 16 | disparity): the smallest key is the
+// reference's best match (lowest energy, lowest disparity among ties, H7) and the energy of the
+// second smallest key is its second-best energy.  Updating needs only min/max.
+struct Best2 {
+  unsigned k1, k2;
+};
+__device__ __forceinline__ void best2_update(Best2& b, unsigned key) {
+  const unsigned hi = max(b.k1, key);
+  b.k1 = min(b.k1, key);
+  b.k2 = min(b.k2, hi);
+}
+__device__ __forceinline__ Best2 best2_merge_warp(Best2 b) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const unsigned o1 = __shfl_xor_sync(0xffffffffu, b.k1, off);
+    const unsigned o2 = __shfl_xor_sync(0xffffffffu, b.k2, off);
+    const unsigned hi = max(b.k1, o1);
+    b.k1 = min(b.k1, o1);
+    b.k2 = min(min(b.k2, o2), hi);
+  }
+  return b;
+}
+
 // KG candidates, executed by a full warp.  rowA_* = descriptor rows of the image the pixels
 // live in, rowB_* = rows of the image searched; dir = -1 (left pixels, search u-d) or +1
 // (right pixels, search u+d); u[k] < 0 = empty slot.  The lanes stride POSITIONS of the
 // searched rows: every lane loads the four searched descriptors of its position once and
 // scores them against all KG candidates (disparity = distance to the candidate), so the
-// shared-memory traffic per candidate drops by KG.  res[k] = disparity or -1.
+// shared-memory traffic per candidate drops by KG.  32-position chunks that lie inside every
+// candidate's range take a path without any range test; the integer pipe then carries little
+// more than the 16 VABSDIFF4 per candidate and position (keys and disparities are formed with
+// IMAD on the FMA pipe).  res[k] = disparity or -1.
 __device__ __forceinline__ void match_group(const Geo& g, const int (&u)[KG], int dir, const uint4* rowA_t,
                                             const uint4* rowA_b, const uint4* rowB_t, const uint4* rowB_b,
                                             const uint4* centre_row, int lane, int (&res)[KG]) {
   const int W = g.W;
   const int dmin = max(g.p.disp_min, 0);
   uint4 a[KG][4];
-  int dmax[KG];
+  int p0[KG], p1[KG];     // position range of candidate k (empty if not ok)
   bool ok[KG];
-  Best best[KG];
-  int plo = 0x7fffffff, phi = -0x7fffffff;
+  Best2 best[KG];
+  int plo = 0x7fffffff, phi = -0x7fffffff;   // union of the ranges
+  int ilo = -0x7fffffff, ihi = 0x7fffffff;   // intersection of the ranges
   uint4 c[KG];
 #pragma unroll
   for (int k = 0; k < KG; k++) {
@@ -83,43 +110,58 @@ __device__ __forceinline__ void match_group(const Geo& g, const int (&u)[KG], in
   }
 #pragma unroll
   for (int k = 0; k < KG; k++) {
-    dmax[k] = (dir < 0) ? min(g.p.disp_max, u[k] - 5) : min(g.p.disp_max, W - u[k] - 5);
-    ok[k] = ok[k] && (int)texture16(c[k]) >= g.p.support_texture && (dmax[k] - dmin >= 10);
-    best[k].key = EMPTY_KEY;
-    best[k].e2 = 32767u;
+    const int dmax = (dir < 0) ? min(g.p.disp_max, u[k] - 5) : min(g.p.disp_max, W - u[k] - 5);
+    ok[k] = ok[k] && (int)texture16(c[k]) >= g.p.support_texture && (dmax - dmin >= 10);
+    best[k].k1 = 0xFFFFFFFFu;
+    best[k].k2 = 0xFFFFFFFFu;
     res[k] = -1;
     if (ok[k]) {
       a[k][0] = rowA_t[u[k] - 2]; a[k][1] = rowA_t[u[k] + 2];
       a[k][2] = rowA_b[u[k] - 2]; a[k][3] = rowA_b[u[k] + 2];
-      int p0 = (dir < 0) ? u[k] - dmax[k] : u[k] + dmin;
-      int p1 = (dir < 0) ? u[k] - dmin : u[k] + dmax[k];
-      plo = min(plo, p0);
-      phi = max(phi, p1);
+      p0[k] = (dir < 0) ? u[k] - dmax : u[k] + dmin;
+      p1[k] = (dir < 0) ? u[k] - dmin : u[k] + dmax;
+      plo = min(plo, p0[k]); phi = max(phi, p1[k]);
+      ilo = max(ilo, p0[k]); ihi = min(ihi, p1[k]);
     } else {
       a[k][0] = a[k][1] = a[k][2] = a[k][3] = make_uint4(0, 0, 0, 0);
+      p0[k] = 1; p1[k] = 0;
     }
   }
   if (plo > phi) return;   // no candidate of the group survives the gates
-  for (int p = plo + lane; p <= phi; p += 32) {
+  // disparity of candidate k at position p:  dir*(p - u[k])  ->  key = e * 65536 + d
+  for (int base = plo; base <= phi; base += 32) {
+    const int p = min(base + lane, phi);
     const uint4 s0 = rowB_t[p - 2], s1 = rowB_t[p + 2], s2 = rowB_b[p - 2], s3 = rowB_b[p + 2];
+    if (base >= ilo && base + 31 <= ihi) {
 #pragma unroll
-    for (int k = 0; k < KG; k++) {
-      const int d = (dir < 0) ? u[k] - p : p - u[k];
-      if (ok[k] && d >= dmin && d <= dmax[k]) {
+      for (int k = 0; k < KG; k++) {
+        if (!ok[k]) continue;
         unsigned e = sad16(a[k][0], s0, 0u);
         e = sad16(a[k][1], s1, e);
         e = sad16(a[k][2], s2, e);
         e = sad16(a[k][3], s3, e);
-        best_update(best[k], e, (unsigned)d);
+        best2_update(best[k], e * 65536u + (unsigned)(dir * (p - u[k])));
+      }
+    } else {
+      const bool lane_in = base + lane <= phi;
+#pragma unroll
+      for (int k = 0; k < KG; k++) {
+        if (!ok[k]) continue;
+        unsigned e = sad16(a[k][0], s0, 0u);
+        e = sad16(a[k][1], s1, e);
+        e = sad16(a[k][2], s2, e);
+        e = sad16(a[k][3], s3, e);
+        const unsigned key = e * 65536u + (unsigned)(dir * (p - u[k]));
+        best2_update(best[k], (lane_in && p >= p0[k] && p <= p1[k]) ? key : 0xFFFFFFFFu);
       }
     }
   }
 #pragma unroll
   for (int k = 0; k < KG; k++) {
     if (!ok[k]) continue;
-    Best b = best_merge_warp(best[k]);
-    float e1 = (float)(b.key >> 16), e2 = (float)b.e2;
-    if (e1 < __fmul_rn(g.p.support_threshold, e2)) res[k] = (int)(b.key & 0xFFFFu);
+    const Best2 b = best2_merge_warp(best[k]);
+    const float e1 = (float)(b.k1 >> 16), e2 = (float)(b.k2 >> 16);
+    if (e1 < __fmul_rn(g.p.support_threshold, e2)) res[k] = (int)(b.k1 & 0xFFFFu);
   }
 }
 
