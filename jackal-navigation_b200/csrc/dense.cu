@@ -92,7 +92,7 @@ __device__ __forceinline__ void eval_candidate(unsigned& best, const uint4& a, c
                                                unsigned rowoff, int u, int dir, int d, unsigned addend,
                                                unsigned wm4) {
   const int uw = u + dir * d;
-  if ((unsigned)(uw - 2) < wm4) {
+  if ((unsigned)(uw - 2) < wm4) {   // u_warp in [2, W-3] (a branch-free variant measured slower)
     const uint4 b = __ldg(Bf + (rowoff + (unsigned)uw));
     best = min(best, sad16(a, b, 0u) * 8192u + (addend + (unsigned)d));
   }
@@ -190,12 +190,23 @@ dense_kernel(Geo g, Workspace ws) {
         const unsigned a1 = ((unsigned)(2048 + (valid ? P1 : 0)) << 13) | (1u << 12);
         const unsigned a2 = ((unsigned)(2048 + (valid ? P2 : 0)) << 13) | (1u << 12);
         const unsigned a3 = ((unsigned)(2048 + (valid ? P3 : 0)) << 13) | (1u << 12);
+        // The 2R+1 plane-range candidates are consecutive descriptors of the searched row: issue
+        // all loads first (clamped addresses, memory-level parallelism), then score and discard
+        // the ones outside [0, disp_max] or outside the image.
+        uint4 bb[2 * R + 1];
 #pragma unroll
         for (int k = -R; k <= R; k++) {
-          const int d = d_plane + k;
+          const int uw = u + dir * (d_plane + k);
+          bb[k + R] = __ldg(Bf + (rowoff + (unsigned)min(max(uw, 2), (int)wm4 + 1)));
+        }
+#pragma unroll
+        for (int k = -R; k <= R; k++) {
+          const int d = d_plane + k, uw = u + dir * d;
           const int ak = k < 0 ? -k : k;
           const unsigned add = ak == 0 ? a0 : (ak == 1 ? a1 : (ak == 2 ? a2 : a3));
-          if (d >= 0 && d <= g.p.disp_max) eval_candidate(best, a, Bf, rowoff, u, dir, d, add, wm4);
+          const unsigned key = sad16(a, bb[k + R], 0u) * 8192u + (add + (unsigned)d);
+          const bool okc = (unsigned)d <= (unsigned)g.p.disp_max && (unsigned)(uw - 2) < wm4;
+          best = min(best, okc ? key : KEY_NONE);
         }
       } else {
         for (int d = lo; d <= hi; d++)
