@@ -79,7 +79,7 @@ __global__ void raster_kernel(Geo g, Workspace ws) {
 }
 
 constexpr int DENSE_THREADS = 128;
-constexpr int DENSE_ROWS = 4;              // image rows per thread (amortises the per-thread setup)
+constexpr int DENSE_ROWS = 8;              // image rows per thread (amortises the per-thread setup)
 constexpr unsigned KEY_NONE = 0xFFFFFFFFu;
 
 // One candidate: 16-byte SAD (+ prior), folded into a packed key

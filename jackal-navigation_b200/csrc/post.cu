@@ -382,6 +382,61 @@ __global__ void mean_v_kernel(Geo g, Workspace ws, const float* __restrict__ in,
   out[(size_t)frame * out_frame_stride + (size_t)c * W + u] = o;
 }
 
+// Both passes in one kernel: a CTA produces a MT_W x MT_H tile of the output.  The input tile
+// (4 / 3 columns and rows of halo) is staged in shared memory once, the horizontally filtered
+// rows the vertical pass needs (MT_H + 7 of them) are computed into shared memory and never
+// touch HBM: one read and one write of the map instead of three reads and two writes.
+constexpr int MT_W = 64, MT_H = 32, MT_IN_W = MT_W + 7, MT_ROWS = MT_H + 7;
+
+__global__ void __launch_bounds__(256)
+mean_fused_kernel(Geo g, Workspace ws, const float* __restrict__ in, float* __restrict__ out,
+                  size_t out_frame_stride) {
+  __shared__ float s_in[MT_ROWS][MT_IN_W + 1];   // rows y0-4 .. y0+MT_H+2, columns x0-4 .. x0+MT_W+2
+  __shared__ float s_tmp[MT_ROWS][MT_W];         // horizontally filtered (the reference's D_tmp)
+  const int frame = blockIdx.z;
+  if (ws.info[frame].status != JN_OK) return;
+  const int W = g.W, H = g.H, tid = threadIdx.x;
+  const int x0 = blockIdx.x * MT_W, y0 = blockIdx.y * MT_H;
+  const float* src = in + (size_t)frame * W * H;
+  for (int i = tid; i < MT_ROWS * MT_IN_W; i += 256) {
+    const int r = i / MT_IN_W, c = i - r * MT_IN_W;
+    const int y = y0 - 4 + r, x = x0 - 4 + c;
+    s_in[r][c] = (x >= 0 && x < W && y >= 0 && y < H) ? src[(size_t)y * W + x] : 0.f;
+  }
+  __syncthreads();
+  // D_tmp: filtered for rows 3..H-4 and centres 4..W-4, otherwise -10 (invalid input) or 0 (H1)
+  for (int i = tid; i < MT_ROWS * MT_W; i += 256) {
+    const int r = i / MT_W, c = i - r * MT_W;
+    const int y = y0 - 4 + r, x = x0 + c;
+    const float d = s_in[r][c + 4];
+    float o = (d < 0) ? -10.f : 0.f;
+    if (W >= 8 && y >= 3 && y <= H - 4 && x >= 4 && x <= W - 4) {
+      float w8[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) { const float t = s_in[r][c + k]; w8[k] = (t < 0) ? -10.f : t; }
+      float m;
+      if (mean8(w8, w8[4], (x - 4) & 3, m)) o = m;
+    }
+    s_tmp[r][c] = o;
+  }
+  __syncthreads();
+  float* dst = out + (size_t)frame * out_frame_stride;
+  for (int i = tid; i < MT_H * MT_W; i += 256) {
+    const int r = i / MT_W, c = i - r * MT_W;
+    const int y = y0 + r, x = x0 + c;
+    if (x >= W || y >= H) continue;
+    float o = s_in[r + 4][c + 4];
+    if (H >= 8 && x >= 3 && x <= W - 4 && y >= 4 && y <= H - 4) {
+      float w8[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) w8[k] = s_tmp[r + k][c];   // rows y-4 .. y+3
+      float m;
+      if (mean8(w8, w8[4], (y - 4) & 3, m)) o = m;
+    }
+    dst[(size_t)y * W + x] = o;
+  }
+}
+
 // ------------------------------------------------------------ median
 __device__ __forceinline__ float median7(float v[7]) {
   // insertion sort, as elas.cpp:1518-1527 (NaNs cannot occur)
@@ -480,10 +535,10 @@ void post_gap(const Geo& g, int B, Workspace& ws, int side, cudaStream_t s) {
 // in -> out (frame stride of out given in floats); tmp = scratch
 void post_mean(const Geo& g, int B, Workspace& ws, const float* in, float* tmp, float* out, size_t ostride,
                cudaStream_t s) {
-  dim3 pg((g.W + 255) / 256, g.H, B);
-  mean_h_kernel<<<pg, 256, 0, s>>>(g, ws, in, tmp);
-  mean_v_kernel<<<pg, 256, 0, s>>>(g, ws, in, tmp, out, ostride);
-  g_jn_launches += 2;
+  (void)tmp;   // the horizontally filtered rows live in shared memory only
+  dim3 grid((g.W + MT_W - 1) / MT_W, (g.H + MT_H - 1) / MT_H, B);
+  mean_fused_kernel<<<grid, 256, 0, s>>>(g, ws, in, out, ostride);
+  g_jn_launches += 1;
 }
 
 void post_median(const Geo& g, int B, Workspace& ws, const float* in, float* tmp, float* out, size_t ostride,
