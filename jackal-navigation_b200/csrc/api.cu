@@ -139,7 +139,6 @@ static int make_geo(const jn_elas_params& p, const int32_t dims[3], Geo* out) {
   g.W = dims[0]; g.H = dims[1]; g.bpl = dims[2];
   if (g.W < 16 || g.H < 16 || g.bpl < g.W) { jn_set_error("bad dims %dx%d stride %d", g.W, g.H, g.bpl); return JN_ERR_ARG; }
   if (p.subsampling) { jn_set_error("subsampling=1 is not built yet"); return JN_ERR_UNSUPPORTED; }
-  if (p.add_corners) { jn_set_error("add_corners=1 is not built yet"); return JN_ERR_UNSUPPORTED; }
   if (p.disp_max < 10 || p.disp_max > 4095 || p.disp_min > p.disp_max || p.candidate_stepsize < 1 ||
       p.grid_size < 1 || p.incon_window_size < 0 || p.incon_window_size > 16) {
     jn_set_error("parameter out of the supported range");
@@ -352,6 +351,7 @@ extern "C" int jn_elas_process(jn_elas* e, const uint8_t* I1, const uint8_t* I2,
   if (rc) return rc;
   int32_t st = 0;
   JN_CUDA_CHECK(cudaMemcpy(&st, e->dStatus, sizeof(st), cudaMemcpyDeviceToHost));
+  if (st < 0) jn_set_error("frame rejected on the device (status %d): parameter combination not supported", st);
   if (st == JN_OK) {  // "<3 support points": outputs untouched (elas.cpp:66-71)
     JN_CUDA_CHECK(cudaMemcpy(D1, e->dD[0], npix * sizeof(float), cudaMemcpyDeviceToHost));
     JN_CUDA_CHECK(cudaMemcpy(D2, e->dD[1], npix * sizeof(float), cudaMemcpyDeviceToHost));

@@ -29,6 +29,9 @@
 void jn_set_error(const char* fmt, ...);
 extern long long g_jn_launches;   // kernels launched by this library (bench.py gpu_launches)
 
+// Right-image x coordinates (u - d) are stored with this bias so that they stay non-negative
+// (corner support points reach u - d = -d); the Delaunay predicates are translation invariant.
+constexpr int JN_XBIAS = 4096;
 constexpr int GRID_LIST = 16;    // entries of the compact per-cell candidate list
 
 // Per-call geometry + parameters, passed to kernels by value.

@@ -472,6 +472,10 @@ delaunay_kernel(Geo g, Workspace ws) {
     bitonic_sort(key, N);
     for (int i = tid; i < nu; i += DT) yl[i] = (int)(key[i] & 0xFFFFFFFFu);
     __syncthreads();
+  } else if (g.p.add_corners) {
+    // corner points are off the lattice the occupancy grid is built on: not supported together
+    if (tid == 0) { info->status = JN_ERR_UNSUPPORTED; info->n_tri[side] = 0; }
+    return;
   } else {
     // large point sets: ranks by prefix sums over an occupancy grid (preset to OCC_EMPTY)
     const int step = g.p.candidate_stepsize;
@@ -479,7 +483,8 @@ delaunay_kernel(Geo g, Workspace ws) {
     const int cells = xdim * Hc;
     int* occ = ws.occ + ((size_t)frame * 2 + side) * ((size_t)g.W * Hc);
     int* scanbig = ws.trimap[side] + (size_t)frame * g.W * g.H;   // >= cells ints, free at this point
-    for (int i = tid; i < n; i += DT) atomicMin(&occ[(px[i] / xdiv) * Hc + py[i] / step], i);
+    const int xb = side ? JN_XBIAS : 0;
+    for (int i = tid; i < n; i += DT) atomicMin(&occ[((px[i] - xb) / xdiv) * Hc + py[i] / step], i);
     __syncthreads();
     for (int c = tid; c < cells; c += DT) scanbig[c] = occ[c] != OCC_EMPTY;
     __syncthreads();

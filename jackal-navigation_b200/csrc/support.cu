@@ -421,11 +421,53 @@ support_filter_kernel(Geo g, const int16_t* __restrict__ dcan_all, int32_t* __re
       if (d >= 0) {
         sup[k] = make_int4(u * step, v * step, d, 0);
         x0[k] = u * step;
-        x1[k] = u * step - d;
+        x1[k] = u * step - d + JN_XBIAS;
         y[k] = v * step;
         k++;
       }
     }
+  }
+  if (g.p.add_corners) {
+    // addCornerSupportPoints (elas.cpp:237-267): the four image corners take the disparity of the
+    // nearest support point (first one among equal squared distances), plus two copies of the
+    // right corners shifted by their disparity.  Nearest = min over (dist << 32 | index) keys.
+    __shared__ unsigned long long s_best[4][FILT_THREADS / 32];
+    __syncthreads();
+    const int cu[4] = {0, 0, g.W - 1, g.W - 1}, cv[4] = {0, g.H - 1, 0, g.H - 1};
+    unsigned long long bk[4] = {~0ull, ~0ull, ~0ull, ~0ull};
+    for (int j = tid; j < total; j += T) {
+      const int4 sj = sup[j];
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        const int du = cu[c] - sj.x, dv = cv[c] - sj.y;
+        const unsigned dist = (unsigned)(du * du + dv * dv);
+        if (dist < 10000000u) bk[c] = min(bk[c], ((unsigned long long)dist << 32) | (unsigned)j);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      for (int off = 16; off > 0; off >>= 1) bk[c] = min(bk[c], __shfl_xor_sync(0xffffffffu, bk[c], off));
+      if (lane == 0) s_best[c][warp] = bk[c];
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int cd[4];
+      for (int c = 0; c < 4; c++) {
+        unsigned long long b = ~0ull;
+        for (int w = 0; w < nwarps; w++) b = min(b, s_best[c][w]);
+        cd[c] = (b == ~0ull) ? 0 : sup[(unsigned)(b & 0xFFFFFFFFull)].z;
+      }
+      const int bu[6] = {0, 0, g.W - 1, g.W - 1, g.W - 1 + cd[2], g.W - 1 + cd[3]};
+      const int bv[6] = {0, g.H - 1, 0, g.H - 1, 0, g.H - 1};
+      const int bd[6] = {cd[0], cd[1], cd[2], cd[3], cd[2], cd[3]};
+      for (int k = 0; k < 6; k++) {
+        sup[total + k] = make_int4(bu[k], bv[k], bd[k], 0);
+        x0[total + k] = bu[k];
+        x1[total + k] = bu[k] - bd[k] + JN_XBIAS;
+        y[total + k] = bv[k];
+      }
+    }
+    total += 6;
   }
   if (tid == 0) {
     info[frame].n_support = total;

@@ -43,6 +43,11 @@ def test_cuda_matches_golden(jn, name, H):
     (640, 480, 255, 5, {"filter_median": 1, "postprocess_only_left": 0}),
     (256, 192, 255, 9, {"ipol_gap_width": 7, "speckle_size": 50, "lr_threshold": 1}),
     (320, 240, 64, 3, {"filter_adaptive_mean": 0}),
+    (320, 240, 64, 8, {"ipol_gap_width": 40, "postprocess_only_left": 0}),          # CTA-scan gap kernels
+    (320, 240, 64, 8, {"ipol_gap_width": 5000, "filter_median": 1, "filter_adaptive_mean": 0,
+                       "postprocess_only_left": 0, "match_texture": 0, "gamma": 5.0, "sradius": 3.0,
+                       "support_threshold": 0.95}),                                    # MIDDLEBURY minus add_corners
+    (2200, 1300, 255, 2, {}),                                          # lattice too large for the smem filter
     (1920, 600, 255, 1001, {}),                                        # C3 with -h 600 crop
 ])
 def test_every_stage_matches_oracle(jn, oracle, synth, W, H, dm, seed, kw):
@@ -51,6 +56,36 @@ def test_every_stage_matches_oracle(jn, oracle, synth, W, H, dm, seed, kw):
     e = jn.Elas(jn.parameters(jn.ROBOTICS, disp_max=dm, **kw))
     b = e.stages(I1, I2)
     assert_stages_equal(a, b)
+    e.close()
+
+
+@pytest.mark.parametrize("W,H,dm,seed", [(320, 240, 64, 3), (640, 480, 255, 12), (333, 251, 100, 7)])
+def test_middlebury_preset_matches_oracle(jn, oracle, synth, W, H, dm, seed):
+    """Elas::parameters(MIDDLEBURY): add_corners (4 corner support points + 2 shifted copies,
+    border extrapolation in the gap interpolation), median, both images, plane radius 3."""
+    I1, I2, _ = synth.synth_pair(W, H, dm, seed)
+    a = oracle.stages(ol.middlebury(dm), I1, I2)
+    e = jn.Elas(jn.parameters(jn.MIDDLEBURY, disp_max=dm))
+    b = e.stages(I1, I2)
+    assert_stages_equal(a, b)
+    assert (b["support"][-6:, :2] == [[0, 0], [0, H - 1], [W - 1, 0], [W - 1, H - 1],
+                                       [W - 1 + b["support"][-2, 2], 0], [W - 1 + b["support"][-1, 2], H - 1]]).all()
+    e.close()
+
+
+def test_add_corners_on_textureless_pair(jn, oracle):
+    """No support point at all: the corners get disparity 0 and the pipeline continues (6 points)."""
+    I = np.full((120, 160), 77, np.uint8)
+    a = oracle.stages(ol.middlebury(32), I, I)
+    e = jn.Elas(jn.parameters(jn.MIDDLEBURY, disp_max=32))
+    b = e.stages(I, I)
+    assert a["rc"] == b["rc"] == 0 and b["n_support"] == 6
+    # With disparity 0 the shifted corner copies coincide with the right corners.  Triangle keeps
+    # whichever duplicate its randomised quicksort meets first, the GPU keeps the lowest index
+    # (DESIGN.md section 4): the vertex ids may differ, coordinates, planes and maps may not.
+    assert_stages_equal(a, b, [k for k in STAGES if k not in ("tri1", "tri2")])
+    for k in ("tri1", "tri2"):
+        assert np.array_equal(a["support"][a[k]], b["support"][b[k]])
     e.close()
 
 
@@ -135,7 +170,7 @@ def test_few_support_points_leave_outputs_untouched(jn, capsys):
 
 def test_unsupported_parameters_fail_loudly(jn):
     I = np.zeros((120, 160), np.uint8); D = np.zeros((120, 160), np.float32)
-    for kw in ({"subsampling": 1}, {"add_corners": 1}):
+    for kw in ({"subsampling": 1},):
         e = jn.Elas(jn.parameters(jn.ROBOTICS, **kw))
         with pytest.raises(jn.JnError):
             e.process(I, I, D, D.copy(), (160, 120, 160))
