@@ -11,17 +11,28 @@ __device__ inline int block_exclusive_scan(int* data, int n, int* part) {
   const int lo = min(t * chunk, n), hi = min(lo + chunk, n);
   int s = 0;
   for (int i = lo; i < hi; i++) s += data[i];
-  part[t] = s;
-  __syncthreads();
-  // Hillis-Steele over the T partials
-  for (int off = 1; off < T; off <<= 1) {
-    int v = (t >= off) ? part[t - off] : 0;
-    __syncthreads();
-    part[t] += v;
-    __syncthreads();
+  // inclusive scan of the T partials: shuffle scan inside each warp, then over the warp totals
+  const int lane = t & 31, w = t >> 5, nw = (T + 31) >> 5;
+  int inc = s;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    int v = __shfl_up_sync(0xffffffffu, inc, off);
+    if (lane >= off) inc += v;
   }
-  int total = part[T - 1];
-  int run = (t == 0) ? 0 : part[t - 1];
+  if (lane == 31) part[w] = inc;          // part[0..nw) = warp totals
+  __syncthreads();
+  if (w == 0) {
+    int wt = (lane < nw) ? part[lane] : 0;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      int v = __shfl_up_sync(0xffffffffu, wt, off);
+      if (lane >= off) wt += v;
+    }
+    if (lane < nw) part[lane] = wt;       // inclusive scan of the warp totals (nw <= 32)
+  }
+  __syncthreads();
+  const int total = part[nw - 1];
+  int run = inc - s + (w ? part[w - 1] : 0);   // exclusive prefix of this thread's chunk
   __syncthreads();
   for (int i = lo; i < hi; i++) {
     int v = data[i];

@@ -59,6 +59,7 @@ struct MeshG {
   __device__ __forceinline__ void setvx(int t, int o, int v) const { vx[3 * t + o] = v; }
   __device__ __forceinline__ int X(int v) const { return x[v]; }
   __device__ __forceinline__ int Y(int v) const { return y[v]; }
+  __device__ __forceinline__ void XY(int v, int& px_, int& py_) const { px_ = x[v]; py_ = y[v]; }
 };
 // Triangle table in shared memory: row = {nb0,nb1,nb2,vx0,vx1,vx2} as u16; 0xFFFF = ghost vertex.
 struct MeshS {
@@ -69,6 +70,11 @@ struct MeshS {
   __device__ __forceinline__ void setvx(int t, int o, int v) const { rows[6 * t + 3 + o] = (unsigned short)v; }
   __device__ __forceinline__ int X(int v) const { return (int)(xy[v] >> 16); }
   __device__ __forceinline__ int Y(int v) const { return (int)(xy[v] & 0xFFFFu); }
+  __device__ __forceinline__ void XY(int v, int& px_, int& py_) const {
+    const unsigned c = xy[v];
+    px_ = (int)(c >> 16);
+    py_ = (int)(c & 0xFFFFu);
+  }
 };
 
 template <class M> __device__ __forceinline__ Ot sym(const M& m, Ot a) { return dec(m.getnb(a.t, a.o)); }
@@ -89,20 +95,22 @@ template <class M> __device__ __forceinline__ Ot newtri(const M& m, int row) {
   return r;
 }
 
-template <class M> __device__ __forceinline__ long long ccw(const M& m, int a, int b, int c) {
-  long long cx = m.X(c), cy = m.Y(c);
-  long long ax = m.X(a) - cx, ay = m.Y(a) - cy;
-  long long bx = m.X(b) - cx, by = m.Y(b) - cy;
-  return ax * by - ay * bx;
+// Exact predicates on coordinates.  |coordinate differences| < 2^13 + 2^12, so the orientation
+// determinant fits in 32 bits; the incircle determinant needs 64 bits only for its last products.
+struct Pt { int x, y; };
+template <class M> __device__ __forceinline__ Pt load_pt(const M& m, int v) { Pt p; m.XY(v, p.x, p.y); return p; }
+__device__ __forceinline__ int ccw_pt(Pt a, Pt b, Pt c) {
+  return (a.x - c.x) * (b.y - c.y) - (a.y - c.y) * (b.x - c.x);
 }
-template <class M> __device__ __forceinline__ bool incircle_pos(const M& m, int a, int b, int c, int d) {
-  long long dx = m.X(d), dy = m.Y(d);
-  long long adx = m.X(a) - dx, ady = m.Y(a) - dy;
-  long long bdx = m.X(b) - dx, bdy = m.Y(b) - dy;
-  long long cdx = m.X(c) - dx, cdy = m.Y(c) - dy;
-  long long al = adx * adx + ady * ady, bl = bdx * bdx + bdy * bdy, cl = cdx * cdx + cdy * cdy;
-  long long det = al * (bdx * cdy - cdx * bdy) + bl * (cdx * ady - adx * cdy) + cl * (adx * bdy - bdx * ady);
+__device__ __forceinline__ bool incircle_pt(Pt a, Pt b, Pt c, Pt d) {
+  const int adx = a.x - d.x, ady = a.y - d.y, bdx = b.x - d.x, bdy = b.y - d.y, cdx = c.x - d.x, cdy = c.y - d.y;
+  const int al = adx * adx + ady * ady, bl = bdx * bdx + bdy * bdy, cl = cdx * cdx + cdy * cdy;   // < 2^29
+  const int t1 = bdx * cdy - cdx * bdy, t2 = cdx * ady - adx * cdy, t3 = adx * bdy - bdx * ady;   // < 2^29
+  const long long det = (long long)al * t1 + (long long)bl * t2 + (long long)cl * t3;
   return det > 0;
+}
+template <class M> __device__ __forceinline__ long long ccw(const M& m, int a, int b, int c) {
+  return ccw_pt(load_pt(m, a), load_pt(m, b), load_pt(m, c));
 }
 
 // Knit the triangulations of two adjacent point sets (mergehulls).  row0/row1 are
@@ -172,9 +180,11 @@ __device__ void merge_hulls(const M& m, Ot& farleft, Ot innerleft, Ot innerright
   if (iro == dest(m, farright)) farright = lprev(base);
   int ll = ild, lr = iro;
   int ul = apex(m, leftcand), ur = apex(m, rightcand);
+  // coordinates of the four active vertices stay in registers
+  Pt pll = load_pt(m, ll), plr = load_pt(m, lr), pul = load_pt(m, ul), pur = load_pt(m, ur);
   for (;;) {
-    bool leftdone = ccw(m, ul, ll, lr) <= 0;
-    bool rightdone = ccw(m, ur, ll, lr) <= 0;
+    bool leftdone = ccw_pt(pul, pll, plr) <= 0;
+    bool rightdone = ccw_pt(pur, pll, plr) <= 0;
     if (leftdone && rightdone) {
       Ot top = newtri(m, row1);
       setorg(m, top, ll);
@@ -206,7 +216,8 @@ __device__ void merge_hulls(const M& m, Ot& farleft, Ot innerleft, Ot innerright
       Ot nxt = sym(m, lprev(leftcand));
       int na = apex(m, nxt);
       if (na != -1) {
-        bool bad = incircle_pos(m, ll, lr, ul, na);
+        Pt pna = load_pt(m, na);
+        bool bad = incircle_pt(pll, plr, pul, pna);
         while (bad) {
           nxt = lnext(nxt);
           Ot topc = sym(m, nxt);
@@ -225,9 +236,14 @@ __device__ void merge_hulls(const M& m, Ot& farleft, Ot innerleft, Ot innerright
           setdest(m, nxt, ul);
           setapex(m, nxt, na);
           ul = na;
+          pul = pna;
           nxt = sidec;
           na = apex(m, nxt);
-          bad = (na != -1) ? incircle_pos(m, ll, lr, ul, na) : false;
+          bad = false;
+          if (na != -1) {
+            pna = load_pt(m, na);
+            bad = incircle_pt(pll, plr, pul, pna);
+          }
         }
       }
     }
@@ -235,7 +251,8 @@ __device__ void merge_hulls(const M& m, Ot& farleft, Ot innerleft, Ot innerright
       Ot nxt = sym(m, lnext(rightcand));
       int na = apex(m, nxt);
       if (na != -1) {
-        bool bad = incircle_pos(m, ll, lr, ur, na);
+        Pt pna = load_pt(m, na);
+        bool bad = incircle_pt(pll, plr, pur, pna);
         while (bad) {
           nxt = lprev(nxt);
           Ot topc = sym(m, nxt);
@@ -254,26 +271,35 @@ __device__ void merge_hulls(const M& m, Ot& farleft, Ot innerleft, Ot innerright
           setdest(m, nxt, -1);
           setapex(m, nxt, na);
           ur = na;
+          pur = pna;
           nxt = sidec;
           na = apex(m, nxt);
-          bad = (na != -1) ? incircle_pos(m, ll, lr, ur, na) : false;
+          bad = false;
+          if (na != -1) {
+            pna = load_pt(m, na);
+            bad = incircle_pt(pll, plr, pur, pna);
+          }
         }
       }
     }
-    if (leftdone || (!rightdone && incircle_pos(m, ul, ll, lr, ur))) {
+    if (leftdone || (!rightdone && incircle_pt(pul, pll, plr, pur))) {
       bond(m, base, rightcand);
       base = lprev(rightcand);
       setdest(m, base, ll);
       lr = ur;
+      plr = pur;
       rightcand = sym(m, base);
       ur = apex(m, rightcand);
+      pur = load_pt(m, ur);
     } else {
       bond(m, base, leftcand);
       base = lnext(leftcand);
       setorg(m, base, lr);
       ll = ul;
+      pll = pul;
       leftcand = sym(m, base);
       ul = apex(m, leftcand);
+      pul = load_pt(m, ul);
     }
   }
 }
