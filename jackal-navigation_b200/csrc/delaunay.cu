@@ -39,7 +39,9 @@ namespace {
 constexpr int DT = 512;
 constexpr int SMEM_MAX_POINTS = 7680;                      // 2n-2 rows * 12 B + n * 4 B <= ~210 KB
 constexpr int SORT_MAX = 8192;                             // bitonic sort capacity (64 KB of keys)
-constexpr size_t DELAUNAY_SMEM = (size_t)(2 * SMEM_MAX_POINTS) * 12 + (size_t)SMEM_MAX_POINTS * 4;
+// dynamic shared memory: sort keys (64 KB), then the partition lists (216 KB), then the triangle
+// table + packed coordinates (2*7680 rows * 12 B + 7680 * 4 B = 210 KB)
+constexpr size_t DELAUNAY_SMEM = 220 * 1024;
 
 struct Ot { int t, o; };
 
@@ -457,13 +459,25 @@ delaunay_kernel(Geo g, Workspace ws) {
   const size_t fo = (size_t)frame * g.cap_s;
   const int* px = ws.px[side] + fo;
   const int* py = ws.py + fo;
-  int* xl = ws.xlist[side] + fo;
-  int* yl = ws.ylist[side] + fo;
-  int* sp = ws.tmpA[side] + fo;
-  int* seglo = ws.tmpB[side] + fo;
-  int* segn = ws.tmpC[side] + fo;
-  int* flag = ws.tmpD[side] + (size_t)frame * g.cap_t;          // cap_t ints
+  int* const xl_g = ws.xlist[side] + fo;
+  int* const flag_g = ws.tmpD[side] + (size_t)frame * g.cap_t;  // cap_t ints
+  int *xl = xl_g, *yl = ws.ylist[side] + fo, *sp = ws.tmpA[side] + fo;
+  int *seglo = ws.tmpB[side] + fo, *segn = ws.tmpC[side] + fo;
+  int* flag = flag_g;
   int* scan = ws.nodeL[side] + (size_t)frame * g.cap_t;         // reused before the merge phase
+  const bool small = n <= g.dl_smem_max;
+  if (small) {
+    // ordering + partition arrays in shared memory (their passes are latency bound in HBM/L2):
+    //   [0,64K) sort keys, later flag + seglo | [64K,156K) xl, yl, sp | [156K,186K) scan | [186K,216K) segn
+    int* base = reinterpret_cast<int*>(dsm);
+    flag = base;
+    seglo = base + SMEM_MAX_POINTS;
+    xl = base + 16384;
+    yl = xl + SMEM_MAX_POINTS;
+    sp = yl + SMEM_MAX_POINTS;
+    scan = sp + SMEM_MAX_POINTS;
+    segn = scan + SMEM_MAX_POINTS;
+  }
   if (tid == 0) info->dt[side][0] = gtime();
 
   // ---- 1. (x,y) order without duplicates, then (y,x) order ------------------------------------
@@ -581,6 +595,11 @@ delaunay_kernel(Geo g, Workspace ws) {
     if (depth & 1) { int* t = xl; xl = sp; sp = t; } else { int* t = yl; yl = sp; sp = t; }
     __syncthreads();
   }
+  if (small) {
+    // the shared memory is recycled for the triangle table: keep the final order in HBM
+    for (int i = tid; i < nu; i += DT) xl_g[i] = xl[i];
+    xl = xl_g;
+  }
   const int* sa = xl;   // Triangle's final sortarray
   if (tid == 0) { info->dt[side][2] = gtime(); info->dmerge_depth = depth; }
 
@@ -597,13 +616,13 @@ delaunay_kernel(Geo g, Workspace ws) {
     for (int i = tid; i < n; i += DT) xy[i] = ((unsigned)px[i] << 16) | (unsigned)py[i];
     m.xy = xy;
     __syncthreads();
-    nt = build_and_emit(m, sa, nu, depth, nodeL, nodeR, flag, tri, s_part);
+    nt = build_and_emit(m, sa, nu, depth, nodeL, nodeR, flag_g, tri, s_part);
   } else {
     MeshG m;
     m.nb = ws.nb[side] + (size_t)frame * g.cap_t * 3;
     m.vx = ws.vx[side] + (size_t)frame * g.cap_t * 3;
     m.x = px; m.y = py;
-    nt = build_and_emit(m, sa, nu, depth, nodeL, nodeR, flag, tri, s_part);
+    nt = build_and_emit(m, sa, nu, depth, nodeL, nodeR, flag_g, tri, s_part);
   }
   if (tid == 0) { info->n_tri[side] = nt; info->dt[side][4] = gtime(); }
 }
