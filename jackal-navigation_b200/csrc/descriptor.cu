@@ -6,28 +6,35 @@
 // pixel at ((v*W+u)*16); pixels outside u in [3,W-4], v in [3,H-4] are 0
 // (the reference leaves them unwritten).
 //
-// Roofline: HBM.  Algorithmic bytes per image = 1*N read + 16*N written; the
-// image tile (+3 px halo) is staged once in shared memory, du/dv never touch
-// HBM, and every warp stores 32 consecutive descriptors = 512 contiguous bytes
+// Roofline: HBM.  Algorithmic bytes per image = 1*N read + 16*N written.  The image tile
+// (+3 px halo) is staged once in shared memory -- by the TMA unit: one 1-D bulk async copy
+// (cp.async.bulk, UBLKCP) per tile row into a 16-byte aligned 96-byte row, completion on an
+// mbarrier; inputs whose stride or base is not 16-byte aligned take a plain-load path.  du/dv
+// never touch HBM, and every warp stores 32 consecutive descriptors = 512 contiguous bytes
 // (one 128-bit store per lane).
 #include "common.cuh"
+#include "blockutil.cuh"
 
 namespace {
 
 constexpr int TW = 64, TH = 16;          // output tile
 constexpr int IW = TW + 6, IH = TH + 6;  // image tile with 3-px halo
 constexpr int GW_ = TW + 4, GH_ = TH + 4; // gradient tile with 2-px halo
-constexpr int IWP = 72;                  // padded row pitches (bytes)
+constexpr int IWP = 96;                  // image tile row: x0-16 .. x0+79 (16-byte aligned for bulk copies)
+constexpr int IOFF = 13;                 // column of pixel x0-3 inside a tile row
 constexpr int GWP = 68;
 
 __device__ __forceinline__ int sat8(int x) { return min(max(x, 0), 255); }
 
 __global__ void __launch_bounds__(256) descriptor_kernel(Geo g, const uint8_t* __restrict__ I1,
                                                          const uint8_t* __restrict__ I2,
-                                                         uint8_t* __restrict__ D1, uint8_t* __restrict__ D2) {
-  __shared__ uint8_t sI[IH * IWP];
+                                                         uint8_t* __restrict__ D1, uint8_t* __restrict__ D2,
+                                                         int tma_ok) {
+  __shared__ __align__(128) uint8_t sIraw[IH * IWP];
   __shared__ uint8_t sU[GH_ * GWP];
   __shared__ uint8_t sV[GH_ * GWP];
+  __shared__ __align__(8) uint64_t s_bar;
+  uint8_t* sI = sIraw + IOFF;   // sI[r * IWP + c] = pixel (x0 - 3 + c, y0 - 3 + r)
 
   const int W = g.W, H = g.H;
   const int frame = blockIdx.z >> 1, side = blockIdx.z & 1;
@@ -36,15 +43,37 @@ __global__ void __launch_bounds__(256) descriptor_kernel(Geo g, const uint8_t* _
   const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
   const int tid = threadIdx.x;
 
-  // 1. image tile, zero outside the image
-  for (int i = tid; i < IH * IW; i += 256) {
-    int r = i / IW, c = i - r * IW;
-    int y = y0 - 3 + r, x = x0 - 3 + c;
-    uint8_t v = 0;
-    if (x >= 0 && x < W && y >= 0 && y < H) v = __ldg(I + (size_t)y * g.bpl + x);
-    sI[r * IWP + c] = v;
+  // 1. image tile.  Pixels outside the image never reach a descriptor that is kept, so only the
+  //    bytes no copy writes are cleared.
+  if (tma_ok) {
+    const int xs = max(x0 - 16, 0), xe = min(x0 + 80, g.bpl & ~15);   // copied byte range of a row
+    const int r0 = max(0, 3 - y0), r1 = min(IH, H + 3 - y0);          // tile rows inside the image
+    if (tid == 0) {
+      mbar_init(&s_bar, 1);
+      fence_mbar_init();
+    }
+    for (int i = tid; i < IH * IWP; i += 256) {
+      const int r = i / IWP, x = x0 - 16 + (i - r * IWP);
+      if (r < r0 || r >= r1 || x < xs || x >= xe) sIraw[i] = 0;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      mbar_arrive_expect_tx(&s_bar, (uint32_t)((r1 - r0) * (xe - xs)));
+      for (int r = r0; r < r1; r++)
+        bulk_g2s(sIraw + r * IWP + (xs - (x0 - 16)), I + (size_t)(y0 - 3 + r) * g.bpl + xs, (uint32_t)(xe - xs),
+                 &s_bar);
+    }
+    mbar_wait(&s_bar, 0);
+  } else {
+    for (int i = tid; i < IH * IW; i += 256) {
+      int r = i / IW, c = i - r * IW;
+      int y = y0 - 3 + r, x = x0 - 3 + c;
+      uint8_t v = 0;
+      if (x >= 0 && x < W && y >= 0 && y < H) v = __ldg(I + (size_t)y * g.bpl + x);
+      sI[r * IWP + c] = v;
+    }
+    __syncthreads();
   }
-  __syncthreads();
 
   // 2. Sobel responses on the gradient tile (origin x0-2, y0-2)
   for (int i = tid; i < GH_ * GW_; i += 256) {
@@ -88,6 +117,9 @@ __global__ void __launch_bounds__(256) descriptor_kernel(Geo g, const uint8_t* _
 
 void launch_descriptor(const Geo& g, int B, const uint8_t* I1, const uint8_t* I2, Workspace& ws, cudaStream_t s) {
   dim3 grid((g.W + TW - 1) / TW, (g.H + TH - 1) / TH, 2 * B);
-  descriptor_kernel<<<grid, 256, 0, s>>>(g, I1, I2, ws.desc[0], ws.desc[1]);
+  // bulk async copies need 16-byte aligned global addresses and sizes
+  const int tma_ok = (g.bpl % 16 == 0) && ((((uintptr_t)I1) | ((uintptr_t)I2)) % 16 == 0) &&
+                     (((size_t)g.bpl * g.H) % 16 == 0);
+  descriptor_kernel<<<grid, 256, 0, s>>>(g, I1, I2, ws.desc[0], ws.desc[1], tma_ok);
   g_jn_launches += 1;
 }
