@@ -128,11 +128,24 @@ __device__ __forceinline__ void match_group(const Geo& g, const int (&u)[KG], in
     }
   }
   if (plo > phi) return;   // no candidate of the group survives the gates
+  bool allok = true;
+#pragma unroll
+  for (int k = 0; k < KG; k++) allok = allok && ok[k];
   // disparity of candidate k at position p:  dir*(p - u[k])  ->  key = e * 65536 + d
   for (int base = plo; base <= phi; base += 32) {
     const int p = min(base + lane, phi);
     const uint4 s0 = rowB_t[p - 2], s1 = rowB_t[p + 2], s2 = rowB_b[p - 2], s3 = rowB_b[p + 2];
-    if (base >= ilo && base + 31 <= ihi) {
+    if (allok && base >= ilo && base + 31 <= ihi) {
+      // common case: every candidate live, chunk inside every range -> straight-line code
+#pragma unroll
+      for (int k = 0; k < KG; k++) {
+        unsigned e = sad16(a[k][0], s0, 0u);
+        e = sad16(a[k][1], s1, e);
+        e = sad16(a[k][2], s2, e);
+        e = sad16(a[k][3], s3, e);
+        best2_update(best[k], e * 65536u + (unsigned)(dir * (p - u[k])));
+      }
+    } else if (base >= ilo && base + 31 <= ihi) {
 #pragma unroll
       for (int k = 0; k < KG; k++) {
         if (!ok[k]) continue;
