@@ -117,27 +117,30 @@ __device__ __forceinline__ void uf_union(int* label, int a, int b) {
   }
 }
 
+// Vertical links.  Pixel (u,v) and the pixel below are linked if both valid and similar.  Only one
+// thread per pair of horizontal runs has to do the union: a thread skips it if its left neighbour
+// makes the same link between the same two runs (both rows continue their runs to the left and
+// the left pixels are vertically similar too).  The left neighbours come from warp shuffles.
 __global__ void seg_merge_kernel(Geo g, Workspace ws, int side) {
   const int frame = blockIdx.z;
   if (ws.info[frame].status != JN_OK) return;
   const int W = g.W, H = g.H;
   const int u = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y;
-  if (u >= W || v + 1 >= H) return;
+  if (v + 1 >= H) return;
   const size_t fp = (size_t)frame * W * H;
   const float* D = ws.Dlr[side] + fp;
-  int* label = ws.label + fp;
+  const float thr = g.p.speckle_sim_threshold;
   const int i = v * W + u;
-  float d = D[i], e = D[i + W];
-  if (d >= 0 && e >= 0 && fabsf(d - e) <= g.p.speckle_sim_threshold) {
-    // only one thread per pair of horizontal runs needs to do the union: skip if my left
-    // neighbour makes the same vertical link between the same two runs
-    if (u > 0 && label[i - 1] >= 0 && label[i + W - 1] >= 0) {
-      float dl = D[i - 1], el = D[i + W - 1];
-      if (fabsf(d - dl) <= g.p.speckle_sim_threshold && fabsf(e - el) <= g.p.speckle_sim_threshold &&
-          fabsf(dl - el) <= g.p.speckle_sim_threshold)
-        return;
-    }
-    uf_union(label, i, i + W);
+  const bool in = u < W;
+  const float d = in ? D[i] : -10.f, e = in ? D[i + W] : -10.f;
+  float dl = __shfl_up_sync(0xffffffffu, d, 1), el = __shfl_up_sync(0xffffffffu, e, 1);
+  if ((threadIdx.x & 31) == 0) {
+    dl = (in && u > 0) ? D[i - 1] : -10.f;
+    el = (in && u > 0) ? D[i + W - 1] : -10.f;
+  }
+  if (d >= 0 && e >= 0 && fabsf(d - e) <= thr) {
+    if (dl >= 0 && el >= 0 && fabsf(d - dl) <= thr && fabsf(e - el) <= thr && fabsf(dl - el) <= thr) return;
+    uf_union(ws.label + fp, i, i + W);
   }
 }
 
