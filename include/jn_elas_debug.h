@@ -53,6 +53,17 @@ typedef struct jn_stage_dump {
 int jn_elas_stages(jn_elas* e, const uint8_t* I1, const uint8_t* I2, const int32_t dims[3],
                    jn_stage_dump* out);
 
+/* Single stages with injected inputs (randomised parity tests): the support filter + compaction on a
+ * caller-supplied candidate image, the Delaunay kernel on caller-supplied integer points, and the
+ * post-processing chain on caller-supplied raw disparity maps. */
+int jn_debug_support_filter(jn_elas* e, const int16_t* dcan, const int32_t dims[3], int16_t* out_incon,
+                            int16_t* out_final, int32_t* support, int32_t cap_support, int32_t* n_support,
+                            int32_t* rounds);
+int jn_debug_triangulate(jn_elas* e, const int32_t* xy, int n, const int32_t dims[3], int32_t* tri,
+                         int32_t cap_tri, int32_t* n_tri);
+int jn_debug_postprocess(jn_elas* e, const float* D1raw, const float* D2raw, const int32_t dims[3],
+                         jn_stage_dump* out);
+
 /* Per-stage device timing of a batch call, CUDA events on the launching stream.
  * Stage order: descriptor, support (match+filter), delaunay, planes+grid, raster,
  * dense match, post-processing. */

@@ -221,6 +221,50 @@ class Elas:
         return o
 
 
+def debug_support_filter(elas, dcan, W, H):
+    """(tests) support filtering + compaction on an injected candidate image."""
+    dcan = np.ascontiguousarray(dcan, np.int16)
+    Hc, Wc = dcan.shape
+    inc = np.zeros_like(dcan); fin = np.zeros_like(dcan)
+    sup = np.zeros((Hc * Wc + 8, 3), np.int32)
+    n = C.c_int32(0); rounds = C.c_int32(0)
+    d = (C.c_int32 * 3)(W, H, W)
+    f = lib().jn_debug_support_filter
+    f.argtypes = [_P, _P, C.POINTER(C.c_int32), _P, _P, _P, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    _check(f(elas._h, _ptr(dcan), d, _ptr(inc), _ptr(fin), _ptr(sup), sup.shape[0], C.byref(n), C.byref(rounds)),
+           "jn_debug_support_filter")
+    return inc, fin, sup[:n.value].copy(), rounds.value
+
+
+def debug_triangulate(elas, xy, W=640, H=480):
+    """(tests) the Delaunay kernel on injected integer points."""
+    xy = np.ascontiguousarray(xy, np.int32)
+    n = xy.shape[0]
+    tri = np.zeros((2 * n + 8, 3), np.int32)
+    nt = C.c_int32(0)
+    d = (C.c_int32 * 3)(W, H, W)
+    f = lib().jn_debug_triangulate
+    f.argtypes = [_P, _P, C.c_int, C.POINTER(C.c_int32), _P, C.c_int32, C.POINTER(C.c_int32)]
+    _check(f(elas._h, _ptr(xy), n, d, _ptr(tri), tri.shape[0], C.byref(nt)), "jn_debug_triangulate")
+    return tri[:nt.value].copy()
+
+
+def debug_postprocess(elas, D1raw, D2raw):
+    """(tests) the post-processing chain on injected raw disparity maps."""
+    D1raw = np.ascontiguousarray(D1raw, np.float32); D2raw = np.ascontiguousarray(D2raw, np.float32)
+    H, W = D1raw.shape
+    o = {k: np.zeros((H, W), np.float32) for k in
+         ("D1_lr", "D2_lr", "D1_seg", "D2_seg", "D1_gap", "D2_gap", "D1_mean", "D2_mean", "D1", "D2")}
+    st = StageDump()
+    for k, a in o.items():
+        setattr(st, k, _ptr(a))
+    d = (C.c_int32 * 3)(W, H, W)
+    f = lib().jn_debug_postprocess
+    f.argtypes = [_P, _P, _P, C.POINTER(C.c_int32), C.POINTER(StageDump)]
+    _check(f(elas._h, _ptr(D1raw), _ptr(D2raw), d, C.byref(st)), "jn_debug_postprocess")
+    return o
+
+
 class Calibration:
     """K1,K2,D1,D2,R,T,XR,XT from the OpenCV YAML + the reprojection matrix Q."""
 

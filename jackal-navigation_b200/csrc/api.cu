@@ -391,6 +391,122 @@ extern "C" int jn_elas_frameinfo(jn_elas* e, int frame, void* out, int bytes) {
   return JN_OK;
 }
 
+// Runs the post-processing chain on ws.Draw of frame slot 0 step by step, copying every stage out.
+static int dump_post(jn_elas* e, jn_stage_dump* o) {
+  const Geo& g = e->g;
+  Workspace& ws = e->ws;
+  const size_t n = (size_t)g.W * g.H;
+  cudaStream_t s = 0;
+  int rc;
+  const int sides = g.p.postprocess_only_left ? 1 : 2;
+  post_lr(g, 1, ws, s);
+  if ((rc = d2h(o->D1_lr, ws.Dlr[0], n))) return rc;
+  if ((rc = d2h(o->D2_lr, ws.Dlr[1], n))) return rc;
+  for (int k = 0; k < sides; k++) post_segments(g, 1, ws, k, s);
+  if ((rc = d2h(o->D1_seg, ws.Dlr[0], n))) return rc;
+  if ((rc = d2h(o->D2_seg, ws.Dlr[1], n))) return rc;
+  for (int k = 0; k < sides; k++) post_gap(g, 1, ws, k, s);
+  if ((rc = d2h(o->D1_gap, ws.Dlr[0], n))) return rc;
+  if ((rc = d2h(o->D2_gap, ws.Dlr[1], n))) return rc;
+  const float* cur[2] = {ws.Dlr[0], ws.Dlr[1]};
+  if (g.p.filter_adaptive_mean)
+    for (int k = 0; k < sides; k++) {
+      post_mean(g, 1, ws, cur[k], ws.Dtmp[k], ws.Dtmp2[k], n, s);
+      cur[k] = ws.Dtmp2[k];
+    }
+  if ((rc = d2h(o->D1_mean, cur[0], n))) return rc;
+  if ((rc = d2h(o->D2_mean, cur[1], n))) return rc;
+  if (g.p.filter_median)
+    for (int k = 0; k < sides; k++) {
+      post_median(g, 1, ws, cur[k], ws.Dtmp[k], e->dD[k], n, s);
+      cur[k] = e->dD[k];
+    }
+  if ((rc = d2h(o->D1, cur[0], n))) return rc;
+  if ((rc = d2h(o->D2, cur[1], n))) return rc;
+  JN_CUDA_CHECK(cudaGetLastError());
+  return JN_OK;
+}
+
+
+// ---- single stages with injected inputs (randomised parity tests) ---------------------------------
+// Support filtering + compaction on a caller-supplied candidate image (Hc x Wc int16).
+extern "C" int jn_debug_support_filter(jn_elas* e, const int16_t* dcan, const int32_t dims[3], int16_t* out_incon,
+                                       int16_t* out_final, int32_t* support, int32_t cap_support, int32_t* n_support,
+                                       int32_t* rounds) {
+  if (!e || !dcan || !dims) return JN_ERR_ARG;
+  int rc = ensure_workspace(e, dims, 1);
+  if (rc) return rc;
+  const Geo& g = e->g;
+  Workspace& ws = e->ws;
+  const size_t np = (size_t)g.Wc * g.Hc;
+  JN_CUDA_CHECK(cudaMemcpy(ws.dcan, dcan, np * sizeof(int16_t), cudaMemcpyHostToDevice));
+  rc = launch_support_filter(g, 1, ws, 0);
+  if (rc) return rc;
+  JN_CUDA_CHECK(cudaDeviceSynchronize());
+  if ((rc = d2h(out_incon, ws.dcan_incon, np))) return rc;
+  if ((rc = d2h(out_final, ws.dcan_final, np))) return rc;
+  FrameInfo info;
+  JN_CUDA_CHECK(cudaMemcpy(&info, ws.info, sizeof(info), cudaMemcpyDeviceToHost));
+  if (n_support) *n_support = info.n_support;
+  if (rounds) *rounds = info.incon_rounds;
+  if (support && info.n_support <= cap_support) {
+    std::vector<int32_t> s4((size_t)info.n_support * 4);
+    JN_CUDA_CHECK(cudaMemcpy(s4.data(), ws.sup, s4.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < info.n_support; i++)
+      for (int k = 0; k < 3; k++) support[3 * i + k] = s4[4 * (size_t)i + k];
+  }
+  return JN_OK;
+}
+
+// Delaunay triangulation of caller-supplied integer points (x,y pairs, 0 <= x,y < 8192).
+extern "C" int jn_debug_triangulate(jn_elas* e, const int32_t* xy, int n, const int32_t dims[3], int32_t* tri,
+                                    int32_t cap_tri, int32_t* n_tri) {
+  if (!e || !xy || !dims || n < 0) return JN_ERR_ARG;
+  int rc = ensure_workspace(e, dims, 1);
+  if (rc) return rc;
+  const Geo& g = e->g;
+  Workspace& ws = e->ws;
+  if (n > g.cap_s) return JN_ERR_ARG;
+  std::vector<int32_t> x(n), y(n);
+  for (int i = 0; i < n; i++) { x[i] = xy[2 * i]; y[i] = xy[2 * i + 1]; }
+  JN_CUDA_CHECK(cudaMemcpy(ws.px[0], x.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice));
+  JN_CUDA_CHECK(cudaMemcpy(ws.px[1], x.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice));
+  JN_CUDA_CHECK(cudaMemcpy(ws.py, y.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice));
+  FrameInfo info;
+  memset(&info, 0, sizeof(info));
+  info.n_support = n;
+  info.status = JN_OK;
+  JN_CUDA_CHECK(cudaMemcpy(ws.info, &info, sizeof(info), cudaMemcpyHostToDevice));
+  rc = launch_delaunay(g, 1, ws, 0);
+  if (rc) return rc;
+  JN_CUDA_CHECK(cudaDeviceSynchronize());
+  JN_CUDA_CHECK(cudaMemcpy(&info, ws.info, sizeof(info), cudaMemcpyDeviceToHost));
+  if (info.status != JN_OK) return info.status;
+  *n_tri = info.n_tri[0];
+  if (info.n_tri[0] <= cap_tri) return d2h(tri, ws.tri[0], (size_t)info.n_tri[0] * 3);
+  return JN_OK;
+}
+
+// Post-processing chain (elas.cpp:108-140) on caller-supplied raw disparity maps.
+extern "C" int jn_debug_postprocess(jn_elas* e, const float* D1raw, const float* D2raw, const int32_t dims[3],
+                                    jn_stage_dump* o) {
+  if (!e || !D1raw || !D2raw || !dims || !o) return JN_ERR_ARG;
+  int rc = ensure_workspace(e, dims, 1);
+  if (rc) return rc;
+  rc = ensure_staging(e, dims);
+  if (rc) return rc;
+  const Geo& g = e->g;
+  Workspace& ws = e->ws;
+  const size_t n = (size_t)g.W * g.H;
+  JN_CUDA_CHECK(cudaMemcpy(ws.Draw[0], D1raw, n * sizeof(float), cudaMemcpyHostToDevice));
+  JN_CUDA_CHECK(cudaMemcpy(ws.Draw[1], D2raw, n * sizeof(float), cudaMemcpyHostToDevice));
+  FrameInfo info;
+  memset(&info, 0, sizeof(info));
+  info.status = JN_OK;
+  JN_CUDA_CHECK(cudaMemcpy(ws.info, &info, sizeof(info), cudaMemcpyHostToDevice));
+  return dump_post(e, o);
+}
+
 extern "C" int jn_elas_stages(jn_elas* e, const uint8_t* I1, const uint8_t* I2, const int32_t dims[3],
                               jn_stage_dump* o) {
   if (!e || !I1 || !I2 || !dims || !o) return JN_ERR_ARG;
@@ -446,33 +562,7 @@ extern "C" int jn_elas_stages(jn_elas* e, const uint8_t* I1, const uint8_t* I2, 
   if ((rc = d2h(o->D1_raw, ws.Draw[0], n))) return rc;
   if ((rc = d2h(o->D2_raw, ws.Draw[1], n))) return rc;
 
-  const int sides = g.p.postprocess_only_left ? 1 : 2;
-  post_lr(g, 1, ws, s);
-  if ((rc = d2h(o->D1_lr, ws.Dlr[0], n))) return rc;
-  if ((rc = d2h(o->D2_lr, ws.Dlr[1], n))) return rc;
-  for (int k = 0; k < sides; k++) post_segments(g, 1, ws, k, s);
-  if ((rc = d2h(o->D1_seg, ws.Dlr[0], n))) return rc;
-  if ((rc = d2h(o->D2_seg, ws.Dlr[1], n))) return rc;
-  for (int k = 0; k < sides; k++) post_gap(g, 1, ws, k, s);
-  if ((rc = d2h(o->D1_gap, ws.Dlr[0], n))) return rc;
-  if ((rc = d2h(o->D2_gap, ws.Dlr[1], n))) return rc;
-  const float* cur[2] = {ws.Dlr[0], ws.Dlr[1]};
-  if (g.p.filter_adaptive_mean)
-    for (int k = 0; k < sides; k++) {
-      post_mean(g, 1, ws, cur[k], ws.Dtmp[k], ws.Dtmp2[k], n, s);
-      cur[k] = ws.Dtmp2[k];
-    }
-  if ((rc = d2h(o->D1_mean, cur[0], n))) return rc;
-  if ((rc = d2h(o->D2_mean, cur[1], n))) return rc;
-  if (g.p.filter_median)
-    for (int k = 0; k < sides; k++) {
-      post_median(g, 1, ws, cur[k], ws.Dtmp[k], e->dD[k], n, s);
-      cur[k] = e->dD[k];
-    }
-  if ((rc = d2h(o->D1, cur[0], n))) return rc;
-  if ((rc = d2h(o->D2, cur[1], n))) return rc;
-  JN_CUDA_CHECK(cudaGetLastError());
-  return JN_OK;
+  return dump_post(e, o);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -506,6 +506,12 @@ int launch_support(const Geo& g, int B, Workspace& ws, cudaStream_t s) {
     attr_set = true;
   }
   support_match_kernel<<<dim3(g.Hc, B), MATCH_THREADS, smem, s>>>(g, ws.desc[0], ws.desc[1], ws.dcan);
+  g_jn_launches += 1;
+  return launch_support_filter(g, B, ws, s);
+}
+
+// Filtering + compaction of the candidate images in ws.dcan (also driven directly by the tests).
+int launch_support_filter(const Geo& g, int B, Workspace& ws, cudaStream_t s) {
   dim3 cb(32, 8), cg((g.Wc + 31) / 32, (g.Hc + 7) / 8, B);
   incon_count_kernel<<<cg, cb, 0, s>>>(g, ws.dcan, ws.cnt);
   const size_t wk_bytes = (size_t)g.Wc * g.Hc * sizeof(int16_t);
@@ -519,6 +525,6 @@ int launch_support(const Geo& g, int B, Workspace& ws, cudaStream_t s) {
   support_filter_kernel<<<B, FILT_THREADS, use_smem ? wk_bytes : 0, s>>>(
       g, ws.dcan, ws.cnt, ws.frontier, ws.dcan_incon, ws.dcan_final, ws.sup, ws.px[0], ws.px[1], ws.py, ws.info,
       use_smem);
-  g_jn_launches += 3;
+  g_jn_launches += 2;
   return JN_OK;
 }
