@@ -55,12 +55,13 @@ static void sobel_port(const uint8_t* I, int w, int h, int stride, uint8_t* du, 
 
 /* 16 bytes per pixel for u in [3,w-4], v in [3,h-4]; everything else 0 (H1).
  * Sample pattern: descriptor.cpp:92-110. */
-int port_descriptor(const uint8_t* I, int w, int h, int stride, uint8_t* desc) {
+/* half != 0: only rows 4, 6, 8, ... are computed (descriptor.cpp:48-78), the others stay 0. */
+static int descriptor_port(const uint8_t* I, int w, int h, int stride, uint8_t* desc, int half) {
   uint8_t* du = (uint8_t*)malloc((size_t)w * h);
   uint8_t* dv = (uint8_t*)malloc((size_t)w * h);
   sobel_port(I, w, h, stride, du, dv);
   memset(desc, 0, (size_t)16 * w * h);
-  for (int v = 3; v < h - 3; v++) {
+  for (int v = half ? 4 : 3; v < h - 3; v += half ? 2 : 1) {
     const uint8_t* u0 = du + (size_t)(v - 2) * w;
     const uint8_t* u1 = du + (size_t)(v - 1) * w;
     const uint8_t* u2 = du + (size_t)v * w;
@@ -82,6 +83,10 @@ int port_descriptor(const uint8_t* I, int w, int h, int stride, uint8_t* desc) {
   free(du);
   free(dv);
   return 0;
+}
+
+int port_descriptor(const uint8_t* I, int w, int h, int stride, uint8_t* desc) {
+  return descriptor_port(I, w, h, stride, desc, 0);
 }
 
 static inline int sad16(const uint8_t* a, const uint8_t* b) {
@@ -337,7 +342,8 @@ static void find_match(const jn_elas_params* p, int w, int h, int u, int v, floa
     cnt->evals++;
     if (val < min_val) { min_val = val; min_d = d; }
   }
-  D[(size_t)v * w + u] = (min_d >= 0) ? (float)min_d : -1.0f;
+  size_t d_addr = p->subsampling ? (size_t)(v / 2) * (w / 2) + (u / 2) : (size_t)v * w + u;
+  D[d_addr] = (min_d >= 0) ? (float)min_d : -1.0f;
 }
 
 static inline int32_t f2u_lo32(float x) { return (int32_t)(uint32_t)(int64_t)x; } /* H6 */
@@ -348,7 +354,9 @@ static void dense_port(const jn_elas_params* p, int w, int h, const uint8_t* des
                        const int32_t* grid, int right_image, float* D, dense_count* cnt) {
   int disp_num = p->disp_max + 1;
   int gw = (int)ceilf((float)w / (float)p->grid_size);
-  for (size_t i = 0; i < (size_t)w * h; i++) D[i] = -10;
+  const int sub = p->subsampling;
+  const size_t nd = sub ? (size_t)(w / 2) * (h / 2) : (size_t)w * h;
+  for (size_t i = 0; i < nd; i++) D[i] = -10;
   int32_t* P = (int32_t*)malloc(sizeof(int32_t) * disp_num);
   int plane_radius;
   prior_table(p, disp_num, P, &plane_radius);
@@ -378,15 +386,19 @@ static void dense_port(const jn_elas_params* p, int w, int h, const uint8_t* des
     int valid = fabs(pa) < 0.7 && fabs(pd) < 0.7;
     if ((int)Au != (int)Bu)
       for (int u = IMAX((int)Au, 0); u < IMIN((int)Bu, w); u++) {
+        if (sub && u % 2) continue;
         int v1 = f2u_lo32(ACa * (float)u + ACb), v2 = f2u_lo32(ABa * (float)u + ABb);
         for (int v = IMIN(v1, v2); v < IMAX(v1, v2); v++)
+          if (!sub || v % 2 == 0)
           find_match(p, w, h, u, v, pa, pb, pc, grid, gw, disp_num, desc1, desc2, P, plane_radius, valid,
                      right_image, D, cnt);
       }
     if ((int)Bu != (int)Cu)
       for (int u = IMAX((int)Bu, 0); u < IMIN((int)Cu, w); u++) {
+        if (sub && u % 2) continue;
         int v1 = f2u_lo32(ACa * (float)u + ACb), v2 = f2u_lo32(BCa * (float)u + BCb);
         for (int v = IMIN(v1, v2); v < IMAX(v1, v2); v++)
+          if (!sub || v % 2 == 0)
           find_match(p, w, h, u, v, pa, pb, pc, grid, gw, disp_num, desc1, desc2, P, plane_radius, valid,
                      right_image, D, cnt);
       }
@@ -414,6 +426,7 @@ void port_prior(const jn_elas_params* p, int32_t* P_out, int32_t* plane_radius_o
 
 /* leftRightConsistencyCheck (elas.cpp:909-979) */
 static void lr_check(const jn_elas_params* p, int w, int h, float* D1, float* D2) {
+  const int sub = p->subsampling;   /* w,h are the map dimensions (already halved) */
   size_t n = (size_t)w * h;
   float* c1 = (float*)malloc(n * sizeof(float));
   float* c2 = (float*)malloc(n * sizeof(float));
@@ -423,7 +436,7 @@ static void lr_check(const jn_elas_params* p, int w, int h, float* D1, float* D2
     for (int v = 0; v < h; v++) {
       size_t a = (size_t)v * w + u;
       float d1 = c1[a], d2 = c2[a];
-      float uw1 = (float)u - d1, uw2 = (float)u + d2;
+      float uw1 = sub ? (float)u - d1 / 2 : (float)u - d1, uw2 = sub ? (float)u + d2 / 2 : (float)u + d2;
       if (d1 >= 0 && uw1 >= 0 && uw1 < w) {
         if (fabs(c2[(size_t)v * w + (int)uw1] - d1) > p->lr_threshold) D1[a] = -10;
       } else D1[a] = -10;
@@ -437,6 +450,8 @@ static void lr_check(const jn_elas_params* p, int w, int h, float* D1, float* D2
 
 /* removeSmallSegments (elas.cpp:981-1099): breadth-first flood fill, seeds u outer / v inner */
 static void remove_small_segments(const jn_elas_params* p, int w, int h, float* D) {
+  /* elas.cpp:986-991: at half resolution the size limit becomes (int)(sqrt(speckle_size)*2) */
+  const int speckle_size = p->subsampling ? (int)(sqrtf((float)p->speckle_size) * 2) : p->speckle_size;
   size_t n = (size_t)w * h;
   uint8_t* done = (uint8_t*)calloc(n, 1);
   int32_t* list = (int32_t*)malloc(n * sizeof(int32_t));
@@ -461,7 +476,7 @@ static void remove_small_segments(const jn_elas_params* p, int w, int h, float* 
         curr++;
         done[a] = 1;
       }
-      if (count < p->speckle_size)
+      if (count < speckle_size)
         for (int i = 0; i < count; i++) D[list[i]] = -10;
     }
   free(done);
@@ -470,7 +485,7 @@ static void remove_small_segments(const jn_elas_params* p, int w, int h, float* 
 
 /* one line of gapInterpolation (elas.cpp:1122-1199 rows, 1203-1283 columns) */
 static void gap_line(const jn_elas_params* p, float* D, int len, size_t stride) {
-  int gap = p->ipol_gap_width, count = 0;
+  int gap = p->subsampling ? p->ipol_gap_width / 2 + 1 : p->ipol_gap_width, count = 0;   /* elas.cpp:1106-1111 */
   for (int i = 0; i < len; i++) {
     if (D[i * stride] >= 0) {
       if (count >= 1 && count <= gap) {
@@ -532,6 +547,55 @@ static inline int mean8(const float win[8], float centre, float* out) {
     if (d >= 0) { *out = d; return 1; }
   }
   return 0;
+}
+
+/* one output of the 4-tap filter of the half-resolution branch (elas.cpp:1339-1355) */
+static inline int mean4(const float win[4], float centre, float* out) {
+  float wgt[4], fac[4];
+  for (int k = 0; k < 4; k++) {
+    float t = 4.0f - buggy_abs(win[k] - centre);
+    wgt[k] = t > 0.0f ? t : 0.0f;
+    fac[k] = win[k] * wgt[k];
+  }
+  float ws = wgt[0] + wgt[1] + wgt[2] + wgt[3];
+  float fs = fac[0] + fac[1] + fac[2] + fac[3];
+  if (ws > 0) {
+    float d = fs / ws;
+    if (d >= 0) { *out = d; return 1; }
+  }
+  return 0;
+}
+
+/* adaptiveMean, half resolution branch (elas.cpp:1323-1391): window = last 4 samples, centre u-1 */
+static void adaptive_mean_half(int w, int h, float* D) {
+  size_t n = (size_t)w * h;
+  float* cp = (float*)malloc(n * sizeof(float));
+  float* tmp = (float*)calloc(n, sizeof(float)); /* H1: unwritten = 0 */
+  memcpy(cp, D, n * sizeof(float));
+  for (size_t i = 0; i < n; i++)
+    if (D[i] < 0) { cp[i] = -10; tmp[i] = -10; }
+  float win[4];
+  if (w >= 4)
+    for (int v = 3; v < h - 3; v++) {
+      const float* row = cp + (size_t)v * w;
+      for (int u = 0; u < 3; u++) win[u] = row[u];
+      for (int u = 3; u < w; u++) {
+        win[u % 4] = row[u];
+        float o;
+        if (mean4(win, row[u - 1], &o)) tmp[(size_t)v * w + (u - 1)] = o;
+      }
+    }
+  if (h >= 4)
+    for (int u = 3; u < w - 3; u++) {
+      for (int v = 0; v < 3; v++) win[v] = tmp[(size_t)v * w + u];
+      for (int v = 3; v < h; v++) {
+        win[v % 4] = tmp[(size_t)v * w + u];
+        float o;
+        if (mean4(win, tmp[(size_t)(v - 1) * w + u], &o)) D[(size_t)(v - 1) * w + u] = o;
+      }
+    }
+  free(cp);
+  free(tmp);
 }
 
 /* adaptiveMean, full resolution branch (elas.cpp:1287-1320, 1394-1492) */
@@ -600,6 +664,7 @@ static void put(float* dst, const float* src, size_t n) {
 
 /* elas.cpp:108-140 */
 void port_postprocess(const jn_elas_params* p, int w, int h, float* D1, float* D2, oracle_stages* st) {
+  if (p->subsampling) { w /= 2; h /= 2; }   /* the maps are (w/2) x (h/2), elas.cpp:914-917 */
   size_t n = (size_t)w * h;
   lr_check(p, w, h, D1, D2);
   if (st) { put(st->D1_lr, D1, n); put(st->D2_lr, D2, n); }
@@ -610,8 +675,8 @@ void port_postprocess(const jn_elas_params* p, int w, int h, float* D1, float* D
   if (!p->postprocess_only_left) gap_interpolation(p, w, h, D2);
   if (st) { put(st->D1_gap, D1, n); put(st->D2_gap, D2, n); }
   if (p->filter_adaptive_mean) {
-    adaptive_mean(w, h, D1);
-    if (!p->postprocess_only_left) adaptive_mean(w, h, D2);
+    if (p->subsampling) adaptive_mean_half(w, h, D1); else adaptive_mean(w, h, D1);
+    if (!p->postprocess_only_left) { if (p->subsampling) adaptive_mean_half(w, h, D2); else adaptive_mean(w, h, D2); }
   }
   if (st) { put(st->D1_mean, D1, n); put(st->D2_mean, D2, n); }
   if (p->filter_median) {
@@ -639,17 +704,17 @@ static int triangulate_support(const int32_t* s, int n, int right_image, int32_t
 
 int port_elas_stages(const jn_elas_params* p, const uint8_t* I1, const uint8_t* I2, const int32_t* dims,
                      oracle_stages* st) {
-  if (p->subsampling) return -3;
   int w = dims[0], h = dims[1], stride = dims[2];
   size_t n = (size_t)w * h;
   uint8_t* desc1 = (uint8_t*)malloc(16 * n);
   uint8_t* desc2 = (uint8_t*)malloc(16 * n);
-  port_descriptor(I1, w, h, stride, desc1);
-  port_descriptor(I2, w, h, stride, desc2);
+  descriptor_port(I1, w, h, stride, desc1, p->subsampling);
+  descriptor_port(I2, w, h, stride, desc2, p->subsampling);
   if (st->desc1) memcpy(st->desc1, desc1, 16 * n);
   if (st->desc2) memcpy(st->desc2, desc2, 16 * n);
 
   int step = p->candidate_stepsize;
+  if (p->subsampling) step += step % 2;   /* only every second line has descriptors (elas.cpp:379-381) */
   int wc = (w + step - 1) / step, hc = (h + step - 1) / step;
   int16_t* dc = (int16_t*)calloc((size_t)wc * hc, sizeof(int16_t)); /* row 0 / col 0 stay 0 (H3) */
   for (int uc = 1; uc < wc; uc++)
@@ -720,8 +785,9 @@ int port_elas_stages(const jn_elas_params* p, const uint8_t* I1, const uint8_t* 
     dense_port(p, w, h, desc1, desc2, s, tri2, pl2, nt2, g2, 1, D2, &cnt);
     st->dense_evals = cnt.evals;
     st->dense_pixels = cnt.pixels;
-    put(st->D1_raw, D1, n);
-    put(st->D2_raw, D2, n);
+    const size_t nd = p->subsampling ? (size_t)(w / 2) * (h / 2) : n;
+    put(st->D1_raw, D1, nd);
+    put(st->D2_raw, D2, nd);
     port_postprocess(p, w, h, D1, D2, st);
     free(D1); free(D2); free(g1); free(g2); free(pl1); free(pl2); free(tri1); free(tri2);
   }
@@ -740,6 +806,7 @@ int port_elas_process(const jn_elas_params* p, const uint8_t* I1, const uint8_t*
   st.D1 = a;
   st.D2 = b;
   int rc = port_elas_stages(p, I1, I2, dims, &st);
+  if (p->subsampling) n = (size_t)(dims[0] / 2) * (dims[1] / 2);
   if (rc == 0) { memcpy(D1, a, n * sizeof(float)); memcpy(D2, b, n * sizeof(float)); }
   free(a);
   free(b);

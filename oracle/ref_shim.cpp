@@ -17,10 +17,25 @@
 #include <stdlib.h>
 #include <vector>
 
+#include <algorithm>
+#include <math.h>
+#include <pmmintrin.h>
+
 #define private public
 #include "elas.h"
 #undef private
+#include "descriptor.h"
+#include "matrix.h"
+#include "filter.h"
+
+/* adaptiveMean (elas.cpp:1297-1298) reads rows of D_tmp it never wrote.  Every header the
+ * reference pulls in has been seen above, so this only rewrites the malloc CALLS inside elas.cpp:
+ * its scratch buffers start zeroed, which is what a fresh mmap'd block gives the stock build and what
+ * the port and the CUDA path define those reads to be.  (ref_set_deterministic_heap below covers the
+ * separately compiled descriptor.cpp the same way for blocks glibc serves from fresh pages.) */
+#define malloc(n) calloc(1, (n))
 #include "elas.cpp"          /* reference translation unit, in place */
+#undef malloc
 
 #include "oracle_abi.h"
 

@@ -71,6 +71,17 @@ def lattice_dims(W, H, step=5):
     return (W + step - 1) // step, (H + step - 1) // step
 
 
+def effective_step(p):
+    """elas.cpp:379-381: with subsampling only even rows carry descriptors, so an odd step is bumped."""
+    s = p.candidate_stepsize
+    return s + s % 2 if p.subsampling else s
+
+
+def map_dims(p, W, H):
+    """(rows, cols) of the disparity maps (elas.cpp:58-63 of main.cpp / elas.h:120-124)."""
+    return (H // 2, W // 2) if p.subsampling else (H, W)
+
+
 def grid_dims(W, H, gs=20):
     return int(math.ceil(np.float32(W) / np.float32(gs))), int(math.ceil(np.float32(H) / np.float32(gs)))
 
@@ -110,8 +121,9 @@ class Oracle:
         H, W = I1.shape
         I1 = np.ascontiguousarray(I1)
         I2 = np.ascontiguousarray(I2)
-        D1 = np.zeros((H, W), np.float32)
-        D2 = np.zeros((H, W), np.float32)
+        Hd, Wd = map_dims(p, W, H)
+        D1 = np.zeros((Hd, Wd), np.float32)
+        D2 = np.zeros((Hd, Wd), np.float32)
         dims = (C.c_int32 * 3)(W, H, W)
         self.fn("elas_process")(C.byref(p), _ptr(I1), _ptr(I2), _ptr(D1), _ptr(D2), dims)
         return D1, D2
@@ -121,8 +133,9 @@ class Oracle:
         H, W = I1.shape
         I1 = np.ascontiguousarray(I1)
         I2 = np.ascontiguousarray(I2)
-        Wc, Hc = lattice_dims(W, H, p.candidate_stepsize)
+        Wc, Hc = lattice_dims(W, H, effective_step(p))
         gw, gh = grid_dims(W, H, p.grid_size)
+        Hd, Wd = map_dims(p, W, H)
         cap_s = Wc * Hc + 8
         cap_t = 2 * cap_s + 8
         o = {}
@@ -161,6 +174,10 @@ class Oracle:
             o["planes2"] = o["planes2"][:st.n_tri2]
         o["dense_evals"] = st.dense_evals
         o["dense_pixels"] = st.dense_pixels
+        if p.subsampling:   # the maps are (H/2) x (W/2), stored contiguously at the front of each buffer
+            for k in ("D1_raw", "D2_raw", "D1_lr", "D2_lr", "D1_seg", "D2_seg", "D1_gap", "D2_gap",
+                      "D1_mean", "D2_mean", "D1", "D2"):
+                o[k] = o[k].reshape(-1)[:Hd * Wd].reshape(Hd, Wd).copy()
         return o
 
     # ---- single stages with injected inputs ------------------------------
