@@ -161,15 +161,23 @@ class Elas:
         """Elas::process(I1, I2, D1, D2, dims) with numpy host arrays (elas.h:162).
 
         Returns JN_OK or JN_FEW_SUPPORT; in the latter case D1/D2 are untouched and the
-        reference's message is printed (elas.cpp:66-71)."""
+        reference's message is printed (elas.cpp:66-71).  With param.subsampling the maps are
+        (H/2) x (W/2) (elas.h:160-162)."""
         for a, dt in ((I1, np.uint8), (I2, np.uint8), (D1, np.float32), (D2, np.float32)):
             if not (isinstance(a, np.ndarray) and a.dtype == dt and a.flags["C_CONTIGUOUS"]):
                 raise TypeError("process expects C-contiguous numpy arrays (uint8 images, float32 maps)")
         d = (C.c_int32 * 3)(*[int(x) for x in dims])
+        Hd, Wd = self.map_shape(d[0], d[1])
+        if D1.size < Hd * Wd or D2.size < Hd * Wd:
+            raise ValueError("disparity maps must hold %d x %d floats" % (Hd, Wd))
         rc = _check(lib().jn_elas_process(self._h, _ptr(I1), _ptr(I2), _ptr(D1), _ptr(D2), d), "jn_elas_process")
         if rc == JN_FEW_SUPPORT:
             print("ERROR: Need at least 3 support points!")
         return rc
+
+    def map_shape(self, W, H):
+        """(rows, cols) of the disparity maps for W x H images."""
+        return (H // 2, W // 2) if self.param.subsampling else (H, W)
 
     def process_batch(self, I1, I2, D1, D2, status, dims, n, stream=0):
         """Device pointers (ints), frame-major batch of n frames; asynchronous on `stream`."""
@@ -183,6 +191,9 @@ class Elas:
         H, W = I1.shape
         p = self.param
         step, gs = p.candidate_stepsize, p.grid_size
+        if p.subsampling:
+            step += step % 2          # elas.cpp:379-381
+        Hd, Wd = self.map_shape(W, H)
         Wc, Hc = (W + step - 1) // step, (H + step - 1) // step
         gw = int(np.ceil(np.float32(W) / np.float32(gs)))
         gh = int(np.ceil(np.float32(H) / np.float32(gs)))
@@ -205,7 +216,7 @@ class Elas:
             o["grid2"] = np.zeros((gh, gw, p.disp_max + 2), np.int32)
         for k in ("D1_raw", "D2_raw", "D1_lr", "D2_lr", "D1_seg", "D2_seg", "D1_gap", "D2_gap",
                   "D1_mean", "D2_mean", "D1", "D2"):
-            o[k] = np.zeros((H, W), np.float32)
+            o[k] = np.zeros((Hd, Wd), np.float32)
         st = StageDump()
         for k, a in o.items():
             setattr(st, k, _ptr(a))
@@ -258,6 +269,8 @@ def debug_postprocess(elas, D1raw, D2raw):
     st = StageDump()
     for k, a in o.items():
         setattr(st, k, _ptr(a))
+    if elas.param.subsampling:      # the injected maps are the half-resolution ones
+        W, H = 2 * W, 2 * H
     d = (C.c_int32 * 3)(W, H, W)
     f = lib().jn_debug_postprocess
     f.argtypes = [_P, _P, _P, C.POINTER(C.c_int32), C.POINTER(StageDump)]

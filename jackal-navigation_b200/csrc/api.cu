@@ -138,14 +138,19 @@ static int make_geo(const jn_elas_params& p, const int32_t dims[3], Geo* out) {
   g.p = p;
   g.W = dims[0]; g.H = dims[1]; g.bpl = dims[2];
   if (g.W < 16 || g.H < 16 || g.bpl < g.W) { jn_set_error("bad dims %dx%d stride %d", g.W, g.H, g.bpl); return JN_ERR_ARG; }
-  if (p.subsampling) { jn_set_error("subsampling=1 is not built yet"); return JN_ERR_UNSUPPORTED; }
   if (p.disp_max < 10 || p.disp_max > 4095 || p.disp_min > p.disp_max || p.candidate_stepsize < 1 ||
       p.grid_size < 1 || p.incon_window_size < 0 || p.incon_window_size > 16) {
     jn_set_error("parameter out of the supported range");
     return JN_ERR_ARG;
   }
   if (g.W >= 8192 || g.H >= 8192) { jn_set_error("image too large for the 64-bit exact predicates"); return JN_ERR_UNSUPPORTED; }
-  const int step = p.candidate_stepsize;
+  // subsampling: only every second line has descriptors, an odd lattice step is bumped (elas.cpp:379-381)
+  if (p.subsampling) g.p.candidate_stepsize += g.p.candidate_stepsize % 2;
+  g.Wd = p.subsampling ? g.W / 2 : g.W;
+  g.Hd = p.subsampling ? g.H / 2 : g.H;
+  g.speckle_eff = p.subsampling ? (int)(sqrtf((float)p.speckle_size) * 2) : p.speckle_size;
+  g.gap_eff = p.subsampling ? p.ipol_gap_width / 2 + 1 : p.ipol_gap_width;
+  const int step = g.p.candidate_stepsize;
   g.Wc = (g.W + step - 1) / step;
   g.Hc = (g.H + step - 1) / step;
   g.gw = (int)ceilf((float)g.W / (float)p.grid_size);
@@ -272,7 +277,7 @@ static int run_pipeline(jn_elas* e, int B, const uint8_t* I1, const uint8_t* I2,
   const Geo& g = e->g;
   const bool prof = e->profile != 0;
   const int Bb = (e->split && !prof && B >= 2 && e->ws2.B >= B / 2) ? B / 2 : 0, Ba = B - Bb;
-  const size_t n = (size_t)g.W * g.H, ibytes = (size_t)g.bpl * g.H;
+  const size_t n = (size_t)g.Wd * g.Hd, ibytes = (size_t)g.bpl * g.H;
   if (Bb) {
     JN_CUDA_CHECK(cudaEventRecord(e->ev_fork, s));
     JN_CUDA_CHECK(cudaStreamWaitEvent(e->aux, e->ev_fork, 0));
@@ -344,7 +349,7 @@ extern "C" int jn_elas_process(jn_elas* e, const uint8_t* I1, const uint8_t* I2,
   if (rc) return rc;
   rc = ensure_staging(e, dims);
   if (rc) return rc;
-  const size_t npix = (size_t)dims[0] * dims[1], nbytes = (size_t)dims[2] * dims[1];
+  const size_t npix = (size_t)e->g.Wd * e->g.Hd, nbytes = (size_t)dims[2] * dims[1];
   JN_CUDA_CHECK(cudaMemcpyAsync(e->dI[0], I1, nbytes, cudaMemcpyHostToDevice, 0));
   JN_CUDA_CHECK(cudaMemcpyAsync(e->dI[1], I2, nbytes, cudaMemcpyHostToDevice, 0));
   rc = run_pipeline(e, 1, e->dI[0], e->dI[1], e->dD[0], e->dD[1], e->dStatus, 0);
@@ -395,7 +400,7 @@ extern "C" int jn_elas_frameinfo(jn_elas* e, int frame, void* out, int bytes) {
 static int dump_post(jn_elas* e, jn_stage_dump* o) {
   const Geo& g = e->g;
   Workspace& ws = e->ws;
-  const size_t n = (size_t)g.W * g.H;
+  const size_t n = (size_t)g.Wd * g.Hd;
   cudaStream_t s = 0;
   int rc;
   const int sides = g.p.postprocess_only_left ? 1 : 2;
@@ -497,7 +502,7 @@ extern "C" int jn_debug_postprocess(jn_elas* e, const float* D1raw, const float*
   if (rc) return rc;
   const Geo& g = e->g;
   Workspace& ws = e->ws;
-  const size_t n = (size_t)g.W * g.H;
+  const size_t n = (size_t)g.Wd * g.Hd;
   JN_CUDA_CHECK(cudaMemcpy(ws.Draw[0], D1raw, n * sizeof(float), cudaMemcpyHostToDevice));
   JN_CUDA_CHECK(cudaMemcpy(ws.Draw[1], D2raw, n * sizeof(float), cudaMemcpyHostToDevice));
   FrameInfo info;
@@ -559,8 +564,8 @@ extern "C" int jn_elas_stages(jn_elas* e, const uint8_t* I1, const uint8_t* I2, 
 
   launch_dense(g, 1, ws, s);
   JN_CUDA_CHECK(cudaDeviceSynchronize());
-  if ((rc = d2h(o->D1_raw, ws.Draw[0], n))) return rc;
-  if ((rc = d2h(o->D2_raw, ws.Draw[1], n))) return rc;
+  if ((rc = d2h(o->D1_raw, ws.Draw[0], (size_t)g.Wd * g.Hd))) return rc;
+  if ((rc = d2h(o->D2_raw, ws.Draw[1], (size_t)g.Wd * g.Hd))) return rc;
 
   return dump_post(e, o);
 }

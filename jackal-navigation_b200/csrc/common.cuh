@@ -10,7 +10,8 @@
 //   tri_out / planes       compacted triangles (c1,c2,c3) + 6 plane floats
 //   gridmask  [2][gh*gw][GW] u32  per-cell disparity bit sets (createGrid)
 //   trimap    [2][H*W] i32  index of the last triangle covering each pixel
-//   D*        H*W f32      disparity maps / post-processing ping-pong buffers
+//   D*        Hd*Wd f32    disparity maps / post-processing ping-pong buffers (Hd x Wd = H x W, or
+//                          H/2 x W/2 with subsampling; frame slots are Hd*Wd floats apart)
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -37,6 +38,9 @@ constexpr int GRID_LIST = 16;    // entries of the compact per-cell candidate li
 // Per-call geometry + parameters, passed to kernels by value.
 struct Geo {
   int W, H, bpl;        // image size, input stride in bytes
+  int Wd, Hd;           // disparity map size: W x H, or W/2 x H/2 with subsampling (elas.cpp:914-917)
+  int speckle_eff;      // removeSmallSegments size limit at the map's resolution (elas.cpp:986-991)
+  int gap_eff;          // gapInterpolation width at the map's resolution (elas.cpp:1106-1111)
   int Wc, Hc;           // candidate lattice (elas.cpp:386-387)
   int gw, gh;           // disparity grid (elas.cpp:90-91)
   int gwords;           // u32 words per grid cell bit set, ceil((disp_max+1)/32) rounded up to 4

@@ -112,20 +112,23 @@ __device__ __forceinline__ void eval_word(unsigned& best, unsigned bits, int w, 
 }
 
 // R = plane radius known at compile time (2: ROBOTICS, 3: MIDDLEBURY), 0 = run-time radius.
-template <int R>
+// SUB = subsampling: only pixels with even u and v are matched (elas.cpp:877-896) and the result
+// goes to (u/2, v/2) of the W/2 x H/2 map (elas.cpp:693); everything else is unchanged.
+template <int R, bool SUB>
 __global__ void __launch_bounds__(DENSE_THREADS)
 dense_kernel(Geo g, Workspace ws) {
   const int side = blockIdx.z & 1, frame = blockIdx.z >> 1;
   if (ws.info[frame].status != JN_OK) return;
   const int W = g.W, H = g.H;
-  const int u = blockIdx.x * DENSE_THREADS + threadIdx.x;
-  if (u >= W) return;
+  const int um = blockIdx.x * DENSE_THREADS + threadIdx.x;     // map column
+  if (um >= g.Wd) return;
+  const int u = SUB ? 2 * um : um;
   // frame-level bases once per thread; everything below is 32-bit offsets from them
   const size_t fpix = (size_t)frame * W * H;
   const uint4* __restrict__ Af = reinterpret_cast<const uint4*>(ws.desc[side] + fpix * 16);
   const uint4* __restrict__ Bf = reinterpret_cast<const uint4*>(ws.desc[side ^ 1] + fpix * 16);
   const int* __restrict__ tmap = ws.trimap[side] + fpix;
-  float* __restrict__ outp = ws.Draw[side] + fpix;
+  float* __restrict__ outp = ws.Draw[side] + (SUB ? (size_t)frame * g.Wd * g.Hd : fpix);
   const float* __restrict__ planes = ws.planes[side] + (size_t)frame * g.cap_t * 6;
   const uint32_t* __restrict__ masks = ws.gridmask[side] + (size_t)frame * g.gw * g.gh * g.gwords;
   const uint16_t* __restrict__ lists = ws.gridlist[side] + (size_t)frame * g.gw * g.gh * GRID_LIST;
@@ -137,7 +140,8 @@ dense_kernel(Geo g, Workspace ws) {
   const int P0 = g.P[0], P1 = g.P[1], P2 = g.P[2], P3 = g.P[3];
   const int v0 = blockIdx.y * DENSE_ROWS;
 #pragma unroll 1
-  for (int v = v0; v < min(v0 + DENSE_ROWS, H); v++) {
+  for (int vm = v0; vm < min(v0 + DENSE_ROWS, g.Hd); vm++) {
+    const int v = SUB ? 2 * vm : vm;
     const unsigned pix = (unsigned)(v * W + u);
     const unsigned rowoff = (unsigned)(max(min(v, H - 3), 2) * W);
     // independent loads first: triangle id, own descriptor
@@ -215,7 +219,7 @@ dense_kernel(Geo g, Workspace ws) {
       }
       out = (best != KEY_NONE) ? (float)(best & 0xFFFu) : -1.f;
     }
-    outp[pix] = out;
+    outp[SUB ? (unsigned)(vm * g.Wd + um) : pix] = out;
   }
 }
 
@@ -230,10 +234,16 @@ void launch_raster(const Geo& g, int B, Workspace& ws, cudaStream_t s) {
 }
 
 void launch_dense_match(const Geo& g, int B, Workspace& ws, cudaStream_t s) {
-  dim3 grid((g.W + DENSE_THREADS - 1) / DENSE_THREADS, (g.H + DENSE_ROWS - 1) / DENSE_ROWS, 2 * B);
-  if (g.plane_radius == 2) dense_kernel<2><<<grid, DENSE_THREADS, 0, s>>>(g, ws);
-  else if (g.plane_radius == 3) dense_kernel<3><<<grid, DENSE_THREADS, 0, s>>>(g, ws);
-  else dense_kernel<0><<<grid, DENSE_THREADS, 0, s>>>(g, ws);
+  dim3 grid((g.Wd + DENSE_THREADS - 1) / DENSE_THREADS, (g.Hd + DENSE_ROWS - 1) / DENSE_ROWS, 2 * B);
+  if (g.p.subsampling) {
+    if (g.plane_radius == 2) dense_kernel<2, true><<<grid, DENSE_THREADS, 0, s>>>(g, ws);
+    else if (g.plane_radius == 3) dense_kernel<3, true><<<grid, DENSE_THREADS, 0, s>>>(g, ws);
+    else dense_kernel<0, true><<<grid, DENSE_THREADS, 0, s>>>(g, ws);
+  } else {
+    if (g.plane_radius == 2) dense_kernel<2, false><<<grid, DENSE_THREADS, 0, s>>>(g, ws);
+    else if (g.plane_radius == 3) dense_kernel<3, false><<<grid, DENSE_THREADS, 0, s>>>(g, ws);
+    else dense_kernel<0, false><<<grid, DENSE_THREADS, 0, s>>>(g, ws);
+  }
   g_jn_launches += 1;
 }
 

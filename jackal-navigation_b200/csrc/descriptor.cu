@@ -97,7 +97,9 @@ __global__ void __launch_bounds__(256) descriptor_kernel(Geo g, const uint8_t* _
     int x = x0 + tx, y = y0 + ly;
     if (x >= W || y >= H) continue;
     uint4 out = make_uint4(0, 0, 0, 0);
-    if (x >= 3 && x <= W - 4 && y >= 3 && y <= H - 4) {
+    // half resolution (descriptor.cpp:48-78): only rows 4, 6, 8, ... carry descriptors
+    const bool row_ok = g.p.subsampling ? (y >= 4 && !(y & 1)) : (y >= 3);
+    if (x >= 3 && x <= W - 4 && row_ok && y <= H - 4) {
       const uint8_t* u = sU + (ly + 2) * GWP + (tx + 2);
       const uint8_t* v = sV + (ly + 2) * GWP + (tx + 2);
       unsigned b0 = u[-2 * GWP], b1 = u[-GWP - 2], b2 = u[-GWP], b3 = u[-GWP + 2];

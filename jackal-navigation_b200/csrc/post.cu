@@ -1,6 +1,8 @@
 // post.cu -- post-processing of the raw disparity maps (elas.cpp:909-1560):
 // leftRightConsistencyCheck, removeSmallSegments, gapInterpolation,
-// adaptiveMean, median.  Full-resolution branches (subsampling = 0).
+// adaptiveMean, median.  The maps are g.Wd x g.Hd: full resolution, or half
+// resolution with subsampling (then the L/R check halves the disparity, the
+// segment-size and gap limits are rescaled and the adaptive mean has 4 taps).
 //
 // All five are HBM-bound streaming passes over H*W floats.
 //   L/R check        one thread per pixel, out of place (the reference copies both maps first).
@@ -26,7 +28,7 @@ namespace {
 __global__ void lr_kernel(Geo g, Workspace ws) {
   const int frame = blockIdx.z;
   if (ws.info[frame].status != JN_OK) return;
-  const int W = g.W, H = g.H;
+  const int W = g.Wd, H = g.Hd;
   const int u = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y;
   if (u >= W) return;
   const size_t fp = (size_t)frame * W * H, a = fp + (size_t)v * W + u;
@@ -35,7 +37,9 @@ __global__ void lr_kernel(Geo g, Workspace ws) {
   const float thr = (float)g.p.lr_threshold;
   float d1 = D1[a], d2 = D2[a];
   float o1 = -10.f, o2 = -10.f;
-  float uw1 = (float)u - d1, uw2 = (float)u + d2;
+  // elas.cpp:937-943: at half resolution a disparity of d moves d/2 map pixels
+  const bool sub = g.p.subsampling != 0;
+  float uw1 = sub ? (float)u - d1 / 2 : (float)u - d1, uw2 = sub ? (float)u + d2 / 2 : (float)u + d2;
   if (d1 >= 0 && uw1 >= 0 && uw1 < (float)W) {
     o1 = (fabsf(D2[fp + (size_t)v * W + (int)uw1] - d1) > thr) ? -10.f : d1;
   }
@@ -54,7 +58,7 @@ __global__ void __launch_bounds__(ROW_THREADS) seg_rows_kernel(Geo g, Workspace 
   __shared__ int s_part[ROW_THREADS];
   const int frame = blockIdx.y, v = blockIdx.x;
   if (ws.info[frame].status != JN_OK) return;
-  const int W = g.W, H = g.H, tid = threadIdx.x;
+  const int W = g.Wd, H = g.Hd, tid = threadIdx.x;
   const size_t base = (size_t)frame * W * H + (size_t)v * W;
   const float* D = ws.Dlr[side] + base;
   int* label = ws.label + base;
@@ -124,7 +128,7 @@ __device__ __forceinline__ void uf_union(int* label, int a, int b) {
 __global__ void seg_merge_kernel(Geo g, Workspace ws, int side) {
   const int frame = blockIdx.z;
   if (ws.info[frame].status != JN_OK) return;
-  const int W = g.W, H = g.H;
+  const int W = g.Wd, H = g.Hd;
   const int u = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y;
   if (v + 1 >= H) return;
   const size_t fp = (size_t)frame * W * H;
@@ -149,7 +153,7 @@ __global__ void seg_merge_kernel(Geo g, Workspace ws, int side) {
 __global__ void seg_count_kernel(Geo g, Workspace ws) {
   const int frame = blockIdx.z;
   if (ws.info[frame].status != JN_OK) return;
-  const int W = g.W, H = g.H;
+  const int W = g.Wd, H = g.Hd;
   const int u = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y;
   if (u >= W) return;
   const size_t fp = (size_t)frame * W * H;
@@ -175,14 +179,14 @@ __global__ void seg_count_kernel(Geo g, Workspace ws) {
 __global__ void seg_apply_kernel(Geo g, Workspace ws, int side) {
   const int frame = blockIdx.z;
   if (ws.info[frame].status != JN_OK) return;
-  const int W = g.W, H = g.H;
+  const int W = g.Wd, H = g.Hd;
   const int u = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y;
   if (u >= W) return;
   const size_t fp = (size_t)frame * W * H, a = fp + (size_t)v * W + u;
   int l = ws.label[a];
   if (l < 0) return;
   const int root = ws.label[fp + l];
-  if (ws.segsize[fp + root] < g.p.speckle_size) ws.Dlr[side][a] = -10.f;
+  if (ws.segsize[fp + root] < g.speckle_eff) ws.Dlr[side][a] = -10.f;
 }
 
 // ------------------------------------------------------------ gap interpolation
@@ -195,7 +199,7 @@ __global__ void __launch_bounds__(ROW_THREADS) gap_rows_kernel(Geo g, Workspace 
   __shared__ int s_prev[ROW_THREADS], s_next[ROW_THREADS];
   const int frame = blockIdx.y, v = blockIdx.x;
   if (ws.info[frame].status != JN_OK) return;
-  const int W = g.W, H = g.H, tid = threadIdx.x, gap = g.p.ipol_gap_width;
+  const int W = g.Wd, H = g.Hd, tid = threadIdx.x, gap = g.gap_eff;
   float* D = ws.Dlr[side] + (size_t)frame * W * H + (size_t)v * W;
   for (int u = tid; u < W; u += ROW_THREADS) s_row[u] = D[u];
   __syncthreads();
@@ -243,7 +247,7 @@ template <bool ROWS>
 __global__ void gap_small_kernel(Geo g, Workspace ws, const float* __restrict__ in, float* __restrict__ out) {
   const int frame = blockIdx.z;
   if (ws.info[frame].status != JN_OK) return;
-  const int W = g.W, H = g.H, gap = g.p.ipol_gap_width;
+  const int W = g.Wd, H = g.Hd, gap = g.gap_eff;
   const int u = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y;
   if (u >= W) return;
   const size_t fp = (size_t)frame * W * H;
@@ -272,7 +276,7 @@ __global__ void gap_small_kernel(Geo g, Workspace ws, const float* __restrict__ 
 __global__ void gap_cols_kernel(Geo g, Workspace ws, int side) {
   const int frame = blockIdx.y;
   if (ws.info[frame].status != JN_OK) return;
-  const int W = g.W, H = g.H, gap = g.p.ipol_gap_width;
+  const int W = g.Wd, H = g.Hd, gap = g.gap_eff;
   const int u = blockIdx.x * blockDim.x + threadIdx.x;
   if (u >= W) return;
   float* D = ws.Dlr[side] + (size_t)frame * W * H + u;
@@ -343,48 +347,6 @@ __device__ __forceinline__ bool mean8(const float x[8], float centre, int rot, f
   return false;
 }
 
-// horizontal: in = post-gap map; tmp = filtered rows 3..H-4, centres 4..W-4; elsewhere -10 if
-// the input is invalid, 0 otherwise (the reference leaves those floats unwritten, H1)
-__global__ void mean_h_kernel(Geo g, Workspace ws, const float* __restrict__ in, float* __restrict__ tmp) {
-  const int frame = blockIdx.z;
-  if (ws.info[frame].status != JN_OK) return;
-  const int W = g.W, H = g.H;
-  const int c = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y;
-  if (c >= W) return;
-  const float* row = in + (size_t)frame * W * H + (size_t)v * W;
-  float d = row[c];
-  float o = (d < 0) ? -10.f : 0.f;
-  if (W >= 8 && v >= 3 && v <= H - 4 && c >= 4 && c <= W - 4) {
-    float x[8];
-#pragma unroll
-    for (int k = 0; k < 8; k++) { float t = row[c - 4 + k]; x[k] = (t < 0) ? -10.f : t; }
-    float m;
-    if (mean8(x, x[4], (c - 4) & 3, m)) o = m;
-  }
-  tmp[(size_t)frame * W * H + (size_t)v * W + c] = o;
-}
-
-// vertical: tmp -> out for columns 3..W-4, centres 4..H-4; every other pixel keeps `in`
-__global__ void mean_v_kernel(Geo g, Workspace ws, const float* __restrict__ in, const float* __restrict__ tmp,
-                              float* __restrict__ out, size_t out_frame_stride) {
-  const int frame = blockIdx.z;
-  if (ws.info[frame].status != JN_OK) return;
-  const int W = g.W, H = g.H;
-  const int u = blockIdx.x * blockDim.x + threadIdx.x, c = blockIdx.y;
-  if (u >= W) return;
-  const size_t fp = (size_t)frame * W * H;
-  float o = in[fp + (size_t)c * W + u];
-  if (H >= 8 && u >= 3 && u <= W - 4 && c >= 4 && c <= H - 4) {
-    const float* col = tmp + fp + u;
-    float x[8];
-#pragma unroll
-    for (int k = 0; k < 8; k++) x[k] = col[(size_t)(c - 4 + k) * W];
-    float m;
-    if (mean8(x, x[4], (c - 4) & 3, m)) o = m;
-  }
-  out[(size_t)frame * out_frame_stride + (size_t)c * W + u] = o;
-}
-
 // Both passes in one kernel: a CTA produces a MT_W x MT_H tile of the output.  The input tile
 // (4 / 3 columns and rows of halo) is staged in shared memory once, the horizontally filtered
 // rows the vertical pass needs (MT_H + 7 of them) are computed into shared memory and never
@@ -398,7 +360,7 @@ mean_fused_kernel(Geo g, Workspace ws, const float* __restrict__ in, float* __re
   __shared__ float s_tmp[MT_ROWS][MT_W];         // horizontally filtered (the reference's D_tmp)
   const int frame = blockIdx.z;
   if (ws.info[frame].status != JN_OK) return;
-  const int W = g.W, H = g.H, tid = threadIdx.x;
+  const int W = g.Wd, H = g.Hd, tid = threadIdx.x;
   const int x0 = blockIdx.x * MT_W, y0 = blockIdx.y * MT_H;
   const float* src = in + (size_t)frame * W * H;
   for (int i = tid; i < MT_ROWS * MT_IN_W; i += 256) {
@@ -440,6 +402,71 @@ mean_fused_kernel(Geo g, Workspace ws, const float* __restrict__ in, float* __re
   }
 }
 
+// Half-resolution branch (elas.cpp:1323-1391): 4 taps at coordinates c-2 .. c+1, centre c.  The
+// reference's ring is indexed by coordinate mod 4 and summed ((l0+l1)+l2)+l3; rot = (c-2) & 3.
+__device__ __forceinline__ bool mean4(const float x[4], float centre, int rot, float& out) {
+  float w[4], f[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    float t = 4.0f - buggy_abs(x[k] - centre);
+    w[k] = fmaxf(0.0f, t);
+    f[k] = x[k] * w[k];
+  }
+  float ws, fs;
+  switch (rot) {
+    case 0: ws = ((w[0] + w[1]) + w[2]) + w[3]; fs = ((f[0] + f[1]) + f[2]) + f[3]; break;
+    case 1: ws = ((w[3] + w[0]) + w[1]) + w[2]; fs = ((f[3] + f[0]) + f[1]) + f[2]; break;
+    case 2: ws = ((w[2] + w[3]) + w[0]) + w[1]; fs = ((f[2] + f[3]) + f[0]) + f[1]; break;
+    default: ws = ((w[1] + w[2]) + w[3]) + w[0]; fs = ((f[1] + f[2]) + f[3]) + f[0]; break;
+  }
+  if (ws > 0) {
+    float d = fs / ws;
+    if (d >= 0) { out = d; return true; }
+  }
+  return false;
+}
+
+// horizontal: rows 3..H-4, centres 2..W-2; elsewhere -10 (invalid input) or 0 (unwritten, H1)
+__global__ void mean4_h_kernel(Geo g, Workspace ws, const float* __restrict__ in, float* __restrict__ tmp) {
+  const int frame = blockIdx.z;
+  if (ws.info[frame].status != JN_OK) return;
+  const int W = g.Wd, H = g.Hd;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y;
+  if (c >= W) return;
+  const float* row = in + (size_t)frame * W * H + (size_t)v * W;
+  float d = row[c];
+  float o = (d < 0) ? -10.f : 0.f;
+  if (W >= 4 && v >= 3 && v <= H - 4 && c >= 2 && c <= W - 2) {
+    float x[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) { float t = row[c - 2 + k]; x[k] = (t < 0) ? -10.f : t; }
+    float m;
+    if (mean4(x, x[2], (c - 2) & 3, m)) o = m;
+  }
+  tmp[(size_t)frame * W * H + (size_t)v * W + c] = o;
+}
+
+// vertical: columns 3..W-4, centres 2..H-2; every other pixel keeps `in`
+__global__ void mean4_v_kernel(Geo g, Workspace ws, const float* __restrict__ in, const float* __restrict__ tmp,
+                               float* __restrict__ out, size_t out_frame_stride) {
+  const int frame = blockIdx.z;
+  if (ws.info[frame].status != JN_OK) return;
+  const int W = g.Wd, H = g.Hd;
+  const int u = blockIdx.x * blockDim.x + threadIdx.x, c = blockIdx.y;
+  if (u >= W) return;
+  const size_t fp = (size_t)frame * W * H;
+  float o = in[fp + (size_t)c * W + u];
+  if (H >= 4 && u >= 3 && u <= W - 4 && c >= 2 && c <= H - 2) {
+    const float* col = tmp + fp + u;
+    float x[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) x[k] = col[(size_t)(c - 2 + k) * W];
+    float m;
+    if (mean4(x, x[2], (c - 2) & 3, m)) o = m;
+  }
+  out[(size_t)frame * out_frame_stride + (size_t)c * W + u] = o;
+}
+
 // ------------------------------------------------------------ median
 __device__ __forceinline__ float median7(float v[7]) {
   // insertion sort, as elas.cpp:1518-1527 (NaNs cannot occur)
@@ -457,7 +484,7 @@ __device__ __forceinline__ float median7(float v[7]) {
 __global__ void median_h_kernel(Geo g, Workspace ws, const float* __restrict__ in, float* __restrict__ tmp) {
   const int frame = blockIdx.z;
   if (ws.info[frame].status != JN_OK) return;
-  const int W = g.W, H = g.H;
+  const int W = g.Wd, H = g.Hd;
   const int u = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y;
   if (u >= W) return;
   const size_t a = (size_t)frame * W * H + (size_t)v * W + u;
@@ -479,7 +506,7 @@ __global__ void median_v_kernel(Geo g, Workspace ws, const float* __restrict__ i
                                 float* __restrict__ out, size_t out_frame_stride) {
   const int frame = blockIdx.z;
   if (ws.info[frame].status != JN_OK) return;
-  const int W = g.W, H = g.H;
+  const int W = g.Wd, H = g.Hd;
   const int u = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y;
   if (u >= W) return;
   const size_t a = (size_t)frame * W * H + (size_t)v * W + u;
@@ -497,7 +524,7 @@ __global__ void copy_out_kernel(Geo g, Workspace ws, const float* __restrict__ i
                                 int32_t* __restrict__ status) {
   const int frame = blockIdx.y;
   const int st = ws.info[frame].status;
-  const size_t n = (size_t)g.W * g.H;
+  const size_t n = (size_t)g.Wd * g.Hd;
   if (status && blockIdx.x == 0 && threadIdx.x == 0) status[frame] = st;
   if (st != JN_OK || out == nullptr) return;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
@@ -508,15 +535,15 @@ __global__ void copy_out_kernel(Geo g, Workspace ws, const float* __restrict__ i
 
 // Step-wise entry points (the debug dump calls them one at a time).
 void post_lr(const Geo& g, int B, Workspace& ws, cudaStream_t s) {
-  lr_kernel<<<dim3((g.W + 255) / 256, g.H, B), 256, 0, s>>>(g, ws);
+  lr_kernel<<<dim3((g.Wd + 255) / 256, g.Hd, B), 256, 0, s>>>(g, ws);
   g_jn_launches += 1;
 }
 
 void post_segments(const Geo& g, int B, Workspace& ws, int side, cudaStream_t s) {
-  dim3 pg((g.W + 255) / 256, g.H, B);
-  cudaMemsetAsync(ws.segsize, 0, (size_t)B * g.W * g.H * sizeof(int32_t), s);
-  cudaMemsetAsync(ws.runlen, 0, (size_t)B * g.W * g.H * sizeof(int32_t), s);
-  seg_rows_kernel<<<dim3(g.H, B), ROW_THREADS, 0, s>>>(g, ws, side);
+  dim3 pg((g.Wd + 255) / 256, g.Hd, B);
+  cudaMemsetAsync(ws.segsize, 0, (size_t)B * g.Wd * g.Hd * sizeof(int32_t), s);
+  cudaMemsetAsync(ws.runlen, 0, (size_t)B * g.Wd * g.Hd * sizeof(int32_t), s);
+  seg_rows_kernel<<<dim3(g.Hd, B), ROW_THREADS, 0, s>>>(g, ws, side);
   seg_merge_kernel<<<pg, 256, 0, s>>>(g, ws, side);
   seg_count_kernel<<<pg, 256, 0, s>>>(g, ws);
   seg_apply_kernel<<<pg, 256, 0, s>>>(g, ws, side);
@@ -524,13 +551,13 @@ void post_segments(const Geo& g, int B, Workspace& ws, int side, cudaStream_t s)
 }
 
 void post_gap(const Geo& g, int B, Workspace& ws, int side, cudaStream_t s) {
-  if (g.p.ipol_gap_width <= SMALL_GAP && !g.p.add_corners) {
-    dim3 pg((g.W + 255) / 256, g.H, B);
+  if (g.gap_eff <= SMALL_GAP && !g.p.add_corners) {
+    dim3 pg((g.Wd + 255) / 256, g.Hd, B);
     gap_small_kernel<true><<<pg, 256, 0, s>>>(g, ws, ws.Dlr[side], ws.Dtmp[side]);
     gap_small_kernel<false><<<pg, 256, 0, s>>>(g, ws, ws.Dtmp[side], ws.Dlr[side]);
   } else {
-    gap_rows_kernel<<<dim3(g.H, B), ROW_THREADS, g.W * sizeof(float), s>>>(g, ws, side);
-    gap_cols_kernel<<<dim3((g.W + 63) / 64, B), 64, 0, s>>>(g, ws, side);
+    gap_rows_kernel<<<dim3(g.Hd, B), ROW_THREADS, g.Wd * sizeof(float), s>>>(g, ws, side);
+    gap_cols_kernel<<<dim3((g.Wd + 63) / 64, B), 64, 0, s>>>(g, ws, side);
   }
   g_jn_launches += 2;
 }
@@ -538,15 +565,22 @@ void post_gap(const Geo& g, int B, Workspace& ws, int side, cudaStream_t s) {
 // in -> out (frame stride of out given in floats); tmp = scratch
 void post_mean(const Geo& g, int B, Workspace& ws, const float* in, float* tmp, float* out, size_t ostride,
                cudaStream_t s) {
+  if (g.p.subsampling) {
+    dim3 pg((g.Wd + 255) / 256, g.Hd, B);
+    mean4_h_kernel<<<pg, 256, 0, s>>>(g, ws, in, tmp);
+    mean4_v_kernel<<<pg, 256, 0, s>>>(g, ws, in, tmp, out, ostride);
+    g_jn_launches += 2;
+    return;
+  }
   (void)tmp;   // the horizontally filtered rows live in shared memory only
-  dim3 grid((g.W + MT_W - 1) / MT_W, (g.H + MT_H - 1) / MT_H, B);
+  dim3 grid((g.Wd + MT_W - 1) / MT_W, (g.Hd + MT_H - 1) / MT_H, B);
   mean_fused_kernel<<<grid, 256, 0, s>>>(g, ws, in, out, ostride);
   g_jn_launches += 1;
 }
 
 void post_median(const Geo& g, int B, Workspace& ws, const float* in, float* tmp, float* out, size_t ostride,
                  cudaStream_t s) {
-  dim3 pg((g.W + 255) / 256, g.H, B);
+  dim3 pg((g.Wd + 255) / 256, g.Hd, B);
   median_h_kernel<<<pg, 256, 0, s>>>(g, ws, in, tmp);
   median_v_kernel<<<pg, 256, 0, s>>>(g, ws, in, tmp, out, ostride);
   g_jn_launches += 2;
@@ -559,7 +593,7 @@ void post_copy(const Geo& g, int B, Workspace& ws, const float* in, float* out, 
 
 // The whole chain for a batch.  D1out/D2out: user buffers (B * W*H floats); D2out may be NULL.
 void launch_post(const Geo& g, int B, Workspace& ws, float* D1out, float* D2out, int32_t* status, cudaStream_t s) {
-  const size_t n = (size_t)g.W * g.H;
+  const size_t n = (size_t)g.Wd * g.Hd;
   post_lr(g, B, ws, s);
   const int sides = g.p.postprocess_only_left ? 1 : 2;
   for (int side = 0; side < sides; side++) {

@@ -206,7 +206,8 @@ void ref_dense(const jn_elas_params* p, int w, int h, const uint8_t* desc1, cons
 void ref_postprocess(const jn_elas_params* p, int w, int h, float* D1, float* D2, oracle_stages* st) {
   Elas elas(to_ref(p));
   elas.width = w; elas.height = h; elas.bpl = w + 15 - (w - 1) % 16;
-  size_t n = (size_t)w * h;
+  /* w, h = IMAGE size; with subsampling the maps hold (w/2) x (h/2) floats (elas.cpp:914-917) */
+  size_t n = p->subsampling ? (size_t)(w / 2) * (h / 2) : (size_t)w * h;
   elas.leftRightConsistencyCheck(D1, D2);
   if (st) { put(st->D1_lr, D1, n); put(st->D2_lr, D2, n); }
   elas.removeSmallSegments(D1);

@@ -6,6 +6,7 @@
 Fixtures (small, compressed):
   elas_robotics_160x120.npz   ROBOTICS preset, disp_max 48, postprocess_only_left
   elas_c5_200x150.npz         ROBOTICS + filter_median + both images post-processed, disp_max 64
+  elas_sub_240x180.npz        ROBOTICS + subsampling (half-resolution maps), disp_max 48
   delaunay_cases.npz          point sets (lattice / cocircular / collinear / duplicates) with the
                               triangle lists the real Triangle ("zQB") returns for them
 """
@@ -50,6 +51,7 @@ def dump(name, W, H, dm, seed, **kw):
 
 dump("elas_robotics_160x120.npz", 160, 120, 48, 3)
 dump("elas_c5_200x150.npz", 200, 150, 64, 11, filter_median=1, postprocess_only_left=0)
+dump("elas_sub_240x180.npz", 240, 180, 48, 21, subsampling=1, postprocess_only_left=0)
 
 rng = np.random.default_rng(42)
 cases = {}

@@ -241,6 +241,8 @@ class Oracle:
         st = Stages()
         for k, arr in o.items():
             setattr(st, k, _ptr(arr))
+        if p.subsampling:           # D1/D2 are the half-resolution maps; the oracle takes the image size
+            W, H = 2 * W, 2 * H
         self.fn("postprocess")(C.byref(p), W, H, _ptr(a), _ptr(b), C.byref(st))
         return o
 

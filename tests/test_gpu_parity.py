@@ -25,7 +25,8 @@ def assert_stages_equal(a, b, keys=STAGES):
         assert np.array_equal(x, y), "%s: %d of %d elements differ" % (k, int((x != y).sum()), x.size)
 
 
-@pytest.mark.parametrize("name,H", [("elas_robotics_160x120.npz", 120), ("elas_c5_200x150.npz", 150)])
+@pytest.mark.parametrize("name,H", [("elas_robotics_160x120.npz", 120), ("elas_c5_200x150.npz", 150),
+                                    ("elas_sub_240x180.npz", 180)])
 def test_cuda_matches_golden(jn, name, H):
     z, p = gu.load(name)
     pj = jn.parameters.from_buffer_copy(bytes(p))
@@ -168,9 +169,34 @@ def test_few_support_points_leave_outputs_untouched(jn, capsys):
     e.close()
 
 
+@pytest.mark.parametrize("W,H,dm,seed,preset,kw", [
+    (320, 240, 64, 1, "robotics", {}),
+    (333, 251, 100, 7, "robotics", {}),                                   # odd width and height
+    (640, 480, 255, 5, "robotics", {"filter_median": 1, "postprocess_only_left": 0}),
+    (326, 241, 80, 6, "robotics", {"candidate_stepsize": 4}),             # even step stays as it is
+    (320, 240, 64, 8, "robotics", {"ipol_gap_width": 40, "speckle_size": 30}),
+    (320, 240, 64, 3, "middlebury", {}),
+    (640, 480, 255, 12, "middlebury", {}),
+    (1920, 1200, 255, 1001, "robotics", {}),
+])
+def test_subsampling_every_stage_matches_oracle(jn, oracle, synth, W, H, dm, seed, preset, kw):
+    """param.subsampling = 1: descriptors on even rows only, lattice step 6, even pixels matched into
+    (H/2) x (W/2) maps, post-processing at half resolution (elas.cpp:380, 693, 877-896, 914-1499)."""
+    I1, I2, _ = synth.synth_pair(W, H, dm, seed)
+    a = oracle.stages(getattr(ol, preset)(dm, subsampling=1, **kw), I1, I2)
+    e = jn.Elas(jn.parameters(jn.ROBOTICS if preset == "robotics" else jn.MIDDLEBURY, disp_max=dm, subsampling=1, **kw))
+    b = e.stages(I1, I2)
+    assert b["D1"].shape == (H // 2, W // 2)
+    assert_stages_equal(a, b)
+    D1 = np.full((H // 2, W // 2), 3.0, np.float32); D2 = D1.copy()
+    assert e.process(I1, I2, D1, D2, (W, H, W)) == jn.JN_OK
+    assert np.array_equal(D1, a["D1"]) and np.array_equal(D2, a["D2"])
+    e.close()
+
+
 def test_unsupported_parameters_fail_loudly(jn):
     I = np.zeros((120, 160), np.uint8); D = np.zeros((120, 160), np.float32)
-    for kw in ({"subsampling": 1},):
+    for kw in ({"sigma": 3.0, "sradius": 3.0},):       # plane radius 9 > 7
         e = jn.Elas(jn.parameters(jn.ROBOTICS, **kw))
         with pytest.raises(jn.JnError):
             e.process(I, I, D, D.copy(), (160, 120, 160))

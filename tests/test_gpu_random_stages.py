@@ -144,3 +144,19 @@ def test_postprocess_random(jn, oracle, mode, kw):
     for k in ("D1_lr", "D2_lr", "D1_seg", "D2_seg", "D1_gap", "D2_gap", "D1_mean", "D2_mean", "D1", "D2"):
         assert np.array_equal(got[k], ref[k]), "%s: %d pixels differ" % (k, int((got[k] != ref[k]).sum()))
     e.close()
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("kw", [{}, {"filter_median": 1, "postprocess_only_left": 0},
+                                {"ipol_gap_width": 30, "speckle_size": 40, "postprocess_only_left": 0}])
+def test_postprocess_random_subsampled(jn, oracle, mode, kw):
+    """Half-resolution branches: d/2 warp in the L/R check, rescaled segment and gap limits, 4-tap mean."""
+    rng = np.random.default_rng(400 + mode)
+    H, W = 150, 211
+    D1, D2 = random_disparity_maps(rng, H, W, mode)
+    ref = oracle.postprocess(ol.robotics(64, subsampling=1, **kw), D1, D2)
+    e = jn.Elas(jn.parameters(jn.ROBOTICS, disp_max=64, subsampling=1, **kw))
+    got = jn.debug_postprocess(e, D1, D2)
+    for k in ("D1_lr", "D2_lr", "D1_seg", "D2_seg", "D1_gap", "D2_gap", "D1_mean", "D2_mean", "D1", "D2"):
+        assert np.array_equal(got[k], ref[k]), "%s: %d pixels differ" % (k, int((got[k] != ref[k]).sum()))
+    e.close()

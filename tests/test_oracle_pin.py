@@ -10,7 +10,8 @@ import oracle_lib as ol
 STAGE_KEYS = gu.EXACT + ["desc1", "desc2", "grid1", "grid2"]
 
 
-@pytest.mark.parametrize("name,H", [("elas_robotics_160x120.npz", 120), ("elas_c5_200x150.npz", 150)])
+@pytest.mark.parametrize("name,H", [("elas_robotics_160x120.npz", 120), ("elas_c5_200x150.npz", 150),
+                                    ("elas_sub_240x180.npz", 180)])
 def test_port_matches_golden(port, name, H):
     z, p = gu.load(name)
     o = port.stages(p, z["I1"], z["I2"])
@@ -33,6 +34,9 @@ def test_port_delaunay_matches_golden_triangle_output(port):
     (640, 480, 64, 1, {}),                                            # BASELINE config C1
     (320, 240, 64, 3, {"filter_median": 1, "postprocess_only_left": 0}),
     (256, 192, 255, 9, {"ipol_gap_width": 7, "speckle_size": 50, "lr_threshold": 1}),
+    (320, 240, 64, 1, {"subsampling": 1}),                            # half-resolution maps
+    (333, 251, 100, 7, {"subsampling": 1, "filter_median": 1, "postprocess_only_left": 0}),
+    (326, 241, 80, 6, {"subsampling": 1, "candidate_stepsize": 4, "add_corners": 1}),
 ])
 def test_port_matches_compiled_reference_every_stage(ref, port, synth, W, H, dm, seed, kw):
     I1, I2, _ = synth.synth_pair(W, H, dm, seed)
