@@ -218,7 +218,6 @@ static void layout(const Geo& g, int B, Workspace& ws, char* base) {
   }
   carve(cur, ws.label, b * n);
   carve(cur, ws.segsize, b * n);
-  carve(cur, ws.runlen, b * n);
   carve(cur, ws.info, b);
   ws.bytes = (size_t)(cur - base);
 }

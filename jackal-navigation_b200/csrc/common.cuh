@@ -100,7 +100,6 @@ struct Workspace {
   float* Dtmp2[2];
   int32_t* label;              // B * H*W  (CCL)
   int32_t* segsize;            // B * H*W
-  int32_t* runlen;             // B * H*W  length of the horizontal run starting at a pixel
   FrameInfo* info;             // B
   size_t bytes;
 };

@@ -52,18 +52,22 @@ __global__ void __launch_bounds__(256) descriptor_kernel(Geo g, const uint8_t* _
       mbar_init(&s_bar, 1);
       fence_mbar_init();
     }
-    for (int i = tid; i < IH * IWP; i += 256) {
-      const int r = i / IWP, x = x0 - 16 + (i - r * IWP);
-      if (r < r0 || r >= r1 || x < xs || x >= xe) sIraw[i] = 0;
-    }
+    // interior tiles are overwritten completely by the copies; only tiles that touch the image
+    // border have bytes no copy writes
+    if (r0 > 0 || r1 < IH || xs > x0 - 16 || xe < x0 + 80)
+      for (int i = tid; i < IH * IWP; i += 256) {
+        const int r = i / IWP, x = x0 - 16 + (i - r * IWP);
+        if (r < r0 || r >= r1 || x < xs || x >= xe) sIraw[i] = 0;
+      }
     __syncthreads();
     if (tid == 0) {
       mbar_arrive_expect_tx(&s_bar, (uint32_t)((r1 - r0) * (xe - xs)));
       for (int r = r0; r < r1; r++)
         bulk_g2s(sIraw + r * IWP + (xs - (x0 - 16)), I + (size_t)(y0 - 3 + r) * g.bpl + xs, (uint32_t)(xe - xs),
                  &s_bar);
+      mbar_wait(&s_bar, 0);   // one waiting thread; the others sleep in the barrier instead of polling
     }
-    mbar_wait(&s_bar, 0);
+    __syncthreads();
   } else {
     for (int i = tid; i < IH * IW; i += 256) {
       int r = i / IW, c = i - r * IW;

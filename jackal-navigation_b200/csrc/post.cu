@@ -6,10 +6,10 @@
 //
 // All five are HBM-bound streaming passes over H*W floats.
 //   L/R check        one thread per pixel, out of place (the reference copies both maps first).
-//   small segments   4-connected components by union-find: rows are pre-linked to
-//                    their run start by a CTA-wide max-scan (depth-1 trees), vertical
-//                    unions use atomicMin with path halving, component sizes are
-//                    counted with warp-aggregated atomics.  At this stage every
+//   small segments   4-connected components by union-find over horizontal RUNS: a warp per
+//                    row links every pixel to its run start and records the run length,
+//                    vertical unions use atomicMin with path halving, every non-root run
+//                    adds its length to its root.  At this stage every
 //                    invalid pixel is exactly -10 and similarity is symmetric, so the
 //                    components equal the reference's breadth-first segments.
 //   gap interpolation rows: one CTA per row (previous/next valid index by scans, any
@@ -53,50 +53,61 @@ __global__ void lr_kernel(Geo g, Workspace ws) {
 // ------------------------------------------------------------ small segments
 constexpr int ROW_THREADS = 256;
 
-// label[i] = index of the first pixel of i's horizontal run of similar valid pixels; -1 if invalid
-__global__ void __launch_bounds__(ROW_THREADS) seg_rows_kernel(Geo g, Workspace ws, int side) {
-  __shared__ int s_part[ROW_THREADS];
-  const int frame = blockIdx.y, v = blockIdx.x;
+// One warp per map row, 32 pixels per iteration, left to right.
+//   label[i]   = index of the first pixel of i's horizontal run of similar valid pixels; -1 if invalid
+//   segsize[s] = length of the run, written (once) for run starts s only -- the union-find below
+//                works on runs, so these are the initial component sizes and nothing else of
+//                segsize is ever read: no clearing pass.
+// Run starts come from one ballot per chunk; a run that crosses a chunk border is carried in
+// (warp-uniform) registers.  All accesses are fully coalesced.
+constexpr int SEG_ROWS_PER_CTA = 8;
+
+__global__ void __launch_bounds__(32 * SEG_ROWS_PER_CTA) seg_rows_kernel(Geo g, Workspace ws, int side) {
+  const int frame = blockIdx.y;
   if (ws.info[frame].status != JN_OK) return;
-  const int W = g.Wd, H = g.Hd, tid = threadIdx.x;
+  const int W = g.Wd, H = g.Hd, lane = threadIdx.x & 31;
+  const int v = blockIdx.x * SEG_ROWS_PER_CTA + (threadIdx.x >> 5);
+  if (v >= H) return;
   const size_t base = (size_t)frame * W * H + (size_t)v * W;
-  const float* D = ws.Dlr[side] + base;
-  int* label = ws.label + base;
+  const float* __restrict__ D = ws.Dlr[side] + base;
+  int* __restrict__ label = ws.label + base;
+  int* __restrict__ segsize = ws.segsize + base;
   const float thr = g.p.speckle_sim_threshold;
-  const int chunk = (W + ROW_THREADS - 1) / ROW_THREADS;
-  const int lo = min(tid * chunk, W), hi = min(lo + chunk, W);
-  // A valid pixel's run starts at the nearest run start at or left of it (an invalid pixel
-  // is always followed by a start), so a max-scan over start positions is enough.
-  int last = -1;
-  for (int u = lo; u < hi; u++) {
-    float d = D[u];
-    if (d >= 0 && (u == 0 || !(D[u - 1] >= 0) || fabsf(d - D[u - 1]) > thr)) last = u;
-  }
-  s_part[tid] = last;
-  __syncthreads();
-  for (int off = 1; off < ROW_THREADS; off <<= 1) {
-    int o = (tid >= off) ? s_part[tid - off] : -1;
-    __syncthreads();
-    s_part[tid] = max(s_part[tid], o);
-    __syncthreads();
-  }
-  int cur = (tid == 0) ? -1 : s_part[tid - 1];
-  // run lengths: runlen[run start] += pixels of the run seen by this thread (runlen is zeroed)
-  int* runlen = ws.runlen + base;
-  int acc = 0, acc_run = -1;
-  for (int u = lo; u < hi; u++) {
-    float d = D[u];
-    if (d < 0) { label[u] = -1; continue; }
-    if (u == 0 || !(D[u - 1] >= 0) || fabsf(d - D[u - 1]) > thr) cur = u;
-    label[u] = v * W + cur;
-    if (cur != acc_run) {
-      if (acc) atomicAdd(runlen + acc_run, acc);
-      acc_run = cur;
-      acc = 0;
+  const unsigned le_mask = 0xFFFFFFFFu >> (31 - lane);   // lanes 0..lane
+  int cur = -1, cur_len = 0;   // start column / length so far of the run reaching the current chunk
+  float prev = -10.f;          // last pixel of the previous chunk
+  for (int u0 = 0; u0 < W; u0 += 32) {
+    const int u = u0 + lane;
+    const float d = (u < W) ? D[u] : -10.f;
+    float dl = __shfl_up_sync(0xffffffffu, d, 1);
+    if (lane == 0) dl = prev;
+    prev = __shfl_sync(0xffffffffu, d, 31);
+    const bool valid = d >= 0;
+    const bool start = valid && (u == 0 || !(dl >= 0) || fabsf(d - dl) > thr);
+    const unsigned sm = __ballot_sync(0xffffffffu, start);
+    const unsigned bm = sm | ~__ballot_sync(0xffffffffu, valid);   // a run cannot continue INTO these pixels
+    const unsigned below = sm & le_mask;
+    if (u < W) label[u] = valid ? v * W + (below ? u0 + 31 - __clz(below) : cur) : -1;
+    if (start) {
+      const unsigned above = bm & ~le_mask;
+      if (above) segsize[u] = __ffs(above) - 1 - lane;   // run ends inside this chunk
     }
-    acc++;
+    if (cur >= 0) {                 // the carried run covers the pixels before the first break
+      const int fb = bm ? __ffs(bm) - 1 : 32;
+      cur_len += fb;
+      if (fb < 32) {
+        if (lane == 0) segsize[cur] = cur_len;
+        cur = -1;
+      }
+    }
+    if (sm) {                       // the last start of the chunk may reach the chunk's end
+      const int ls = 31 - __clz(sm);
+      if (ls == 31 || (bm >> (ls + 1)) == 0u) { cur = u0 + ls; cur_len = 32 - ls; }
+    }
   }
-  if (acc) atomicAdd(runlen + acc_run, acc);
+  // pixels beyond W count as invalid, so a run touching the right border was closed in the loop
+  // unless W is a multiple of 32
+  if (cur >= 0 && lane == 0) segsize[cur] = cur_len;
 }
 
 __device__ __forceinline__ int uf_find(int* label, int x) {
@@ -149,8 +160,9 @@ __global__ void seg_merge_kernel(Geo g, Workspace ws, int side) {
 }
 
 // Only the first pixel of every horizontal run walks to its root (runs, not pixels, are the
-// union-find elements); it adds the run length to the root's size and leaves label[start] = root.
-__global__ void seg_count_kernel(Geo g, Workspace ws) {
+// union-find elements); a start that is not a root adds its run length to the root's size and
+// leaves label[start] = root.  Starts are recognised from the map itself.
+__global__ void seg_count_kernel(Geo g, Workspace ws, int side) {
   const int frame = blockIdx.z;
   if (ws.info[frame].status != JN_OK) return;
   const int W = g.Wd, H = g.Hd;
@@ -158,8 +170,13 @@ __global__ void seg_count_kernel(Geo g, Workspace ws) {
   if (u >= W) return;
   const size_t fp = (size_t)frame * W * H;
   const int i = v * W + u;
-  const int len = ws.runlen[fp + i];
-  if (len == 0) return;                 // not a run start
+  const float* __restrict__ D = ws.Dlr[side] + fp;
+  const float d = D[i];
+  if (!(d >= 0)) return;
+  if (u > 0) {
+    const float dl = D[i - 1];
+    if (dl >= 0 && fabsf(d - dl) <= g.p.speckle_sim_threshold) return;   // not a run start
+  }
   int* label = ws.label + fp;
   // A component's root is its smallest pixel index and labels only decrease towards it, so
   // compressing with atomicMin can never replace a root by a larger ancestor.
@@ -170,8 +187,10 @@ __global__ void seg_count_kernel(Geo g, Workspace ws) {
     x = p;
     p = gp;
   }
+  if (x == i) return;                   // a root keeps its own run length
   atomicMin(label + i, x);
-  atomicAdd(ws.segsize + fp + x, len);
+  // i is not a root, so nobody adds to segsize[i]: a plain read is safe
+  atomicAdd(ws.segsize + fp + x, ws.segsize[fp + i]);
 }
 
 // label[i] is i's run start or one of its ancestors (always a run start), and after
@@ -321,6 +340,10 @@ __device__ __forceinline__ float buggy_abs(float x) { return __uint_as_float(__f
 // One output of the 8-tap filter.  x[k] = sample at coordinate c-4+k; the reference keeps
 // samples in a ring indexed by coordinate mod 8 and adds lanes (s, s+4) first, then
 // ((l0+l1)+l2)+l3 (elas.cpp:1425-1432); `rot` = (c-4) & 3 restores that order.
+// UNIFORM = rot is the same for the whole warp (vertical pass: a warp works on one row): a
+// uniform switch.  Otherwise (horizontal pass: rot = lane & 3) the four pair sums are rotated
+// into ring order with selects instead of a four-way divergent branch.
+template <bool UNIFORM>
 __device__ __forceinline__ bool mean8(const float x[8], float centre, int rot, float& out) {
   float w[8], f[8];
 #pragma unroll
@@ -334,11 +357,22 @@ __device__ __forceinline__ bool mean8(const float x[8], float centre, int rot, f
   for (int k = 0; k < 4; k++) { wq[k] = w[k] + w[k + 4]; fq[k] = f[k] + f[k + 4]; }
   // lane s holds pair k with (rot + k) & 3 == s  ->  k = (s - rot) & 3
   float ws, fs;
-  switch (rot) {
-    case 0: ws = ((wq[0] + wq[1]) + wq[2]) + wq[3]; fs = ((fq[0] + fq[1]) + fq[2]) + fq[3]; break;
-    case 1: ws = ((wq[3] + wq[0]) + wq[1]) + wq[2]; fs = ((fq[3] + fq[0]) + fq[1]) + fq[2]; break;
-    case 2: ws = ((wq[2] + wq[3]) + wq[0]) + wq[1]; fs = ((fq[2] + fq[3]) + fq[0]) + fq[1]; break;
-    default: ws = ((wq[1] + wq[2]) + wq[3]) + wq[0]; fs = ((fq[1] + fq[2]) + fq[3]) + fq[0]; break;
+  if (UNIFORM) {
+    switch (rot) {
+      case 0: ws = ((wq[0] + wq[1]) + wq[2]) + wq[3]; fs = ((fq[0] + fq[1]) + fq[2]) + fq[3]; break;
+      case 1: ws = ((wq[3] + wq[0]) + wq[1]) + wq[2]; fs = ((fq[3] + fq[0]) + fq[1]) + fq[2]; break;
+      case 2: ws = ((wq[2] + wq[3]) + wq[0]) + wq[1]; fs = ((fq[2] + fq[3]) + fq[0]) + fq[1]; break;
+      default: ws = ((wq[1] + wq[2]) + wq[3]) + wq[0]; fs = ((fq[1] + fq[2]) + fq[3]) + fq[0]; break;
+    }
+  } else {
+    const bool r1 = rot & 1, r2 = rot & 2;
+    float a[4], b[4], c[4], d[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) { a[j] = r1 ? wq[(j + 3) & 3] : wq[j]; b[j] = r1 ? fq[(j + 3) & 3] : fq[j]; }
+#pragma unroll
+    for (int j = 0; j < 4; j++) { c[j] = r2 ? a[(j + 2) & 3] : a[j]; d[j] = r2 ? b[(j + 2) & 3] : b[j]; }
+    ws = ((c[0] + c[1]) + c[2]) + c[3];
+    fs = ((d[0] + d[1]) + d[2]) + d[3];
   }
   if (ws > 0) {
     float d = fs / ws;
@@ -380,7 +414,7 @@ mean_fused_kernel(Geo g, Workspace ws, const float* __restrict__ in, float* __re
 #pragma unroll
       for (int k = 0; k < 8; k++) { const float t = s_in[r][c + k]; w8[k] = (t < 0) ? -10.f : t; }
       float m;
-      if (mean8(w8, w8[4], (x - 4) & 3, m)) o = m;
+      if (mean8<false>(w8, w8[4], (x - 4) & 3, m)) o = m;
     }
     s_tmp[r][c] = o;
   }
@@ -396,7 +430,7 @@ mean_fused_kernel(Geo g, Workspace ws, const float* __restrict__ in, float* __re
 #pragma unroll
       for (int k = 0; k < 8; k++) w8[k] = s_tmp[r + k][c];   // rows y-4 .. y+3
       float m;
-      if (mean8(w8, w8[4], (y - 4) & 3, m)) o = m;
+      if (mean8<true>(w8, w8[4], (y - 4) & 3, m)) o = m;
     }
     dst[(size_t)y * W + x] = o;
   }
@@ -541,11 +575,9 @@ void post_lr(const Geo& g, int B, Workspace& ws, cudaStream_t s) {
 
 void post_segments(const Geo& g, int B, Workspace& ws, int side, cudaStream_t s) {
   dim3 pg((g.Wd + 255) / 256, g.Hd, B);
-  cudaMemsetAsync(ws.segsize, 0, (size_t)B * g.Wd * g.Hd * sizeof(int32_t), s);
-  cudaMemsetAsync(ws.runlen, 0, (size_t)B * g.Wd * g.Hd * sizeof(int32_t), s);
-  seg_rows_kernel<<<dim3(g.Hd, B), ROW_THREADS, 0, s>>>(g, ws, side);
+  seg_rows_kernel<<<dim3((g.Hd + SEG_ROWS_PER_CTA - 1) / SEG_ROWS_PER_CTA, B), 32 * SEG_ROWS_PER_CTA, 0, s>>>(g, ws, side);
   seg_merge_kernel<<<pg, 256, 0, s>>>(g, ws, side);
-  seg_count_kernel<<<pg, 256, 0, s>>>(g, ws);
+  seg_count_kernel<<<pg, 256, 0, s>>>(g, ws, side);
   seg_apply_kernel<<<pg, 256, 0, s>>>(g, ws, side);
   g_jn_launches += 4;
 }

@@ -25,116 +25,89 @@
 namespace {
 
 constexpr int MATCH_THREADS = 512;
-constexpr unsigned EMPTY_KEY = (32767u << 16) | 0xFFFFu;
-
-struct Best {
-  unsigned key;  // (energy << 16) | disparity of the best match
-  unsigned e2;   // second smallest energy
-};
-
-__device__ __forceinline__ void best_update(Best& b, unsigned e, unsigned d) {
-  unsigned k = (e << 16) | d;
-  if (k < b.key) {
-    b.e2 = b.key >> 16;
-    b.key = k;
-  } else if (e < b.e2) {
-    b.e2 = e;
-  }
-}
-
-__device__ __forceinline__ Best best_merge_warp(Best b) {
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) {
-    unsigned ok = __shfl_xor_sync(0xffffffffu, b.key, off);
-    unsigned oe = __shfl_xor_sync(0xffffffffu, b.e2, off);
-    if (ok < b.key) {
-      b.e2 = min(b.key >> 16, oe);
-      b.key = ok;
-    } else {
-      b.e2 = min(ok >> 16, b.e2);
-    }
-  }
-  return b;
-}
-
 constexpr int KG = 4;   // candidates matched together by one warp
+constexpr int KEY_EMPTY = 0x7fffffff;
 
 // (best, second best) as two packed keys (energy << 16 | disparity): the smallest key is the
 // reference's best match (lowest energy, lowest disparity among ties, H7) and the energy of the
-// second smallest key is its second-best energy.  Updating needs only min/max.
+// second smallest key is its second-best energy.  Updating needs only min/max.  Inside the
+// search the keys are kept SHIFTED by a per-candidate constant (energy * 65536 + dir * position
+// instead of + disparity; disparity = dir * (position - u)), which preserves their order, is the
+// same for all KG candidates of a lane and is undone once after the search; shifted keys can be
+// slightly negative, hence signed.
 struct Best2 {
-  unsigned k1, k2;
+  int k1, k2;
 };
-__device__ __forceinline__ void best2_update(Best2& b, unsigned key) {
-  const unsigned hi = max(b.k1, key);
+__device__ __forceinline__ void best2_update(Best2& b, int key) {
+  const int hi = max(b.k1, key);
   b.k1 = min(b.k1, key);
   b.k2 = min(b.k2, hi);
 }
+// Warp-wide (smallest, second smallest) with two REDUX.MIN: keys of one candidate are distinct
+// across lanes and iterations (one per position), so the second smallest is the minimum over the
+// lanes of "my smallest, or my second smallest if mine is the global one".
 __device__ __forceinline__ Best2 best2_merge_warp(Best2 b) {
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) {
-    const unsigned o1 = __shfl_xor_sync(0xffffffffu, b.k1, off);
-    const unsigned o2 = __shfl_xor_sync(0xffffffffu, b.k2, off);
-    const unsigned hi = max(b.k1, o1);
-    b.k1 = min(b.k1, o1);
-    b.k2 = min(min(b.k2, o2), hi);
-  }
-  return b;
+  Best2 r;
+  r.k1 = __reduce_min_sync(0xffffffffu, b.k1);
+  r.k2 = __reduce_min_sync(0xffffffffu, (b.k1 == r.k1) ? b.k2 : b.k1);
+  return r;
+}
+
+// Gates of computeMatchingDisparity that do not depend on the search (elas.cpp:283-307): window
+// inside the image, texture of the centre descriptor, at least 11 disparities to look at.
+template <int DIR>
+__device__ __forceinline__ bool candidate_gate(const Geo& g, int u, const uint4* __restrict__ centre_row) {
+  if (u < 5 || u > g.W - 6) return false;
+  const int dmin = max(g.p.disp_min, 0);
+  const int dmax = (DIR < 0) ? min(g.p.disp_max, u - 5) : min(g.p.disp_max, g.W - u - 5);
+  if (dmax - dmin < 10) return false;
+  return (int)texture16(__ldg(centre_row + u)) >= g.p.support_texture;
 }
 
 // KG candidates, executed by a full warp.  rowA_* = descriptor rows of the image the pixels
-// live in, rowB_* = rows of the image searched; dir = -1 (left pixels, search u-d) or +1
-// (right pixels, search u+d); u[k] < 0 = empty slot.  The lanes stride POSITIONS of the
-// searched rows: every lane loads the four searched descriptors of its position once and
-// scores them against all KG candidates (disparity = distance to the candidate), so the
-// shared-memory traffic per candidate drops by KG.  32-position chunks that lie inside every
-// candidate's range take a path without any range test; the integer pipe then carries little
-// more than the 16 VABSDIFF4 per candidate and position (keys and disparities are formed with
-// IMAD on the FMA pipe).  res[k] = disparity or -1.
-__device__ __forceinline__ void match_group(const Geo& g, const int (&u)[KG], int dir, const uint4* rowA_t,
+// live in, rowB_* = rows of the image searched; DIR = -1 (left pixels, search u-d) or +1
+// (right pixels, search u+d); bit k of okmask = candidate k passed candidate_gate (the others
+// only need a readable u).  The lanes stride POSITIONS of the searched rows: every lane loads
+// the four searched descriptors of its position once and scores them against all KG candidates
+// (disparity = distance to the candidate), so the shared-memory traffic per candidate drops by
+// KG.  32-position chunks that lie inside every candidate's range take a straight-line path whose
+// integer-pipe work is the 16 VABSDIFF4 and 3 min/max per candidate and position (the keys are
+// formed with one IMAD each on the FMA pipe).  res[k] = disparity or -1.
+template <int DIR>
+__device__ __forceinline__ void match_group(const Geo& g, const int (&u)[KG], unsigned okmask, const uint4* rowA_t,
                                             const uint4* rowA_b, const uint4* rowB_t, const uint4* rowB_b,
-                                            const uint4* centre_row, int lane, int (&res)[KG]) {
+                                            int lane, int (&res)[KG]) {
   const int W = g.W;
   const int dmin = max(g.p.disp_min, 0);
+#pragma unroll
+  for (int k = 0; k < KG; k++) res[k] = -1;
+  if (okmask == 0u) return;
   uint4 a[KG][4];
   int p0[KG], p1[KG];     // position range of candidate k (empty if not ok)
-  bool ok[KG];
   Best2 best[KG];
   int plo = 0x7fffffff, phi = -0x7fffffff;   // union of the ranges
   int ilo = -0x7fffffff, ihi = 0x7fffffff;   // intersection of the ranges
-  uint4 c[KG];
 #pragma unroll
   for (int k = 0; k < KG; k++) {
-    ok[k] = u[k] >= 5 && u[k] <= W - 6;
-    c[k] = ok[k] ? __ldg(centre_row + u[k]) : make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u);
-  }
-#pragma unroll
-  for (int k = 0; k < KG; k++) {
-    const int dmax = (dir < 0) ? min(g.p.disp_max, u[k] - 5) : min(g.p.disp_max, W - u[k] - 5);
-    ok[k] = ok[k] && (int)texture16(c[k]) >= g.p.support_texture && (dmax - dmin >= 10);
-    best[k].k1 = 0xFFFFFFFFu;
-    best[k].k2 = 0xFFFFFFFFu;
-    res[k] = -1;
-    if (ok[k]) {
-      a[k][0] = rowA_t[u[k] - 2]; a[k][1] = rowA_t[u[k] + 2];
-      a[k][2] = rowA_b[u[k] - 2]; a[k][3] = rowA_b[u[k] + 2];
-      p0[k] = (dir < 0) ? u[k] - dmax : u[k] + dmin;
-      p1[k] = (dir < 0) ? u[k] - dmin : u[k] + dmax;
+    const bool ok = (okmask >> k) & 1u;
+    const int uk = ok ? u[k] : 8;             // any readable column: the scores are discarded
+    a[k][0] = rowA_t[uk - 2]; a[k][1] = rowA_t[uk + 2];
+    a[k][2] = rowA_b[uk - 2]; a[k][3] = rowA_b[uk + 2];
+    best[k].k1 = KEY_EMPTY;
+    best[k].k2 = KEY_EMPTY;
+    const int dmax = (DIR < 0) ? min(g.p.disp_max, uk - 5) : min(g.p.disp_max, W - uk - 5);
+    p0[k] = ok ? ((DIR < 0) ? uk - dmax : uk + dmin) : 1;
+    p1[k] = ok ? ((DIR < 0) ? uk - dmin : uk + dmax) : 0;
+    if (ok) {
       plo = min(plo, p0[k]); phi = max(phi, p1[k]);
       ilo = max(ilo, p0[k]); ihi = min(ihi, p1[k]);
-    } else {
-      a[k][0] = a[k][1] = a[k][2] = a[k][3] = make_uint4(0, 0, 0, 0);
-      p0[k] = 1; p1[k] = 0;
     }
   }
-  if (plo > phi) return;   // no candidate of the group survives the gates
-  bool allok = true;
-#pragma unroll
-  for (int k = 0; k < KG; k++) allok = allok && ok[k];
-  // disparity of candidate k at position p:  dir*(p - u[k])  ->  key = e * 65536 + d
+  const bool allok = okmask == (1u << KG) - 1u;
   for (int base = plo; base <= phi; base += 32) {
     const int p = min(base + lane, phi);
     const uint4 s0 = rowB_t[p - 2], s1 = rowB_t[p + 2], s2 = rowB_b[p - 2], s3 = rowB_b[p + 2];
+    const int shift = DIR * p;
     if (allok && base >= ilo && base + 31 <= ihi) {
       // common case: every candidate live, chunk inside every range -> straight-line code
 #pragma unroll
@@ -143,38 +116,30 @@ __device__ __forceinline__ void match_group(const Geo& g, const int (&u)[KG], in
         e = sad16(a[k][1], s1, e);
         e = sad16(a[k][2], s2, e);
         e = sad16(a[k][3], s3, e);
-        best2_update(best[k], e * 65536u + (unsigned)(dir * (p - u[k])));
-      }
-    } else if (base >= ilo && base + 31 <= ihi) {
-#pragma unroll
-      for (int k = 0; k < KG; k++) {
-        if (!ok[k]) continue;
-        unsigned e = sad16(a[k][0], s0, 0u);
-        e = sad16(a[k][1], s1, e);
-        e = sad16(a[k][2], s2, e);
-        e = sad16(a[k][3], s3, e);
-        best2_update(best[k], e * 65536u + (unsigned)(dir * (p - u[k])));
+        best2_update(best[k], (int)e * 65536 + shift);
       }
     } else {
       const bool lane_in = base + lane <= phi;
 #pragma unroll
       for (int k = 0; k < KG; k++) {
-        if (!ok[k]) continue;
         unsigned e = sad16(a[k][0], s0, 0u);
         e = sad16(a[k][1], s1, e);
         e = sad16(a[k][2], s2, e);
         e = sad16(a[k][3], s3, e);
-        const unsigned key = e * 65536u + (unsigned)(dir * (p - u[k]));
-        best2_update(best[k], (lane_in && p >= p0[k] && p <= p1[k]) ? key : 0xFFFFFFFFu);
+        // p0 > p1 for a candidate that is not ok: never in range
+        best2_update(best[k], (lane_in && p >= p0[k] && p <= p1[k]) ? (int)e * 65536 + shift : KEY_EMPTY);
       }
     }
   }
 #pragma unroll
   for (int k = 0; k < KG; k++) {
-    if (!ok[k]) continue;
+    if (!((okmask >> k) & 1u)) continue;
     const Best2 b = best2_merge_warp(best[k]);
-    const float e1 = (float)(b.k1 >> 16), e2 = (float)(b.k2 >> 16);
-    if (e1 < __fmul_rn(g.p.support_threshold, e2)) res[k] = (int)(b.k1 & 0xFFFFu);
+    // undo the shift: key = e * 65536 + DIR * (p - u)
+    const int t1 = b.k1 - DIR * u[k];
+    const float e1 = (float)(t1 >> 16);
+    const float e2 = (b.k2 == KEY_EMPTY) ? 65535.f : (float)((b.k2 - DIR * u[k]) >> 16);
+    if (e1 < __fmul_rn(g.p.support_threshold, e2)) res[k] = t1 & 0xFFFF;
   }
 }
 
@@ -204,8 +169,8 @@ support_match_kernel(Geo g, const uint8_t* __restrict__ desc1, const uint8_t* __
   uint4* R_t = reinterpret_cast<uint4*>(smem + 2 * rowbytes);
   uint4* R_b = reinterpret_cast<uint4*>(smem + 3 * rowbytes);
   int* fwd = reinterpret_cast<int*>(smem + 4 * rowbytes);             // forward disparity per candidate
-  int* list = reinterpret_cast<int*>(smem + 4 * rowbytes + wcb);      // candidates that passed forward
-  int* resv = reinterpret_cast<int*>(smem + 4 * rowbytes + 2 * wcb);  // final disparity per candidate
+  int* list = reinterpret_cast<int*>(smem + 4 * rowbytes + wcb);      // candidates that go to the cross check
+  int* resv = reinterpret_cast<int*>(smem + 4 * rowbytes + 2 * wcb);  // gate flags, then final disparity
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 4 * rowbytes + 3 * wcb);
 
   const uint8_t* d1 = desc1 + (size_t)frame * W * H * 16;
@@ -222,32 +187,46 @@ support_match_kernel(Geo g, const uint8_t* __restrict__ desc1, const uint8_t* __
     bulk_g2s(R_t, d2 + (size_t)(v - 2) * rowbytes, (uint32_t)rowbytes, bar);
     bulk_g2s(R_b, d2 + (size_t)(v + 2) * rowbytes, (uint32_t)rowbytes, bar);
   }
-  for (int uc = tid; uc < Wc; uc += MATCH_THREADS) resv[uc] = (uc == 0) ? 0 : -1;
-  mbar_wait(bar, 0);
-
   const uint4* c1 = reinterpret_cast<const uint4*>(d1 + (size_t)v * rowbytes);
   const uint4* c2 = reinterpret_cast<const uint4*>(d2 + (size_t)v * rowbytes);
+  // while the rows are in flight: gates of the forward candidates (centre descriptors from L2)
+  for (int uc = tid; uc < Wc; uc += MATCH_THREADS) {
+    resv[uc] = (uc >= 1 && candidate_gate<-1>(g, uc * step, c1)) ? 1 : 0;
+    fwd[uc] = -1;
+  }
+  __syncthreads();
+  mbar_wait(bar, 0);
 
   // forward: left pixels (u,v) -> right image, KG lattice neighbours per warp pass
   const int ngroups = (Wc - 1 + KG - 1) / KG;
   for (int gi = warp; gi < ngroups; gi += nwarps) {
     int u[KG], r[KG];
+    unsigned okmask = 0u;
 #pragma unroll
     for (int k = 0; k < KG; k++) {
-      int uc = 1 + gi * KG + k;
-      u[k] = (uc < Wc) ? uc * step : -1;
+      const int uc = 1 + gi * KG + k;
+      u[k] = uc * step;
+      if (uc < Wc && resv[uc]) okmask |= 1u << k;
     }
-    match_group(g, u, -1, L_t, L_b, R_t, R_b, c1, lane, r);
+    match_group<-1>(g, u, okmask, L_t, L_b, R_t, R_b, lane, r);
     if (lane == 0) {
 #pragma unroll
       for (int k = 0; k < KG; k++) {
-        int uc = 1 + gi * KG + k;
+        const int uc = 1 + gi * KG + k;
         if (uc < Wc) fwd[uc] = r[k];
       }
     }
   }
   __syncthreads();
-  // compact the candidates that have a forward match (order preserved: neighbours stay together)
+  // gates of the backward candidates (right pixel u-d), all threads; then the final-result array
+  for (int uc = tid; uc < Wc; uc += MATCH_THREADS) {
+    const int d = fwd[uc];
+    const bool go = d >= 0 && candidate_gate<+1>(g, uc * step - d, c2);
+    if (!go) fwd[uc] = -1;
+    resv[uc] = (uc == 0) ? 0 : -1;
+  }
+  __syncthreads();
+  // compact the candidates that go on (order preserved: neighbours stay together)
   if (warp == 0) {
     int n = 0;
     for (int base = 1; base < Wc; base += 32) {
@@ -264,14 +243,16 @@ support_match_kernel(Geo g, const uint8_t* __restrict__ desc1, const uint8_t* __
   const int nvalid = s_nvalid;
   for (int gi = warp; gi * KG < nvalid; gi += nwarps) {
     int u[KG], r[KG], ucs[KG], df[KG];
+    unsigned okmask = 0u;
 #pragma unroll
     for (int k = 0; k < KG; k++) {
-      int i = gi * KG + k;
+      const int i = gi * KG + k;
       ucs[k] = (i < nvalid) ? list[i] : -1;
       df[k] = (ucs[k] >= 0) ? fwd[ucs[k]] : 0;
-      u[k] = (ucs[k] >= 0) ? ucs[k] * step - df[k] : -1;
+      u[k] = (ucs[k] >= 0) ? ucs[k] * step - df[k] : 8;
+      if (ucs[k] >= 0) okmask |= 1u << k;
     }
-    match_group(g, u, +1, R_t, R_b, L_t, L_b, c2, lane, r);
+    match_group<+1>(g, u, okmask, R_t, R_b, L_t, L_b, lane, r);
     if (lane == 0) {
 #pragma unroll
       for (int k = 0; k < KG; k++)
