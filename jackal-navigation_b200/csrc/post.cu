@@ -50,6 +50,37 @@ __global__ void lr_kernel(Geo g, Workspace ws) {
   ws.Dlr[1][a] = o2;
 }
 
+// Four pixels per thread (map width a multiple of 4): 128-bit loads and stores, four times the
+// memory-level parallelism per thread.  Same arithmetic as lr_kernel.
+constexpr int Q_THREADS = 128;   // threads per CTA of the quad kernels; a CTA covers 512 pixels of a row
+
+__global__ void __launch_bounds__(Q_THREADS) lr4_kernel(Geo g, Workspace ws) {
+  const int frame = blockIdx.z;
+  if (ws.info[frame].status != JN_OK) return;
+  const int W = g.Wd, H = g.Hd;
+  const int q = blockIdx.x * Q_THREADS + threadIdx.x, v = blockIdx.y;
+  if (4 * q >= W) return;
+  const size_t rb = (size_t)frame * W * H + (size_t)v * W;
+  const float* __restrict__ D1 = ws.Draw[0] + rb;
+  const float* __restrict__ D2 = ws.Draw[1] + rb;
+  const float thr = (float)g.p.lr_threshold;
+  const bool sub = g.p.subsampling != 0;
+  const float4 a = reinterpret_cast<const float4*>(D1)[q], b = reinterpret_cast<const float4*>(D2)[q];
+  const float d1[4] = {a.x, a.y, a.z, a.w}, d2[4] = {b.x, b.y, b.z, b.w};
+  float o1[4], o2[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const int u = 4 * q + j;
+    const float uw1 = sub ? (float)u - d1[j] / 2 : (float)u - d1[j], uw2 = sub ? (float)u + d2[j] / 2 : (float)u + d2[j];
+    o1[j] = -10.f;
+    o2[j] = -10.f;
+    if (d1[j] >= 0 && uw1 >= 0 && uw1 < (float)W) o1[j] = (fabsf(D2[(int)uw1] - d1[j]) > thr) ? -10.f : d1[j];
+    if (d2[j] >= 0 && uw2 >= 0 && uw2 < (float)W) o2[j] = (fabsf(D1[(int)uw2] - d2[j]) > thr) ? -10.f : d2[j];
+  }
+  reinterpret_cast<float4*>(ws.Dlr[0] + rb)[q] = make_float4(o1[0], o1[1], o1[2], o1[3]);
+  reinterpret_cast<float4*>(ws.Dlr[1] + rb)[q] = make_float4(o2[0], o2[1], o2[2], o2[3]);
+}
+
 // ------------------------------------------------------------ small segments
 constexpr int ROW_THREADS = 256;
 
@@ -208,6 +239,102 @@ __global__ void seg_apply_kernel(Geo g, Workspace ws, int side) {
   if (ws.segsize[fp + root] < g.speckle_eff) ws.Dlr[side][a] = -10.f;
 }
 
+// Quad versions of the three kernels above (map width a multiple of 4).
+__global__ void __launch_bounds__(Q_THREADS) seg_merge4_kernel(Geo g, Workspace ws, int side) {
+  const int frame = blockIdx.z;
+  if (ws.info[frame].status != JN_OK) return;
+  const int W = g.Wd, H = g.Hd;
+  const int q = blockIdx.x * Q_THREADS + threadIdx.x, v = blockIdx.y;
+  if (v + 1 >= H) return;                       // uniform per CTA
+  const size_t fp = (size_t)frame * W * H;
+  const float* __restrict__ D = ws.Dlr[side] + fp;
+  const float thr = g.p.speckle_sim_threshold;
+  const int i0 = v * W + 4 * q;
+  const bool in = 4 * q < W;
+  const float4 none = make_float4(-10.f, -10.f, -10.f, -10.f);
+  const float4 dq = in ? *reinterpret_cast<const float4*>(D + i0) : none;
+  const float4 eq = in ? *reinterpret_cast<const float4*>(D + i0 + W) : none;
+  float dl = __shfl_up_sync(0xffffffffu, dq.w, 1), el = __shfl_up_sync(0xffffffffu, eq.w, 1);
+  if ((threadIdx.x & 31) == 0) {
+    dl = (in && q > 0) ? D[i0 - 1] : -10.f;
+    el = (in && q > 0) ? D[i0 + W - 1] : -10.f;
+  }
+  const float d[4] = {dq.x, dq.y, dq.z, dq.w}, e[4] = {eq.x, eq.y, eq.z, eq.w};
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    if (d[j] >= 0 && e[j] >= 0 && fabsf(d[j] - e[j]) <= thr &&
+        !(dl >= 0 && el >= 0 && fabsf(d[j] - dl) <= thr && fabsf(e[j] - el) <= thr && fabsf(dl - el) <= thr))
+      uf_union(ws.label + fp, i0 + j, i0 + j + W);
+    dl = d[j];
+    el = e[j];
+  }
+}
+
+__global__ void __launch_bounds__(Q_THREADS) seg_count4_kernel(Geo g, Workspace ws, int side) {
+  const int frame = blockIdx.z;
+  if (ws.info[frame].status != JN_OK) return;
+  const int W = g.Wd, H = g.Hd;
+  const int q = blockIdx.x * Q_THREADS + threadIdx.x, v = blockIdx.y;
+  const size_t fp = (size_t)frame * W * H;
+  const float* __restrict__ D = ws.Dlr[side] + fp;
+  const float thr = g.p.speckle_sim_threshold;
+  const int i0 = v * W + 4 * q;
+  const bool in = 4 * q < W;
+  const float4 dq = in ? *reinterpret_cast<const float4*>(D + i0) : make_float4(-10.f, -10.f, -10.f, -10.f);
+  float prev = __shfl_up_sync(0xffffffffu, dq.w, 1);
+  if ((threadIdx.x & 31) == 0) prev = (in && q > 0) ? D[i0 - 1] : -10.f;
+  if (q == 0) prev = -10.f;
+  const float d[4] = {dq.x, dq.y, dq.z, dq.w};
+  int* label = ws.label + fp;
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const bool start = d[j] >= 0 && !(prev >= 0 && fabsf(d[j] - prev) <= thr);
+    prev = d[j];
+    if (!start) continue;
+    const int i = i0 + j;
+    int x = i, p = __ldcg(label + x);
+    while (p != x) {
+      int gp = __ldcg(label + p);
+      if (gp != p) atomicMin(label + x, gp);
+      x = p;
+      p = gp;
+    }
+    if (x == i) continue;
+    atomicMin(label + i, x);
+    atomicAdd(ws.segsize + fp + x, ws.segsize[fp + i]);
+  }
+}
+
+__global__ void __launch_bounds__(Q_THREADS) seg_apply4_kernel(Geo g, Workspace ws, int side) {
+  const int frame = blockIdx.z;
+  if (ws.info[frame].status != JN_OK) return;
+  const int W = g.Wd, H = g.Hd;
+  const int q = blockIdx.x * Q_THREADS + threadIdx.x, v = blockIdx.y;
+  if (4 * q >= W) return;
+  const size_t fp = (size_t)frame * W * H;
+  const size_t a = fp + (size_t)v * W + 4 * q;
+  const int4 lq = *reinterpret_cast<const int4*>(ws.label + a);
+  if (lq.x < 0 && lq.y < 0 && lq.z < 0 && lq.w < 0) return;
+  const int l[4] = {lq.x, lq.y, lq.z, lq.w};
+  bool kill[4], any = false, pk = false;
+  int pl = -1;
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    if (l[j] < 0) { kill[j] = false; continue; }
+    if (l[j] != pl) {       // pixels of one run share the label: look the component up once
+      pl = l[j];
+      pk = ws.segsize[fp + ws.label[fp + pl]] < g.speckle_eff;
+    }
+    kill[j] = pk;
+    any = any || pk;
+  }
+  if (!any) return;
+  float* D = ws.Dlr[side] + a;
+#pragma unroll
+  for (int j = 0; j < 4; j++)
+    if (kill[j]) D[j] = -10.f;
+}
+
 // ------------------------------------------------------------ gap interpolation
 __device__ __forceinline__ float ipol(float d1, float d2) {
   return (fabsf(d1 - d2) < 3.0f) ? (d1 + d2) / 2 : fminf(d1, d2);
@@ -290,6 +417,45 @@ __global__ void gap_small_kernel(Geo g, Workspace ws, const float* __restrict__ 
     }
   }
   out[fp + i] = d;
+}
+
+// Quad version: pixels are valid far more often than not, and a quad without an invalid pixel is
+// one 128-bit load and one 128-bit store.
+template <bool ROWS>
+__global__ void __launch_bounds__(Q_THREADS)
+gap_small4_kernel(Geo g, Workspace ws, const float* __restrict__ in, float* __restrict__ out) {
+  const int frame = blockIdx.z;
+  if (ws.info[frame].status != JN_OK) return;
+  const int W = g.Wd, H = g.Hd, gap = g.gap_eff;
+  const int q = blockIdx.x * Q_THREADS + threadIdx.x, v = blockIdx.y;
+  if (4 * q >= W) return;
+  const size_t fp = (size_t)frame * W * H;
+  const float* D = in + fp;
+  const int i0 = v * W + 4 * q;
+  const float4 c = *reinterpret_cast<const float4*>(D + i0);
+  float d[4] = {c.x, c.y, c.z, c.w};
+  if (!(c.x >= 0 && c.y >= 0 && c.z >= 0 && c.w >= 0)) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      if (d[j] >= 0) continue;
+      const int i = i0 + j;
+      const int pos = ROWS ? 4 * q + j : v, len = ROWS ? W : H, stride = ROWS ? 1 : W;
+      int l = 0, r = 0;
+      float dl = -1.f, dr = -1.f;
+      for (int k = 1; k <= gap && pos - k >= 0; k++) {
+        float t = D[i - k * stride];
+        if (t >= 0) { l = k; dl = t; break; }
+      }
+      if (l > 0) {
+        for (int k = 1; k <= gap + 1 - l && pos + k < len; k++) {
+          float t = D[i + k * stride];
+          if (t >= 0) { r = k; dr = t; break; }
+        }
+        if (r > 0) d[j] = ipol(dl, dr);   // run length l + r - 1 <= gap
+      }
+    }
+  }
+  *reinterpret_cast<float4*>(out + fp + i0) = make_float4(d[0], d[1], d[2], d[3]);
 }
 
 __global__ void gap_cols_kernel(Geo g, Workspace ws, int side) {
@@ -569,24 +735,38 @@ __global__ void copy_out_kernel(Geo g, Workspace ws, const float* __restrict__ i
 
 // Step-wise entry points (the debug dump calls them one at a time).
 void post_lr(const Geo& g, int B, Workspace& ws, cudaStream_t s) {
-  lr_kernel<<<dim3((g.Wd + 255) / 256, g.Hd, B), 256, 0, s>>>(g, ws);
+  if (g.Wd % 4 == 0) lr4_kernel<<<dim3((g.Wd / 4 + Q_THREADS - 1) / Q_THREADS, g.Hd, B), Q_THREADS, 0, s>>>(g, ws);
+  else lr_kernel<<<dim3((g.Wd + 255) / 256, g.Hd, B), 256, 0, s>>>(g, ws);
   g_jn_launches += 1;
 }
 
 void post_segments(const Geo& g, int B, Workspace& ws, int side, cudaStream_t s) {
   dim3 pg((g.Wd + 255) / 256, g.Hd, B);
   seg_rows_kernel<<<dim3((g.Hd + SEG_ROWS_PER_CTA - 1) / SEG_ROWS_PER_CTA, B), 32 * SEG_ROWS_PER_CTA, 0, s>>>(g, ws, side);
-  seg_merge_kernel<<<pg, 256, 0, s>>>(g, ws, side);
-  seg_count_kernel<<<pg, 256, 0, s>>>(g, ws, side);
-  seg_apply_kernel<<<pg, 256, 0, s>>>(g, ws, side);
+  if (g.Wd % 4 == 0) {
+    dim3 qg((g.Wd / 4 + Q_THREADS - 1) / Q_THREADS, g.Hd, B);
+    seg_merge4_kernel<<<qg, Q_THREADS, 0, s>>>(g, ws, side);
+    seg_count4_kernel<<<qg, Q_THREADS, 0, s>>>(g, ws, side);
+    seg_apply4_kernel<<<qg, Q_THREADS, 0, s>>>(g, ws, side);
+  } else {
+    seg_merge_kernel<<<pg, 256, 0, s>>>(g, ws, side);
+    seg_count_kernel<<<pg, 256, 0, s>>>(g, ws, side);
+    seg_apply_kernel<<<pg, 256, 0, s>>>(g, ws, side);
+  }
   g_jn_launches += 4;
 }
 
 void post_gap(const Geo& g, int B, Workspace& ws, int side, cudaStream_t s) {
   if (g.gap_eff <= SMALL_GAP && !g.p.add_corners) {
-    dim3 pg((g.Wd + 255) / 256, g.Hd, B);
-    gap_small_kernel<true><<<pg, 256, 0, s>>>(g, ws, ws.Dlr[side], ws.Dtmp[side]);
-    gap_small_kernel<false><<<pg, 256, 0, s>>>(g, ws, ws.Dtmp[side], ws.Dlr[side]);
+    if (g.Wd % 4 == 0) {
+      dim3 qg((g.Wd / 4 + Q_THREADS - 1) / Q_THREADS, g.Hd, B);
+      gap_small4_kernel<true><<<qg, Q_THREADS, 0, s>>>(g, ws, ws.Dlr[side], ws.Dtmp[side]);
+      gap_small4_kernel<false><<<qg, Q_THREADS, 0, s>>>(g, ws, ws.Dtmp[side], ws.Dlr[side]);
+    } else {
+      dim3 pg((g.Wd + 255) / 256, g.Hd, B);
+      gap_small_kernel<true><<<pg, 256, 0, s>>>(g, ws, ws.Dlr[side], ws.Dtmp[side]);
+      gap_small_kernel<false><<<pg, 256, 0, s>>>(g, ws, ws.Dtmp[side], ws.Dlr[side]);
+    }
   } else {
     gap_rows_kernel<<<dim3(g.Hd, B), ROW_THREADS, g.Wd * sizeof(float), s>>>(g, ws, side);
     gap_cols_kernel<<<dim3((g.Wd + 63) / 64, B), 64, 0, s>>>(g, ws, side);
