@@ -160,9 +160,40 @@ int jn_points_from_disparity(jn_scan* s, const float* D, double* points,
                              int32_t* n_points, double ranges[JN_SCAN_BINS],
                              jn_scan_meta* meta);
 
+/* sensor_msgs/PointCloud payload of the -g path (point_cloud.cpp:351-383), same point order as
+ * jn_points_from_disparity: xyz = geometry_msgs/Point32 per point (float32 x,y,z), rgb = one
+ * ChannelFloat32 value per point (bits of int32 red<<16 | green<<8 | blue taken from the left
+ * image at the point's pixel).  image: host, `channels` = 3 (BGR, 3 bytes per pixel) or 1 (the
+ * reference's grayscale frames, which it still indexes as Vec3b: bytes 3i..3i+2 of row j, 0
+ * beyond the buffer); image_stride in bytes.  xyz: W*H*3 floats capacity, rgb: W*H floats.
+ * Also returns the scan of those points like jn_points_from_disparity. */
+int jn_pointcloud_from_disparity(jn_scan* s, const float* D, const uint8_t* image, int32_t image_stride,
+                                 int32_t channels, float* xyz, float* rgb, int32_t* n_points,
+                                 double ranges[JN_SCAN_BINS], jn_scan_meta* meta);
+
 /* Compacted LaserScan.ranges as the reference publishes them: finite bins,
  * k = 89..0 (point_cloud.cpp:278-282).  Returns the count. */
 int jn_scan_compact(const double ranges[JN_SCAN_BINS], float* out);
+
+/* ---- rectification ahead of the stereo path ------------
+ * Replaces, per camera frame,
+ *     cv::remap(tmp, leftim, lmapx, lmapy, cv::INTER_LINEAR);           point_cloud.cpp:440, 481
+ *     leftim_res = leftim(Rect(crop_offset_x, crop_offset_y, w, h));    point_cloud.cpp:442, 483
+ * for 8-bit single-channel frames and the default border (constant 0), bit for bit with
+ * OpenCV's fixed-point bilinear remap (1/32-pixel coordinates, 15-bit weights). */
+typedef struct jn_rectify jn_rectify;
+
+/* mapx/mapy: the CV_32FC1 pair cv::initUndistortRectifyMap returns (point_cloud.cpp:553-554),
+ * host pointers, map_w x map_h, row-major.  The tables are converted to OpenCV's fixed-point form
+ * once and kept on `device`.  NULL on error (jn_last_error). */
+jn_rectify* jn_rectify_create(const float* mapx, const float* mapy, int32_t map_w, int32_t map_h, int32_t device);
+void jn_rectify_destroy(jn_rectify* r);
+
+/* n frames, DEVICE pointers, asynchronous on `stream` (cudaStream_t).  src: n frames of src_h
+ * rows, src_stride bytes per row.  roi = {x, y, w, h} in map coordinates (NULL = the whole map).
+ * dst: n frames of roi h rows, dst_stride bytes per row -- rows laid out as Elas::process takes them. */
+int jn_rectify_batch(jn_rectify* r, int32_t n, const uint8_t* src, int32_t src_w, int32_t src_h, int32_t src_stride,
+                     const int32_t roi[4], uint8_t* dst, int32_t dst_stride, void* stream);
 
 #ifdef __cplusplus
 }

@@ -113,6 +113,12 @@ def lib():
         l.jn_scan_from_disparity.argtypes = [_P, _P, _P, C.POINTER(ScanMeta), _P]
         l.jn_points_from_disparity.argtypes = [_P, _P, _P, C.POINTER(C.c_int32), _P, C.POINTER(ScanMeta)]
         l.jn_scan_compact.argtypes = [_P, _P]
+        l.jn_pointcloud_from_disparity.argtypes = [_P, _P, _P, C.c_int32, C.c_int32, _P, _P, C.POINTER(C.c_int32), _P,
+                                                   C.POINTER(ScanMeta)]
+        l.jn_rectify_create.restype = _P
+        l.jn_rectify_create.argtypes = [_P, _P, C.c_int32, C.c_int32, C.c_int32]
+        l.jn_rectify_destroy.argtypes = [_P]
+        l.jn_rectify_batch.argtypes = [_P, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, C.c_int32, _P]
         _lib = l
     return _lib
 
@@ -353,6 +359,22 @@ class ObstacleScan:
                "jn_points_from_disparity")
         return pts[:n.value], ranges, meta
 
+    def pointcloud(self, D, image):
+        """sensor_msgs/PointCloud payload (point_cloud.cpp:351-383): (xyz float32 n x 3, rgb float32 n,
+        ranges, meta).  image: H x W x 3 BGR or H x W grayscale (the reference's Vec3b-on-gray quirk)."""
+        D = np.ascontiguousarray(D, np.float32)
+        image = np.ascontiguousarray(image, np.uint8)
+        channels = 3 if image.ndim == 3 else 1
+        xyz = np.zeros((self.W * self.H, 3), np.float32)
+        rgb = np.zeros(self.W * self.H, np.float32)
+        n = C.c_int32(0)
+        ranges = np.zeros(SCAN_BINS, np.float64)
+        meta = ScanMeta()
+        _check(lib().jn_pointcloud_from_disparity(self._h, _ptr(D), _ptr(image), image.strides[0], channels, _ptr(xyz),
+                                                  _ptr(rgb), C.byref(n), _ptr(ranges), C.byref(meta)),
+               "jn_pointcloud_from_disparity")
+        return xyz[:n.value], rgb[:n.value], ranges, meta
+
 
 def scan_compact(ranges):
     """LaserScan.ranges as the reference publishes them (finite bins, k = 89..0)."""
@@ -360,3 +382,36 @@ def scan_compact(ranges):
     out = np.zeros(SCAN_BINS, np.float32)
     n = lib().jn_scan_compact(_ptr(ranges), _ptr(out))
     return out[:n]
+
+
+class Rectifier:
+    """cv::remap(frame, out, mapx, mapy, INTER_LINEAR) + ROI crop of one camera (point_cloud.cpp:440-442),
+    with the CV_32FC1 map pair of cv::initUndistortRectifyMap (point_cloud.cpp:553-554)."""
+
+    def __init__(self, mapx, mapy, device=0):
+        mapx = np.ascontiguousarray(mapx, np.float32)
+        mapy = np.ascontiguousarray(mapy, np.float32)
+        if mapx.shape != mapy.shape or mapx.ndim != 2:
+            raise ValueError("mapx and mapy must be 2-D arrays of the same shape")
+        self.map_h, self.map_w = mapx.shape
+        self._h = lib().jn_rectify_create(_ptr(mapx), _ptr(mapy), self.map_w, self.map_h, int(device))
+        if not self._h:
+            raise JnError("jn_rectify_create: " + last_error())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().jn_rectify_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def remap_batch(self, src, n, src_w, src_h, src_stride, dst, dst_stride, roi=None, stream=0):
+        """Device pointers (ints); asynchronous on `stream`."""
+        r = (C.c_int32 * 4)(*[int(x) for x in roi]) if roi is not None else None
+        return _check(lib().jn_rectify_batch(self._h, int(n), _P(src), int(src_w), int(src_h), int(src_stride), r,
+                                             _P(dst), int(dst_stride), _P(stream) if stream else None),
+                      "jn_rectify_batch")

@@ -248,6 +248,30 @@ __global__ void points_write_kernel(ScanConst c, const float* __restrict__ D, co
     k++;
   }
 }
+// Point32 + rgb channel of every point, in the order of points_write_kernel (point_cloud.cpp:351-383)
+__global__ void cloud_pack_kernel(ScanConst c, const float* __restrict__ D, const int* __restrict__ coloff,
+                                  const double* __restrict__ pts, const uint8_t* __restrict__ img, int stride,
+                                  int channels, float* __restrict__ xyz, float* __restrict__ rgb) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c.W) return;
+  size_t k = coloff[i];
+  const size_t img_bytes = (size_t)stride * c.H;
+  for (int j = 0; j < c.H; j++) {
+    if (to_u8(D[(size_t)j * c.W + i]) < 2) continue;
+    xyz[3 * k] = (float)pts[3 * k];
+    xyz[3 * k + 1] = (float)pts[3 * k + 1];
+    xyz[3 * k + 2] = (float)pts[3 * k + 2];
+    int ch[3];
+#pragma unroll
+    for (int b = 0; b < 3; b++) {
+      const size_t a = (size_t)j * stride + 3 * (size_t)i + b;
+      ch[b] = (channels == 3 || a < img_bytes) ? img[a] : 0;
+    }
+    rgb[k] = __int_as_float((ch[2] << 16) | (ch[1] << 8) | ch[0]);
+    k++;
+  }
+}
+
 __global__ void __launch_bounds__(SCAN_THREADS)
 scan_points_kernel(ScanConst c, const double* __restrict__ pts, const int* __restrict__ n_ptr,
                    unsigned long long* __restrict__ acc) {
@@ -384,6 +408,46 @@ extern "C" int jn_points_from_disparity(jn_scan* s, const float* D, double* poin
   JN_CUDA_CHECK(cudaMemcpy(points, s->dPts, (size_t)total * 3 * sizeof(double), cudaMemcpyDeviceToHost));
   JN_CUDA_CHECK(cudaMemcpy(ranges, s->dRanges, JN_SCAN_BINS * sizeof(double), cudaMemcpyDeviceToHost));
   JN_CUDA_CHECK(cudaMemcpy(meta, s->dMeta, sizeof(jn_scan_meta), cudaMemcpyDeviceToHost));
+  return JN_OK;
+}
+
+extern "C" int jn_pointcloud_from_disparity(jn_scan* s, const float* D, const uint8_t* image, int32_t image_stride,
+                                            int32_t channels, float* xyz, float* rgb, int32_t* n_points,
+                                            double ranges[JN_SCAN_BINS], jn_scan_meta* meta) {
+  if (!s || !D || !image || !xyz || !rgb || !n_points || !ranges || !meta || (channels != 1 && channels != 3) ||
+      image_stride < s->c.W * channels) {
+    jn_set_error("jn_pointcloud_from_disparity: bad arguments");
+    return JN_ERR_ARG;
+  }
+  const size_t n = (size_t)s->c.W * s->c.H, ibytes = (size_t)image_stride * s->c.H;
+  int rc = ensure_acc(s, 1);
+  if (rc) return rc;
+  JN_CUDA_CHECK(cudaSetDevice(s->device));
+  uint8_t* dImg = nullptr;
+  float* dXyz = nullptr;
+  JN_CUDA_CHECK(cudaMalloc(&dImg, ibytes));
+  if (cudaMalloc(&dXyz, n * 4 * sizeof(float)) != cudaSuccess) { cudaFree(dImg); jn_set_error("cudaMalloc failed"); return JN_ERR_CUDA; }
+  float* dRgb = dXyz + n * 3;
+  cudaMemcpy(dImg, image, ibytes, cudaMemcpyHostToDevice);
+  cudaMemcpy(s->dD, D, n * sizeof(float), cudaMemcpyHostToDevice);
+  points_count_kernel<<<(s->c.W + 127) / 128, 128>>>(s->c, s->dD, s->dCol);
+  points_scan_kernel<<<1, 32>>>(s->dCol, s->c.W, s->dTotal);
+  points_write_kernel<<<(s->c.W + 127) / 128, 128>>>(s->c, s->dD, s->dCol, s->dPts);
+  cloud_pack_kernel<<<(s->c.W + 127) / 128, 128>>>(s->c, s->dD, s->dCol, s->dPts, dImg, image_stride, channels, dXyz, dRgb);
+  acc_reset_kernel<<<1, 128>>>(s->acc, 1);
+  scan_points_kernel<<<148, SCAN_THREADS>>>(s->c, s->dPts, s->dTotal, s->acc);
+  scan_finalize_kernel<<<1, 96>>>(s->acc, s->dRanges, s->dMeta);
+  g_jn_launches += 7;
+  int total = 0;
+  cudaError_t e = cudaMemcpy(&total, s->dTotal, sizeof(int), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(xyz, dXyz, (size_t)total * 3 * sizeof(float), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(rgb, dRgb, (size_t)total * sizeof(float), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(ranges, s->dRanges, JN_SCAN_BINS * sizeof(double), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(meta, s->dMeta, sizeof(jn_scan_meta), cudaMemcpyDeviceToHost);
+  cudaFree(dImg);
+  cudaFree(dXyz);
+  if (e != cudaSuccess) { jn_set_error("jn_pointcloud_from_disparity: %s", cudaGetErrorString(e)); return JN_ERR_CUDA; }
+  *n_points = total;
   return JN_OK;
 }
 

@@ -131,6 +131,37 @@ int port_points_from_dmap(const double* Q, const double* XR, const double* XT, c
   return n;
 }
 
+/* sensor_msgs/PointCloud payload of publishPointCloud (point_cloud.cpp:351-383): per point a
+ * geometry_msgs/Point32 (the robot-frame doubles narrowed to float32) and one "rgb" channel value =
+ * the bits of int32 (red << 16 | green << 8 | blue) with red/green/blue = leftim_res.at<Vec3b>(j,i)[2,1,0].
+ * channels = 3: `img` is that BGR image.  channels = 1: the reference decodes GRAYSCALE frames
+ * (point_cloud.cpp:436) and still indexes them as Vec3b, i.e. it reads bytes 3i, 3i+1, 3i+2 of row j
+ * (running into the following rows); restated literally, bytes beyond the H x stride buffer read as 0. */
+int port_pointcloud_pack(const double* Q, const double* XR, const double* XT, const uint8_t* dmap, int W, int H,
+                         int ox, int oy, const uint8_t* img, int stride, int channels, float* xyz, float* rgb) {
+  int n = 0;
+  const size_t img_bytes = (size_t)stride * H;
+  for (int i = 0; i < W; i++)
+    for (int j = 0; j < H; j++) {
+      int d = dmap[(size_t)j * W + i];
+      if (d < 2) continue;
+      double p[3];
+      reproject(Q, XR, XT, (double)(i + ox), (double)(j + oy), (double)d, p);
+      xyz[3 * (size_t)n] = (float)p[0];
+      xyz[3 * (size_t)n + 1] = (float)p[1];
+      xyz[3 * (size_t)n + 2] = (float)p[2];
+      int32_t c[3];
+      for (int k = 0; k < 3; k++) {
+        size_t a = (size_t)j * stride + 3 * (size_t)i + k;
+        c[k] = (channels == 3 || a < img_bytes) ? img[a] : 0;
+      }
+      int32_t v = (c[2] << 16) | (c[1] << 8) | c[0];
+      memcpy(rgb + n, &v, 4);
+      n++;
+    }
+  return n;
+}
+
 /* publishObstacleScan(vector<Point3d>, seq)  (point_cloud.cpp:149-211) */
 void port_scan_from_points(const double* pts, int n, double* scan, oracle_scan_meta* meta) {
   scan_init(scan, meta);

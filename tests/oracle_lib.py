@@ -252,3 +252,29 @@ def load(kind):
         return Oracle(kind)
     except (FileNotFoundError, OSError):
         return None
+
+
+def port_remap(src, mapx, mapy, roi=None):
+    """oracle/remap_port.c: cv::remap(INTER_LINEAR, constant border 0) + ROI crop on the CPU."""
+    lib = C.CDLL(PORT_SO)
+    src = np.ascontiguousarray(src, np.uint8)
+    mapx = np.ascontiguousarray(mapx, np.float32)
+    mapy = np.ascontiguousarray(mapy, np.float32)
+    H, W = mapx.shape
+    x0, y0, w, h = roi if roi is not None else (0, 0, W, H)
+    dst = np.zeros((h, w), np.uint8)
+    lib.port_remap_u8(_ptr(src), src.shape[1], src.shape[0], src.strides[0], _ptr(mapx), _ptr(mapy), W,
+                      x0, y0, w, h, _ptr(dst), dst.strides[0])
+    return dst
+
+
+def remap_golden_cases():
+    """(name, src, mapx, mapy, dst) of tests/golden/remap_cv2.npz (outputs of cv2.remap)."""
+    z = np.load(os.path.join(ROOT, "tests", "golden", "remap_cv2.npz"))
+    for k in ("calib0", "calib1", "rand"):
+        if k + "_src" in z.files:
+            src = z[k + "_src"]
+        else:
+            sd, h, w = [int(x) for x in z[k + "_src_seed"]]
+            src = np.random.default_rng(sd).integers(0, 256, (h, w), dtype=np.uint8)
+        yield k, src, z[k + "_mapx"], z[k + "_mapy"], z[k + "_dst"]

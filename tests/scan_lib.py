@@ -60,6 +60,19 @@ class ScanPort:
         n = f(_p(Q), _p(XR), _p(XT), _p(dmap), W, H, ox, oy, _p(pts))
         return pts[:n]
 
+    def pointcloud(self, Q, XR, XT, dmap, image, ox=0, oy=0):
+        """(xyz float32 n x 3, rgb float32 n) as publishPointCloud fills sensor_msgs/PointCloud."""
+        H, W = dmap.shape
+        Q = np.ascontiguousarray(Q, np.float64); XR = np.ascontiguousarray(XR, np.float64)
+        XT = np.ascontiguousarray(XT, np.float64)
+        dmap = np.ascontiguousarray(dmap, np.uint8); image = np.ascontiguousarray(image, np.uint8)
+        xyz = np.zeros((W * H, 3), np.float32); rgb = np.zeros(W * H, np.float32)
+        f = self.lib.port_pointcloud_pack
+        f.restype = C.c_int
+        n = f(_p(Q), _p(XR), _p(XT), _p(dmap), W, H, ox, oy, _p(image), image.strides[0], 3 if image.ndim == 3 else 1,
+              _p(xyz), _p(rgb))
+        return xyz[:n], rgb[:n]
+
     def scan_points(self, pts):
         pts = np.ascontiguousarray(pts, np.float64)
         ranges = np.zeros(90, np.float64)

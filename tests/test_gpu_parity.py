@@ -283,6 +283,16 @@ def test_obstacle_scan_matches_port(jn, oracle, synth, qname, W, H, dm, seed):
     r2_ref, m2_ref = sp.scan_points(pts_ref)
     assert np.array_equal(r2 < 1e9 - 1, r2_ref < 1e9 - 1)
     assert np.allclose(r2, r2_ref, rtol=0, atol=1e-9)
+    # sensor_msgs/PointCloud payload: Point32 + packed rgb channel, BGR image and the grayscale quirk
+    rng = np.random.default_rng(3)
+    for img in (rng.integers(0, 256, D1.shape + (3,), dtype=np.uint8), rng.integers(0, 256, D1.shape, dtype=np.uint8)):
+        xyz_ref, rgb_ref = sp.pointcloud(A["Q"], A["XR"], A["XT"], u8_ref, img)
+        xyz, rgb, r3, m3 = sc.pointcloud(D1, img)
+        assert xyz.shape == xyz_ref.shape and np.abs(xyz - xyz_ref).max() <= 1e-3
+        assert np.array_equal(rgb.view(np.int32), rgb_ref.view(np.int32))
+        assert np.array_equal(r3, r2)
+    j, i = np.argwhere(u8_ref.T >= 2)[0][::-1]           # first point in column-major order
+    assert rgb_ref.view(np.int32)[0] == (int(img[j, 3 * i + 2]) << 16 | int(img[j, 3 * i + 1]) << 8 | int(img[j, 3 * i]))
     sc.close()
 
 
@@ -297,3 +307,36 @@ def test_scan_batch_and_empty_map(jn):
     assert (r == 1e9).all() and m.n_finite == 0 and m.n_points == 0
     assert m.angle_min == 400 and m.angle_max == -400 and m.range_min == 1e9 and m.range_max == -500
     sc.close()
+
+
+def test_rectify_matches_opencv_golden_and_port(jn, port):
+    """jn_rectify_batch = cv::remap(INTER_LINEAR) + ROI crop, bit for bit: against the committed cv2.remap
+    outputs, and against the port on a random batch with a ROI and padded strides."""
+    import torch
+    dev = torch.device("cuda", 0)
+    for name, src, mx, my, dst in ol.remap_golden_cases():
+        r = jn.Rectifier(mx, my)
+        dsrc = torch.from_numpy(np.ascontiguousarray(src)).to(dev)
+        dout = torch.zeros(dst.shape, dtype=torch.uint8, device=dev)
+        r.remap_batch(dsrc.data_ptr(), 1, src.shape[1], src.shape[0], src.shape[1], dout.data_ptr(), dst.shape[1])
+        torch.cuda.synchronize()
+        assert np.array_equal(dout.cpu().numpy(), dst), name
+        r.close()
+    rng = np.random.default_rng(11)
+    B, SH, SW, SS, H, W = 3, 70, 90, 96, 64, 80
+    src = rng.integers(0, 256, (B, SH, SS), dtype=np.uint8)
+    mx = rng.uniform(-2, SW + 2, (H, W)).astype(np.float32)
+    my = rng.uniform(-2, SH + 2, (H, W)).astype(np.float32)
+    roi = (5, 3, 61, 50)
+    r = jn.Rectifier(mx, my)
+    dsrc = torch.from_numpy(src).to(dev)
+    dout = torch.full((B, roi[3], 64), 9, dtype=torch.uint8, device=dev)
+    r.remap_batch(dsrc.data_ptr(), B, SW, SH, SS, dout.data_ptr(), 64, roi=roi)
+    torch.cuda.synchronize()
+    out = dout.cpu().numpy()
+    for f in range(B):
+        assert np.array_equal(out[f, :, :roi[2]], ol.port_remap(src[f, :, :SW], mx, my, roi)), f
+    assert (out[:, :, roi[2]:] == 9).all()          # row padding untouched
+    with pytest.raises(jn.JnError):
+        r.remap_batch(dsrc.data_ptr(), B, SW, SH, SS, dout.data_ptr(), 64, roi=(40, 3, 61, 50))
+    r.close()

@@ -113,3 +113,16 @@ def test_adaptive_mean_step_weights(port):
         expect = np.float32((7 * 4.0 * 20.0 + w * (20.0 + delta)) / (7 * 4.0 + w))
         assert abs(D[8, 14] - expect) < 1e-4, (delta, D[8, 14], expect)
         assert D[8, 5] == 20.0 and ref_row[5] == 20.0
+
+
+def test_remap_port_matches_opencv_golden(port):
+    """oracle/remap_port.c against outputs of cv2.remap itself (calibration maps of the shipped YAML and
+    adversarial maps: integer / tie / negative / far-outside coordinates)."""
+    n = 0
+    for name, src, mx, my, dst in ol.remap_golden_cases():
+        got = ol.port_remap(src, mx, my)
+        assert np.array_equal(got, dst), (name, int((got != dst).sum()))
+        roi = (3, 2, mx.shape[1] - 7, mx.shape[0] - 5)
+        assert np.array_equal(ol.port_remap(src, mx, my, roi), dst[2:2 + roi[3], 3:3 + roi[2]]), name
+        n += 1
+    assert n == 3
