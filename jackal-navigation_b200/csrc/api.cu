@@ -32,18 +32,21 @@ void post_mean(const Geo& g, int B, Workspace& ws, const float* in, float* tmp, 
 void post_median(const Geo& g, int B, Workspace& ws, const float* in, float* tmp, float* out, size_t ostride, cudaStream_t s);
 void post_copy(const Geo& g, int B, Workspace& ws, const float* in, float* out, int32_t* status, cudaStream_t s);
 
+constexpr int JN_MAX_PARTS = 4;
+
 struct jn_elas {
   jn_elas_params p;
   int device;
   Geo g;            // geometry the workspace was built for
-  Workspace ws;     // frame slots for a whole batch (first half-batch in split mode)
+  Workspace ws;     // frame slots for a whole batch (part 0 in split mode)
   void* arena;      // one cudaMalloc
-  Workspace ws2;    // frame slots of the second half-batch (split mode)
-  void* arena2;
-  int split;        // 1: run the two halves of a batch on two streams so that latency-bound
-                    // kernels of one half overlap the bandwidth-bound kernels of the other
-  cudaStream_t aux;
-  cudaEvent_t ev_fork, ev_join;
+  Workspace wsx[JN_MAX_PARTS - 1];   // frame slots of parts 1.. (split mode)
+  void* arenax[JN_MAX_PARTS - 1];
+  int parts;        // > 1: run a batch as `parts` sub-batches on as many streams so that the
+                    // latency-bound kernels (Delaunay, support filter: a CTA or two per frame) of
+                    // one part overlap the bandwidth-bound kernels of the others
+  cudaStream_t aux[JN_MAX_PARTS - 1];
+  cudaEvent_t ev_fork, ev_join[JN_MAX_PARTS - 1];
   // single-frame staging for the host-pointer entry point
   uint8_t* dI[2];
   float* dD[2];
@@ -107,17 +110,22 @@ extern "C" jn_elas* jn_elas_create(const jn_elas_params* p, int device) {
   memset(e, 0, sizeof(*e));
   e->p = *p;
   e->device = device;
-  const char* sp = getenv("JN_ELAS_SPLIT");
-  e->split = sp ? atoi(sp) : 1;
+  const char* sp = getenv("JN_ELAS_SPLIT");   // number of sub-batches / streams, 1 = off
+  e->parts = sp ? atoi(sp) : 2;
+  if (e->parts < 1) e->parts = 1;
+  if (e->parts > JN_MAX_PARTS) e->parts = JN_MAX_PARTS;
   return e;
 }
 
 static void free_workspace(jn_elas* e) {
   if (e->arena) cudaFree(e->arena);
-  if (e->arena2) cudaFree(e->arena2);
-  e->arena = e->arena2 = nullptr;
+  e->arena = nullptr;
   memset(&e->ws, 0, sizeof(e->ws));
-  memset(&e->ws2, 0, sizeof(e->ws2));
+  for (int k = 0; k < JN_MAX_PARTS - 1; k++) {
+    if (e->arenax[k]) cudaFree(e->arenax[k]);
+    e->arenax[k] = nullptr;
+    memset(&e->wsx[k], 0, sizeof(e->wsx[k]));
+  }
 }
 
 extern "C" void jn_elas_destroy(jn_elas* e) {
@@ -128,7 +136,9 @@ extern "C" void jn_elas_destroy(jn_elas* e) {
   cudaFree(e->dStatus);
   if (e->ev[0])
     for (int i = 0; i <= JN_PROFILE_STAGES; i++) cudaEventDestroy(e->ev[i]);
-  if (e->aux) { cudaStreamDestroy(e->aux); cudaEventDestroy(e->ev_fork); cudaEventDestroy(e->ev_join); }
+  if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+  for (int k = 0; k < JN_MAX_PARTS - 1; k++)
+    if (e->aux[k]) { cudaStreamDestroy(e->aux[k]); cudaEventDestroy(e->ev_join[k]); }
   delete e;
 }
 
@@ -227,8 +237,11 @@ static int ensure_workspace(jn_elas* e, const int32_t dims[3], int B) {
   int rc = make_geo(e->p, dims, &g);
   if (rc) return rc;
   JN_CUDA_CHECK(cudaSetDevice(e->device));
-  const int B2 = (e->split && B >= 2) ? B / 2 : 0;
-  if (e->arena && e->g.W == g.W && e->g.H == g.H && e->ws.B >= B && e->ws2.B >= B2) {
+  // sub-batches: parts 1.. take B / K frames each, part 0 the rest
+  const int K = (e->parts < B) ? e->parts : B, Bx = (K > 1) ? B / K : 0;
+  bool fits = e->arena && e->g.W == g.W && e->g.H == g.H && e->ws.B >= B;
+  for (int k = 0; k + 1 < K; k++) fits = fits && e->wsx[k].B >= Bx;
+  if (fits) {
     e->g = g;  // stride may differ between calls
     return JN_OK;
   }
@@ -239,17 +252,17 @@ static int ensure_workspace(jn_elas* e, const int32_t dims[3], int B) {
   JN_CUDA_CHECK(cudaMalloc(&e->arena, probe.bytes));
   JN_CUDA_CHECK(cudaMemset(e->arena, 0, probe.bytes));
   layout(g, B, e->ws, (char*)e->arena);
-  if (B2 > 0) {
-    layout(g, B2, probe, nullptr);
-    JN_CUDA_CHECK(cudaMalloc(&e->arena2, probe.bytes));
-    JN_CUDA_CHECK(cudaMemset(e->arena2, 0, probe.bytes));
-    layout(g, B2, e->ws2, (char*)e->arena2);
-    if (!e->aux) {
-      JN_CUDA_CHECK(cudaStreamCreateWithFlags(&e->aux, cudaStreamNonBlocking));
-      JN_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
-      JN_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
+  for (int k = 0; k + 1 < K; k++) {
+    layout(g, Bx, probe, nullptr);
+    JN_CUDA_CHECK(cudaMalloc(&e->arenax[k], probe.bytes));
+    JN_CUDA_CHECK(cudaMemset(e->arenax[k], 0, probe.bytes));
+    layout(g, Bx, e->wsx[k], (char*)e->arenax[k]);
+    if (!e->aux[k]) {
+      JN_CUDA_CHECK(cudaStreamCreateWithFlags(&e->aux[k], cudaStreamNonBlocking));
+      JN_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_join[k], cudaEventDisableTiming));
     }
   }
+  if (K > 1 && !e->ev_fork) JN_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
   e->g = g;
   return JN_OK;
 }
@@ -268,33 +281,39 @@ static int run_stage(int stage, const Geo& g, int B, Workspace& ws, const uint8_
   }
 }
 
-// Elas::process for B frames.  Single stream: everything on `s`.  Split mode: frames
-// [0,B-B/2) on `s` with e->ws and frames [B-B/2,B) on the auxiliary stream with e->ws2, stage
-// launches interleaved; the auxiliary stream forks from and joins back into `s`.
+// Elas::process for B frames.  Single stream: everything on `s`.  Split mode: the batch is cut
+// into K sub-batches; part 0 runs on `s` with e->ws, part k on auxiliary stream k with e->wsx[k-1],
+// stage launches interleaved; the auxiliary streams fork from and join back into `s`.
 static int run_pipeline(jn_elas* e, int B, const uint8_t* I1, const uint8_t* I2, float* D1, float* D2,
                         int32_t* status, cudaStream_t s) {
   const Geo& g = e->g;
   const bool prof = e->profile != 0;
-  const int Bb = (e->split && !prof && B >= 2 && e->ws2.B >= B / 2) ? B / 2 : 0, Ba = B - Bb;
+  int K = (e->parts < B) ? e->parts : B;
+  if (prof) K = 1;
+  const int Bx = (K > 1) ? B / K : 0;
+  for (int k = 0; k + 1 < K; k++)
+    if (e->wsx[k].B < Bx) K = 1;
+  const int B0 = B - (K - 1) * Bx;
   const size_t n = (size_t)g.Wd * g.Hd, ibytes = (size_t)g.bpl * g.H;
-  if (Bb) {
+  if (K > 1) {
     JN_CUDA_CHECK(cudaEventRecord(e->ev_fork, s));
-    JN_CUDA_CHECK(cudaStreamWaitEvent(e->aux, e->ev_fork, 0));
+    for (int k = 0; k + 1 < K; k++) JN_CUDA_CHECK(cudaStreamWaitEvent(e->aux[k], e->ev_fork, 0));
   }
   for (int stage = 0; stage < JN_PROFILE_STAGES; stage++) {
     if (prof) cudaEventRecord(e->ev[stage], s);
-    int rc = run_stage(stage, g, Ba, e->ws, I1, I2, D1, D2, status, s);
+    int rc = run_stage(stage, g, B0, e->ws, I1, I2, D1, D2, status, s);
     if (rc) return rc;
-    if (Bb) {
-      rc = run_stage(stage, g, Bb, e->ws2, I1 + Ba * ibytes, I2 + Ba * ibytes, D1 + Ba * n, D2 ? D2 + Ba * n : nullptr,
-                     status ? status + Ba : nullptr, e->aux);
+    for (int k = 0; k + 1 < K; k++) {
+      const size_t f0 = (size_t)B0 + (size_t)k * Bx;   // first frame of part k+1
+      rc = run_stage(stage, g, Bx, e->wsx[k], I1 + f0 * ibytes, I2 + f0 * ibytes, D1 + f0 * n,
+                     D2 ? D2 + f0 * n : nullptr, status ? status + f0 : nullptr, e->aux[k]);
       if (rc) return rc;
     }
   }
   if (prof) cudaEventRecord(e->ev[JN_PROFILE_STAGES], s);
-  if (Bb) {
-    JN_CUDA_CHECK(cudaEventRecord(e->ev_join, e->aux));
-    JN_CUDA_CHECK(cudaStreamWaitEvent(s, e->ev_join, 0));
+  for (int k = 0; k + 1 < K; k++) {
+    JN_CUDA_CHECK(cudaEventRecord(e->ev_join[k], e->aux[k]));
+    JN_CUDA_CHECK(cudaStreamWaitEvent(s, e->ev_join[k], 0));
   }
   JN_CUDA_CHECK(cudaGetLastError());
   return JN_OK;

@@ -265,21 +265,35 @@ support_match_kernel(Geo g, const uint8_t* __restrict__ desc1, const uint8_t* __
 
 // c0(p) = number of lattice points q in the (2r+1)^2 window (p included) that are
 // valid and within incon_threshold of p, on the ORIGINAL candidate image.
-__global__ void incon_count_kernel(Geo g, const int16_t* __restrict__ dcan, int32_t* __restrict__ cnt) {
+__global__ void __launch_bounds__(256) incon_count_kernel(Geo g, const int16_t* __restrict__ dcan,
+                                                          int32_t* __restrict__ cnt) {
+  // candidate tile + window halo in shared memory (window radius <= 16, checked in make_geo);
+  // lattice points outside the image read as invalid
+  __shared__ int16_t tile[(8 + 32) * (32 + 32)];
   const int Wc = g.Wc, Hc = g.Hc, r = g.p.incon_window_size, thr = g.p.incon_threshold;
   const int frame = blockIdx.z;
-  const int u = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y * blockDim.y + threadIdx.y;
-  if (u >= Wc || v >= Hc) return;
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  const int TWD = 32 + 2 * r, THT = 8 + 2 * r;
+  const int u0 = blockIdx.x * 32 - r, v0 = blockIdx.y * 8 - r;
   const int16_t* dc = dcan + (size_t)frame * Wc * Hc;
-  int d = dc[v * Wc + u];
+  for (int i = tid; i < TWD * THT; i += 256) {
+    const int ty = i / TWD, tx = i - ty * TWD;
+    const int uu = u0 + tx, vv = v0 + ty;
+    tile[i] = (uu >= 0 && uu < Wc && vv >= 0 && vv < Hc) ? dc[vv * Wc + uu] : (int16_t)-1;
+  }
+  __syncthreads();
+  const int u = blockIdx.x * 32 + threadIdx.x, v = blockIdx.y * 8 + threadIdx.y;
+  if (u >= Wc || v >= Hc) return;
+  const int d = tile[(threadIdx.y + r) * TWD + threadIdx.x + r];
   int c = 0;
   if (d >= 0) {
-    int v0 = max(v - r, 0), v1 = min(v + r, Hc - 1), u0 = max(u - r, 0), u1 = min(u + r, Wc - 1);
-    for (int v2 = v0; v2 <= v1; v2++)
-      for (int u2 = u0; u2 <= u1; u2++) {
-        int d2 = dc[v2 * Wc + u2];
+    for (int dv = 0; dv <= 2 * r; dv++) {
+      const int16_t* row = tile + (threadIdx.y + dv) * TWD + threadIdx.x;
+      for (int du = 0; du <= 2 * r; du++) {
+        const int d2 = row[du];
         c += (d2 >= 0 && abs(d - d2) <= thr) ? 1 : 0;
       }
+    }
   }
   cnt[(size_t)frame * Wc * Hc + v * Wc + u] = c;
 }
