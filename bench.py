@@ -356,7 +356,7 @@ def run_ours(a):
     tpath = os.path.join(ROOT, "profiles", "dense_traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            traffic = json.load(open(tpath)).get("dram_bytes_per_frame") * B   # per launch of B frames, like `achieved`
         except Exception:
             traffic = None
     line = {
