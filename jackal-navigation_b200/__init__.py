@@ -17,7 +17,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libjn_elas.so")
+LIB_PATH = os.environ.get("JN_ELAS_LIB") or os.path.join(_HERE, "libjn_elas.so")   # override: kernel tuning sweeps
 
 ROBOTICS, MIDDLEBURY = 0, 1
 JN_OK, JN_FEW_SUPPORT = 0, 1

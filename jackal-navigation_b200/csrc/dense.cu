@@ -78,8 +78,16 @@ __global__ void raster_kernel(Geo g, Workspace ws) {
   }
 }
 
-constexpr int DENSE_THREADS = 128;
-constexpr int DENSE_ROWS = 8;              // image rows per thread (amortises the per-thread setup)
+// Tile shape: columns per CTA x rows per thread.  Swept on the B200 at the end of round 1
+// (64..256 x 4..16): all within 3 %, 256 x 8 best (wider tiles re-read less of the searched rows).
+#ifndef JN_DENSE_THREADS
+#define JN_DENSE_THREADS 256
+#endif
+#ifndef JN_DENSE_ROWS
+#define JN_DENSE_ROWS 8
+#endif
+constexpr int DENSE_THREADS = JN_DENSE_THREADS;
+constexpr int DENSE_ROWS = JN_DENSE_ROWS;         // image rows per thread (amortises the per-thread setup)
 constexpr unsigned KEY_NONE = 0xFFFFFFFFu;
 
 // One candidate: 16-byte SAD (+ prior), folded into a packed key
