@@ -104,21 +104,26 @@ __device__ __forceinline__ void match_group(const Geo& g, const int (&u)[KG], un
     }
   }
   const bool allok = okmask == (1u << KG) - 1u;
-  for (int base = plo; base <= phi; base += 32) {
-    const int p = min(base + lane, phi);
-    const uint4 s0 = rowB_t[p - 2], s1 = rowB_t[p + 2], s2 = rowB_b[p - 2], s3 = rowB_b[p + 2];
-    const int shift = DIR * p;
-    if (allok && base >= ilo && base + 31 <= ihi) {
-      // common case: every candidate live, chunk inside every range -> straight-line code
-#pragma unroll
-      for (int k = 0; k < KG; k++) {
-        unsigned e = sad16(a[k][0], s0, 0u);
-        e = sad16(a[k][1], s1, e);
-        e = sad16(a[k][2], s2, e);
-        e = sad16(a[k][3], s3, e);
-        best2_update(best[k], (int)e * 65536 + shift);
-      }
-    } else {
+  // Chunks of 32 positions from plo.  Chunks [j_lo, j_hi] lie inside every candidate's range and
+  // take the straight-line path; the few before and after them (range borders) are masked per
+  // candidate and lane.
+  const int j_end = (phi - plo) >> 5;
+  int j_lo = 0, j_hi = -1;
+  if (allok && ihi - ilo >= 31) {
+    j_lo = (ilo - plo + 31) >> 5;
+    j_hi = (ihi - 31 - plo) >> 5;          // >= j_lo - 1; empty if the intersection holds no whole chunk
+  }
+#pragma unroll 1
+  for (int part = 0; part < 2; part++) {
+    // border chunks: [0, j_lo) before the middle, (j_hi, j_end] after it (everything if there is no middle)
+    const bool mid = j_hi >= j_lo;
+    const int jb = part ? (mid ? j_hi + 1 : 0) : 0, je = part ? j_end : (mid ? j_lo - 1 : -1);
+#pragma unroll 1
+    for (int j = jb; j <= je; j++) {
+      const int base = plo + 32 * j;
+      const int p = min(base + lane, phi);
+      const uint4 s0 = rowB_t[p - 2], s1 = rowB_t[p + 2], s2 = rowB_b[p - 2], s3 = rowB_b[p + 2];
+      const int shift = DIR * p;
       const bool lane_in = base + lane <= phi;
 #pragma unroll
       for (int k = 0; k < KG; k++) {
@@ -128,6 +133,27 @@ __device__ __forceinline__ void match_group(const Geo& g, const int (&u)[KG], un
         e = sad16(a[k][3], s3, e);
         // p0 > p1 for a candidate that is not ok: never in range
         best2_update(best[k], (lane_in && p >= p0[k] && p <= p1[k]) ? (int)e * 65536 + shift : KEY_EMPTY);
+      }
+    }
+    if (part == 0 && mid) {
+      // middle: every candidate live at every lane -> 4 loads, 64 SADs, 4 keys, 12 min/max per chunk
+      const uint4* qt = rowB_t + (plo + 32 * j_lo + lane);
+      const uint4* qb = rowB_b + (plo + 32 * j_lo + lane);
+      int shift = DIR * (plo + 32 * j_lo + lane);
+#pragma unroll 1
+      for (int j = j_lo; j <= j_hi; j++) {
+        const uint4 s0 = qt[-2], s1 = qt[2], s2 = qb[-2], s3 = qb[2];
+#pragma unroll
+        for (int k = 0; k < KG; k++) {
+          unsigned e = sad16(a[k][0], s0, 0u);
+          e = sad16(a[k][1], s1, e);
+          e = sad16(a[k][2], s2, e);
+          e = sad16(a[k][3], s3, e);
+          best2_update(best[k], (int)e * 65536 + shift);
+        }
+        qt += 32;
+        qb += 32;
+        shift += DIR * 32;
       }
     }
   }
