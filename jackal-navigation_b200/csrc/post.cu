@@ -563,10 +563,16 @@ mean_fused_kernel(Geo g, Workspace ws, const float* __restrict__ in, float* __re
   const int W = g.Wd, H = g.Hd, tid = threadIdx.x;
   const int x0 = blockIdx.x * MT_W, y0 = blockIdx.y * MT_H;
   const float* src = in + (size_t)frame * W * H;
-  for (int i = tid; i < MT_ROWS * MT_IN_W; i += 256) {
-    const int r = i / MT_IN_W, c = i - r * MT_IN_W;
-    const int y = y0 - 4 + r, x = x0 - 4 + c;
-    s_in[r][c] = (x >= 0 && x < W && y >= 0 && y < H) ? src[(size_t)y * W + x] : 0.f;
+  // a warp per tile row, lanes along the row (71 columns = 3 passes): no index division
+  for (int r = tid >> 5; r < MT_ROWS; r += 8) {
+    const int y = y0 - 4 + r;
+    const bool yin = y >= 0 && y < H;
+    const float* row = src + (size_t)(yin ? y : 0) * W;
+#pragma unroll
+    for (int c = tid & 31; c < MT_IN_W; c += 32) {
+      const int x = x0 - 4 + c;
+      s_in[r][c] = (yin && x >= 0 && x < W) ? row[x] : 0.f;
+    }
   }
   __syncthreads();
   // D_tmp: filtered for rows 3..H-4 and centres 4..W-4, otherwise -10 (invalid input) or 0 (H1)

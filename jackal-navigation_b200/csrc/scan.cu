@@ -22,6 +22,7 @@ struct ScanConst {
   double Q[16], XR[9], XT[3];
   double tan_gp;          // tan(4 * 3.1415 / 180)
   int W, H, ox, oy;
+  int q_simple;           // Q has stereoRectify's sparsity: only Q03, Q13, Q23, Q32 and the two unit entries
 };
 
 namespace {
@@ -41,9 +42,19 @@ __device__ __forceinline__ double okey_inv(unsigned long long k) {
 
 __device__ __forceinline__ void reproject(const ScanConst& c, double x, double y, double d, double out[3]) {
   double pos[4];
+  if (c.q_simple) {
+    // Q = [[1,0,0,Q03],[0,1,0,Q13],[0,0,0,Q23],[0,0,Q32,0]] (point_cloud.cpp:543, zero-disparity
+    // flag): the products with the exact 0 and 1 entries change nothing, so these are the general
+    // expressions below bit for bit (the + 0.0 keeps pos[3] = +0 for d = 0 as ((0+0)+Q32*d)+0 gives)
+    pos[0] = x + c.Q[3];
+    pos[1] = y + c.Q[7];
+    pos[2] = c.Q[11];
+    pos[3] = c.Q[14] * d + 0.0;
+  } else {
 #pragma unroll
-  for (int i = 0; i < 4; i++)
-    pos[i] = ((c.Q[4 * i] * x + c.Q[4 * i + 1] * y) + c.Q[4 * i + 2] * d) + c.Q[4 * i + 3] * 1.0;
+    for (int i = 0; i < 4; i++)
+      pos[i] = ((c.Q[4 * i] * x + c.Q[4 * i + 1] * y) + c.Q[4 * i + 2] * d) + c.Q[4 * i + 3] * 1.0;
+  }
   double X = pos[0] / pos[3], Y = pos[1] / pos[3], Z = pos[2] / pos[3];
 #pragma unroll
   for (int i = 0; i < 3; i++) out[i] = ((c.XR[3 * i] * X + c.XR[3 * i + 1] * Y) + c.XR[3 * i + 2] * Z) + c.XT[i];
@@ -99,8 +110,10 @@ __device__ __forceinline__ void lacc_add(LocalAcc& l, BlockAcc& a, double X, dou
   double deg = th * 180. / 3.1415;
   // defined here: a NaN reprojection (d = 0 through a wrapped gate divides by W = 0, H8) is skipped
   if (th != th || X != X || Y != Y) return;
-  double r = sqrt(Y * Y + X * X);
-  unsigned long long kt = okey(th), kr = okey(r);
+  // ranges are tracked as r^2 (same roundings as the reference's sqrt argument); sqrt is monotone,
+  // so min/max of sqrt(r2) = sqrt of min/max r2 and the root is taken once per bin at the end
+  const double r2 = Y * Y + X * X;
+  unsigned long long kt = okey(th), kr = okey(r2);
   l.amin = min(l.amin, kt);
   l.amax = max(l.amax, kt);
   l.rmin = min(l.rmin, kr);
@@ -201,7 +214,7 @@ __global__ void scan_finalize_kernel(const unsigned long long* __restrict__ acc,
   if (tid == 0) s_fin = 0;
   __syncthreads();
   if (tid < JN_SCAN_BINS) {
-    double r = (a[tid] == ~0ull) ? SCAN_INF : okey_inv(a[tid]);
+    double r = (a[tid] == ~0ull) ? SCAN_INF : sqrt(okey_inv(a[tid]));
     ranges[(size_t)frame * JN_SCAN_BINS + tid] = r;
     if (r < SCAN_INF - 1) atomicAdd(&s_fin, 1);
   }
@@ -211,8 +224,8 @@ __global__ void scan_finalize_kernel(const unsigned long long* __restrict__ acc,
     unsigned long long n = a[JN_SCAN_BINS + 4];
     m.angle_min = n ? okey_inv(a[JN_SCAN_BINS + 0]) : 400.;
     m.angle_max = n ? okey_inv(a[JN_SCAN_BINS + 1]) : -400.;
-    m.range_min = n ? okey_inv(a[JN_SCAN_BINS + 2]) : SCAN_INF;
-    m.range_max = n ? okey_inv(a[JN_SCAN_BINS + 3]) : -500.;
+    m.range_min = n ? sqrt(okey_inv(a[JN_SCAN_BINS + 2])) : SCAN_INF;
+    m.range_max = n ? sqrt(okey_inv(a[JN_SCAN_BINS + 3])) : -500.;
     m.n_finite = s_fin;
     m.n_points = (int)n;
     meta[frame] = m;
@@ -325,6 +338,11 @@ extern "C" jn_scan* jn_scan_create(const jn_calib* cal, int width, int height, i
   for (int i = 0; i < 9; i++) s->c.XR[i] = cal->XR[i];
   for (int i = 0; i < 3; i++) s->c.XT[i] = cal->XT[i];
   s->c.tan_gp = tan(4. * 3.1415 / 180.);
+  {
+    const double* q = s->c.Q;
+    s->c.q_simple = q[0] == 1 && q[1] == 0 && q[2] == 0 && q[4] == 0 && q[5] == 1 && q[6] == 0 && q[8] == 0 &&
+                    q[9] == 0 && q[10] == 0 && q[12] == 0 && q[13] == 0 && q[15] == 0;
+  }
   s->c.W = width; s->c.H = height; s->c.ox = ox; s->c.oy = oy;
   size_t n = (size_t)width * height;
   if (cudaMalloc(&s->gate, 2 * n) != cudaSuccess || cudaMalloc(&s->dD, n * sizeof(float)) != cudaSuccess ||

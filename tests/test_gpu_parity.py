@@ -296,6 +296,34 @@ def test_obstacle_scan_matches_port(jn, oracle, synth, qname, W, H, dm, seed):
     sc.close()
 
 
+def test_obstacle_scan_general_q_matrix(jn):
+    """A Q without stereoRectify's sparsity (CALIB_ZERO_DISPARITY off: Q33 != 0, plus a skew term) takes
+    the general 4x4 product; same checks against the port as the sparse one."""
+    sp = scan_lib.ScanPort()
+    fx = scan_lib.fixtures()
+    Q = np.array(fx["Q"]["640x480"], np.float64).reshape(4, 4).copy()
+    Q[3, 3] = 0.37
+    Q[0, 1] = 1e-3
+    cal = jn.Calibration(scan_lib.CALIB_YML)
+    cal.set_q_matrix(Q)
+    A = cal.arrays()
+    W, H = 640, 480
+    rng = np.random.default_rng(5)
+    D = np.floor(rng.uniform(-20, 120, (H, W))).astype(np.float32)
+    sc = jn.ObstacleScan(cal, W, H)
+    gate_ref = sp.gate(A["Q"], A["XR"], A["XT"], W, H)
+    assert np.array_equal(sc.gate_cache(), gate_ref)
+    u8_ref = sp.convert_u8(D)
+    r_ref, m_ref = sp.scan(A["Q"], A["XR"], A["XT"], gate_ref, u8_ref)
+    r, m, _ = sc.from_disparity(D)
+    assert m.n_points == m_ref.n_points and m.n_finite == m_ref.n_finite
+    assert np.array_equal(r < 1e9 - 1, r_ref < 1e9 - 1)
+    assert np.allclose(r, r_ref, rtol=0, atol=1e-9)
+    for k in ("angle_min", "angle_max", "range_min", "range_max"):
+        assert abs(getattr(m, k) - getattr(m_ref, k)) <= 1e-9, k
+    sc.close()
+
+
 def test_scan_batch_and_empty_map(jn):
     import torch
     fx = scan_lib.fixtures()
