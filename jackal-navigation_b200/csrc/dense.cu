@@ -9,9 +9,10 @@
 //                  (same float operations, same truncations) and
 //                  records, per pixel, the HIGHEST triangle index covering it
 //                  (atomicMax = "the later triangle wins");
-//   dense_kernel   one thread per pixel, a warp = a run of 32 pixels of one row:
-//                  plane prior of the recorded triangle, candidate set = grid
-//                  bits outside the plane range, then the plane range with the
+//   dense_kernel   one thread per column walking 8 rows, a warp = a run of 32 pixels
+//                  of one row: plane prior of the recorded triangle, candidate set =
+//                  the cell's sorted candidate list (bit set for overflowing cells)
+//                  outside the plane range, then the plane range with the
 //                  integer prior P, 16-byte SAD per candidate on the integer
 //                  pipe (4 x VABSDIFF4.U8.ACC), strict '<' in the reference's
 //                  evaluation order (H7).  Left descriptors are read once, fully
@@ -21,7 +22,11 @@
 //
 // Roofline: HBM (72 N bytes per frame: 2 passes x (2 descriptor images 32 N +
 // 4 N written)), second roofline the integer pipe (16 byte-absdiffs = 4
-// instructions per candidate).  Compiled with -fmad=false: d_plane and the edge
+// instructions per candidate).  Measured: DRAM 35 % busy, issue slots 81 % with
+// all 64 warps per SM resident at 32 registers: bound by instruction issue and
+// the dependent loads triangle id -> plane -> candidates of every row (variants
+// with more registers per thread, prefetches or streaming loads were all slower,
+// see DESIGN.md section 3).  Compiled with -fmad=false: d_plane and the edge
 // equations must round exactly as the reference's SSE code does.
 #include "common.cuh"
 

@@ -7,11 +7,14 @@
 // support_match_kernel: one CTA per candidate row.  The four descriptor rows a
 // candidate row touches (v-2 and v+2 of both images, W*16 bytes each) are
 // fetched once with 1-D bulk async copies (TMA unit) into shared memory; a warp
-// owns one candidate, its lanes stride the disparities, every disparity costs
-// four conflict-free 128-bit shared loads and 16 VABSDIFF4.U8.ACC.  The
-// (best, second best) pair is order independent (second best = second smallest
-// energy of the multiset, best = lowest disparity among the minima, H7), so it
-// is reduced with warp shuffles.
+// owns four neighbouring candidates, its lanes stride the POSITIONS of the
+// searched rows: a lane loads the four searched descriptors of its position once
+// (conflict-free 128-bit shared loads) and scores them against all four
+// candidates, 16 VABSDIFF4.U8.ACC each.  The (best, second best) pair is order
+// independent (second best = second smallest energy of the multiset, best =
+// lowest disparity among the minima, H7), so it is kept as two packed keys per
+// lane and reduced over the warp with two REDUX.MIN.  The kernel is bound by the
+// integer ALU pipe (85 % busy, 61 % of that in the SADs themselves).
 //
 // The in-place, scan-ordered inconsistency filter (H3) is computed exactly by
 // a monotone frontier propagation: a point's final validity only depends on
