@@ -3,12 +3,16 @@
  *
  * Plain-C restatement of the per-pixel part of the reference's
  * src/obstacle_avoidance/point_cloud.cpp (it needs ROS + OpenCV C++ and cannot
- * be compiled here).  PARITY UNPINNED: the reference holds
- * no test, fixture or golden output for this code, and the OpenCV it links
- * (2.4-era, version not pinned in package.xml) is not in /root/reference; the
- * arithmetic below follows the call sites literally, with cv::Mat products
- * evaluated as OpenCV's small-matrix gemm does: ((a0*b0 + a1*b1) + a2*b2) [+ a3*b3],
- * then + C.
+ * be compiled here).  PARITY UNPINNED against the
+ * reference itself: it holds no test, fixture or golden output for this code, and
+ * the OpenCV it links (2.4-era, version not pinned in package.xml) is not in
+ * /root/reference.  The arithmetic below follows the call sites literally, with
+ * cv::Mat products evaluated as OpenCV's small-matrix gemm does:
+ * ((a0*b0 + a1*b1) + a2*b2) [+ a3*b3], then + C.  PINNED against OpenCV 4.13 for
+ * the parts that live in OpenCV: tests/golden/scan_cv2.npz holds cv2.gemm results
+ * for Q*V and XR*p+XT (sparse and dense Q) and the saturate_cast<uchar> of
+ * convertTo(CV_8U); tests/test_oracle_pin.py checks reproject() and
+ * port_convert_u8 against them bit for bit.  atan2/sqrt/floor are libm.
  *
  * One behaviour is DEFINED here because the reference leaves it undefined (H8):
  * a bin index outside [0,89] (|theta| > 45 deg) is skipped; the reference writes

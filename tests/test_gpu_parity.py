@@ -4,6 +4,7 @@ Integer stages (descriptors, support points, triangles, grid, SAD argmin dispari
 segments) must be bit-exact; with identical arithmetic order and no FMA the float stages
 (planes, gap interpolation, adaptive mean, median) are bit-exact too, so every comparison
 below is exact unless a tolerance is written next to it."""
+import os
 import numpy as np
 import pytest
 import golden_util as gu
@@ -321,6 +322,30 @@ def test_obstacle_scan_general_q_matrix(jn):
     assert np.allclose(r, r_ref, rtol=0, atol=1e-9)
     for k in ("angle_min", "angle_max", "range_min", "range_max"):
         assert abs(getattr(m, k) - getattr(m_ref, k)) <= 1e-9, k
+    sc.close()
+
+
+def test_reprojection_matches_opencv_golden(jn):
+    """Device reprojection (sparse-Q path and general path) and u8 conversion against values computed by
+    OpenCV itself (cv2.gemm, saturate_cast; tests/golden/scan_cv2.npz): bit for bit."""
+    z = np.load(os.path.join(ol.ROOT, "tests", "golden", "scan_cv2.npz"))
+    H, W = z["dmap"].shape
+    cal = jn.Calibration(scan_lib.CALIB_YML)
+    for qk, pk, dmap in (("Q", "pts", z["dmap"]), ("Qg", "ptsg", None)):
+        if dmap is None:
+            dmap = np.zeros_like(z["dmap"]); dmap[::3, ::3] = z["dmap"][::3, ::3]
+        cal.set_q_matrix(z[qk])
+        for i in range(9): cal.c.XR[i] = float(z["XR"].reshape(-1)[i])
+        for i in range(3): cal.c.XT[i] = float(z["XT"].reshape(-1)[i])
+        sc = jn.ObstacleScan(cal, W, H, int(z["ox"]), int(z["oy"]))
+        pts, _, _ = sc.points(dmap.astype(np.float32))
+        assert np.array_equal(pts, z[pk]), qk
+        sc.close()
+    Dl = z["D"]
+    cal.set_q_matrix(z["Q"])
+    sc = jn.ObstacleScan(cal, Dl.shape[1], 1)
+    _, _, u8 = sc.from_disparity(Dl, want_u8=True)
+    assert np.array_equal(u8, z["u8"])
     sc.close()
 
 

@@ -126,3 +126,16 @@ def test_remap_port_matches_opencv_golden(port):
         assert np.array_equal(ol.port_remap(src, mx, my, roi), dst[2:2 + roi[3], 3:3 + roi[2]]), name
         n += 1
     assert n == 3
+
+
+def test_scan_port_matches_opencv_arithmetic():
+    """The parts of point_cloud.cpp's per-pixel arithmetic that live in OpenCV (cv::Mat products = cv::gemm,
+    convertTo(CV_8U) = saturate_cast), evaluated by cv2 4.13 itself (tests/golden/make_scan_golden.py)."""
+    import scan_lib
+    z = np.load(gu.GOLD + "/scan_cv2.npz")
+    sp = scan_lib.ScanPort()
+    ox, oy = int(z["ox"]), int(z["oy"])
+    assert np.array_equal(sp.points(z["Q"], z["XR"], z["XT"], z["dmap"], ox, oy), z["pts"])
+    sub = np.zeros_like(z["dmap"]); sub[::3, ::3] = z["dmap"][::3, ::3]
+    assert np.array_equal(sp.points(z["Qg"], z["XR"], z["XT"], sub, ox, oy), z["ptsg"])      # dense Q
+    assert np.array_equal(sp.convert_u8(z["D"]), z["u8"])
