@@ -25,7 +25,7 @@ void jn_set_error(const char* fmt, ...) {
 }
 
 // step-wise post-processing (post.cu)
-void post_lr(const Geo& g, int B, Workspace& ws, cudaStream_t s);
+void post_lr(const Geo& g, int B, Workspace& ws, cudaStream_t s, bool need_right = true);
 void post_segments(const Geo& g, int B, Workspace& ws, int side, cudaStream_t s);
 void post_gap(const Geo& g, int B, Workspace& ws, int side, cudaStream_t s);
 void post_mean(const Geo& g, int B, Workspace& ws, const float* in, float* tmp, float* out, size_t ostride, cudaStream_t s);

@@ -54,6 +54,9 @@ __global__ void lr_kernel(Geo g, Workspace ws) {
 // memory-level parallelism per thread.  Same arithmetic as lr_kernel.
 constexpr int Q_THREADS = 128;   // threads per CTA of the quad kernels; a CTA covers 512 pixels of a row
 
+// RIGHT = false: the right map is neither post-processed nor returned (ROBOTICS preset with D2 = NULL),
+// so only the left result is computed and written.
+template <bool RIGHT>
 __global__ void __launch_bounds__(Q_THREADS) lr4_kernel(Geo g, Workspace ws) {
   const int frame = blockIdx.z;
   if (ws.info[frame].status != JN_OK) return;
@@ -75,10 +78,11 @@ __global__ void __launch_bounds__(Q_THREADS) lr4_kernel(Geo g, Workspace ws) {
     o1[j] = -10.f;
     o2[j] = -10.f;
     if (d1[j] >= 0 && uw1 >= 0 && uw1 < (float)W) o1[j] = (fabsf(D2[(int)uw1] - d1[j]) > thr) ? -10.f : d1[j];
-    if (d2[j] >= 0 && uw2 >= 0 && uw2 < (float)W) o2[j] = (fabsf(D1[(int)uw2] - d2[j]) > thr) ? -10.f : d2[j];
+    if (RIGHT && d2[j] >= 0 && uw2 >= 0 && uw2 < (float)W)
+      o2[j] = (fabsf(D1[(int)uw2] - d2[j]) > thr) ? -10.f : d2[j];
   }
   reinterpret_cast<float4*>(ws.Dlr[0] + rb)[q] = make_float4(o1[0], o1[1], o1[2], o1[3]);
-  reinterpret_cast<float4*>(ws.Dlr[1] + rb)[q] = make_float4(o2[0], o2[1], o2[2], o2[3]);
+  if (RIGHT) reinterpret_cast<float4*>(ws.Dlr[1] + rb)[q] = make_float4(o2[0], o2[1], o2[2], o2[3]);
 }
 
 // ------------------------------------------------------------ small segments
@@ -740,8 +744,10 @@ __global__ void copy_out_kernel(Geo g, Workspace ws, const float* __restrict__ i
 }  // namespace
 
 // Step-wise entry points (the debug dump calls them one at a time).
-void post_lr(const Geo& g, int B, Workspace& ws, cudaStream_t s) {
-  if (g.Wd % 4 == 0) lr4_kernel<<<dim3((g.Wd / 4 + Q_THREADS - 1) / Q_THREADS, g.Hd, B), Q_THREADS, 0, s>>>(g, ws);
+void post_lr(const Geo& g, int B, Workspace& ws, cudaStream_t s, bool need_right) {
+  const dim3 qg((g.Wd / 4 + Q_THREADS - 1) / Q_THREADS, g.Hd, B);
+  if (g.Wd % 4 == 0 && need_right) lr4_kernel<true><<<qg, Q_THREADS, 0, s>>>(g, ws);
+  else if (g.Wd % 4 == 0) lr4_kernel<false><<<qg, Q_THREADS, 0, s>>>(g, ws);
   else lr_kernel<<<dim3((g.Wd + 255) / 256, g.Hd, B), 256, 0, s>>>(g, ws);
   g_jn_launches += 1;
 }
@@ -812,8 +818,8 @@ void post_copy(const Geo& g, int B, Workspace& ws, const float* in, float* out, 
 // The whole chain for a batch.  D1out/D2out: user buffers (B * W*H floats); D2out may be NULL.
 void launch_post(const Geo& g, int B, Workspace& ws, float* D1out, float* D2out, int32_t* status, cudaStream_t s) {
   const size_t n = (size_t)g.Wd * g.Hd;
-  post_lr(g, B, ws, s);
   const int sides = g.p.postprocess_only_left ? 1 : 2;
+  post_lr(g, B, ws, s, sides == 2 || D2out != nullptr);
   for (int side = 0; side < sides; side++) {
     post_segments(g, B, ws, side, s);
     post_gap(g, B, ws, side, s);
