@@ -587,8 +587,10 @@ mean_fused_kernel(Geo g, Workspace ws, const float* __restrict__ in, float* __re
     float o = (d < 0) ? -10.f : 0.f;
     if (W >= 8 && y >= 3 && y <= H - 4 && x >= 4 && x <= W - 4) {
       float w8[8];
+      // the reference first sets every negative sample to -10 (elas.cpp:1304-1309); after the L/R check
+      // (always run before, elas.cpp:108-118) -10 is the only negative value there is
 #pragma unroll
-      for (int k = 0; k < 8; k++) { const float t = s_in[r][c + k]; w8[k] = (t < 0) ? -10.f : t; }
+      for (int k = 0; k < 8; k++) w8[k] = s_in[r][c + k];
       float m;
       if (mean8<false>(w8, w8[4], (x - 4) & 3, m)) o = m;
     }
@@ -649,7 +651,7 @@ __global__ void mean4_h_kernel(Geo g, Workspace ws, const float* __restrict__ in
   if (W >= 4 && v >= 3 && v <= H - 4 && c >= 2 && c <= W - 2) {
     float x[4];
 #pragma unroll
-    for (int k = 0; k < 4; k++) { float t = row[c - 2 + k]; x[k] = (t < 0) ? -10.f : t; }
+    for (int k = 0; k < 4; k++) x[k] = row[c - 2 + k];   // negatives are exactly -10 here, see mean_fused_kernel
     float m;
     if (mean4(x, x[2], (c - 2) & 3, m)) o = m;
   }
