@@ -518,6 +518,11 @@ __device__ __forceinline__ bool mean8(const float x[8], float centre, int rot, f
   float w[8], f[8];
 #pragma unroll
   for (int k = 0; k < 8; k++) {
+    if (k == 4) {   // the centre sample itself (both callers pass centre = x[4]): difference 0, weight 4
+      w[k] = 4.0f;
+      f[k] = x[k] * 4.0f;
+      continue;
+    }
     float t = 4.0f - buggy_abs(x[k] - centre);
     w[k] = fmaxf(0.0f, t);
     f[k] = x[k] * w[k];
@@ -620,6 +625,11 @@ __device__ __forceinline__ bool mean4(const float x[4], float centre, int rot, f
   float w[4], f[4];
 #pragma unroll
   for (int k = 0; k < 4; k++) {
+    if (k == 2) {   // the centre sample itself (both callers pass centre = x[2])
+      w[k] = 4.0f;
+      f[k] = x[k] * 4.0f;
+      continue;
+    }
     float t = 4.0f - buggy_abs(x[k] - centre);
     w[k] = fmaxf(0.0f, t);
     f[k] = x[k] * w[k];
