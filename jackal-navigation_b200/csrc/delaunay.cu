@@ -640,12 +640,9 @@ int launch_delaunay(const Geo& g_in, int B, Workspace& ws, cudaStream_t s) {
   Geo g = g_in;
   g.dl_sort_max = g_sort_max;
   g.dl_smem_max = g_smem_max;
-  static bool attr_set = false;
-  if (!attr_set) {
-    JN_CUDA_CHECK(cudaFuncSetAttribute(delaunay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)DELAUNAY_SMEM));
-    attr_set = true;
-  }
+  // per device (context), not per process: set on every launch, it is a host-side table write
+  JN_CUDA_CHECK(cudaFuncSetAttribute(delaunay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)DELAUNAY_SMEM));
   // the occupancy grids (only used above SORT_MAX points) start "empty" = 0x7f7f7f7f
   if (g.cap_s > g.dl_sort_max)
     JN_CUDA_CHECK(cudaMemsetAsync(ws.occ, 0x7f, (size_t)B * 2 * g.W * g.Hc * sizeof(int32_t), s));

@@ -523,12 +523,9 @@ int launch_support(const Geo& g, int B, Workspace& ws, cudaStream_t s) {
     jn_set_error("image width %d too large for the shared-memory support matcher", g.W);
     return JN_ERR_UNSUPPORTED;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    JN_CUDA_CHECK(cudaFuncSetAttribute(support_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       226 * 1024));
-    attr_set = true;
-  }
+  // per device (context), not per process: set on every launch, it is a host-side table write
+  JN_CUDA_CHECK(cudaFuncSetAttribute(support_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     226 * 1024));
   support_match_kernel<<<dim3(g.Hc, B), MATCH_THREADS, smem, s>>>(g, ws.desc[0], ws.desc[1], ws.dcan);
   g_jn_launches += 1;
   return launch_support_filter(g, B, ws, s);
@@ -540,12 +537,9 @@ int launch_support_filter(const Geo& g, int B, Workspace& ws, cudaStream_t s) {
   incon_count_kernel<<<cg, cb, 0, s>>>(g, ws.dcan, ws.cnt);
   const size_t wk_bytes = (size_t)g.Wc * g.Hc * sizeof(int16_t);
   const int use_smem = wk_bytes <= 212 * 1024;
-  static bool attr2_set = false;
-  if (!attr2_set) {
-    JN_CUDA_CHECK(cudaFuncSetAttribute(support_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       212 * 1024));
-    attr2_set = true;
-  }
+  // per device (context), not per process: set on every launch, it is a host-side table write
+  JN_CUDA_CHECK(cudaFuncSetAttribute(support_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     212 * 1024));
   support_filter_kernel<<<B, FILT_THREADS, use_smem ? wk_bytes : 0, s>>>(
       g, ws.dcan, ws.cnt, ws.frontier, ws.dcan_incon, ws.dcan_final, ws.sup, ws.px[0], ws.px[1], ws.py, ws.info,
       use_smem);
