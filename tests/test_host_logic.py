@@ -79,6 +79,27 @@ def test_no_cpu_fallback(jn):
         jn.Elas(jn.parameters())
 
 
+def test_rectifier_and_scan_have_no_cpu_fallback(jn):
+    """The neighbours of the path (rectification, scan) also refuse to run without a device."""
+    import torch
+    import numpy as np
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    m = np.zeros((4, 4), np.float32)
+    with pytest.raises(jn.JnError):
+        jn.Rectifier(m, m)
+    cal = jn.Calibration(os.path.join(ROOT, "tests", "golden", "calib_c920.yml"))
+    cal.set_q(320.0, 240.0, 600.0, -0.1)
+    with pytest.raises(jn.JnError):
+        jn.ObstacleScan(cal, 64, 48)
+
+
+def test_rectifier_rejects_bad_maps(jn):
+    import numpy as np
+    with pytest.raises(ValueError):
+        jn.Rectifier(np.zeros((4, 4), np.float32), np.zeros((4, 5), np.float32))
+
+
 def test_product_does_not_reference_the_oracle():
     pkg = os.path.join(ROOT, "jackal-navigation_b200")
     for dp, _, fs in os.walk(pkg):
