@@ -34,6 +34,20 @@ namespace {
 
 __device__ __forceinline__ int f2u_lo32(float x) { return (int)(unsigned)(unsigned long long)__float2ll_rz(x); }
 
+// One column span [vlo, vhi) of triangle i.  Scan-converted triangles of a planar triangulation only
+// ever overlap in the first or last row of a span (neighbours evaluate the same edge function, so
+// spans abut exactly; what overlaps there is comes from edges meeting at a vertex and float
+// rounding): "the later triangle wins" (atomicMax) is needed for those two rows only, the rows in
+// between belong to this triangle alone and take a plain store.  Checked on the CPU restatement
+// (tests/test_oracle_pin.py::test_raster_overlaps_stay_on_span_borders): 0 of 61 M covered pixels
+// over 3 000 random and 37 pipeline triangulations had a second cover strictly inside a span.
+__device__ __forceinline__ void write_span(int* __restrict__ map, int W, int u, int vlo, int vhi, int i) {
+  if (vhi <= vlo) return;
+  atomicMax(&map[vlo * W + u], i);
+  if (vhi - 1 > vlo) atomicMax(&map[(vhi - 1) * W + u], i);
+  for (int v = vlo + 1; v < vhi - 1; v++) map[v * W + u] = i;
+}
+
 __global__ void raster_kernel(Geo g, Workspace ws) {
   const int side = blockIdx.y, frame = blockIdx.z;
   const FrameInfo* info = ws.info + frame;
@@ -72,13 +86,13 @@ __global__ void raster_kernel(Geo g, Workspace ws) {
       for (int u = max((int)Au, 0) + lane; u < min((int)Bu, W); u += 32) {
         int v1 = f2u_lo32(ACa * (float)u + ACb), v2 = f2u_lo32(ABa * (float)u + ABb);
         int vlo = max(min(v1, v2), 0), vhi = min(max(v1, v2), H);
-        for (int v = vlo; v < vhi; v++) atomicMax(&map[v * W + u], i);
+        write_span(map, W, u, vlo, vhi, i);
       }
     if ((int)Bu != (int)Cu)
       for (int u = max((int)Bu, 0) + lane; u < min((int)Cu, W); u += 32) {
         int v1 = f2u_lo32(ACa * (float)u + ACb), v2 = f2u_lo32(BCa * (float)u + BCb);
         int vlo = max(min(v1, v2), 0), vhi = min(max(v1, v2), H);
-        for (int v = vlo; v < vhi; v++) atomicMax(&map[v * W + u], i);
+        write_span(map, W, u, vlo, vhi, i);
       }
   }
 }

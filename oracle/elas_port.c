@@ -414,6 +414,59 @@ void port_dense(const jn_elas_params* p, int w, int h, const uint8_t* desc1, con
   dense_port(p, w, h, desc1, desc2, support, tri, planes, n_tri, grid, right_image, D, &c);
 }
 
+/* Study helper (tests / design notes only): how do the scan-converted triangles of computeDisparity
+ * (elas.cpp:843-903) overlap?  Counts pixels covered by more than one triangle, and among those the
+ * ones where some covering triangle has the pixel strictly inside its column span (not in the span's
+ * first or last row after clamping to the image).  out = {pixels covered, pixels covered more than
+ * once, of those with an interior covering, maximum cover count}. */
+void port_raster_overlap_study(int w, int h, const int32_t* s, const int32_t* tri, int n_tri, int right_image,
+                               int64_t out[4]) {
+  uint8_t* cnt = (uint8_t*)calloc((size_t)w * h, 1);
+  uint8_t* inter = (uint8_t*)calloc((size_t)w * h, 1);
+  for (int i = 0; i < n_tri; i++) {
+    float tu[3], tv[3];
+    for (int k = 0; k < 3; k++) {
+      int c = tri[3 * i + k];
+      tu[k] = right_image ? (float)(s[3 * c] - s[3 * c + 2]) : (float)s[3 * c];
+      tv[k] = (float)s[3 * c + 1];
+    }
+    for (int j = 0; j < 3; j++)
+      for (int k = 0; k < j; k++)
+        if (tu[k] > tu[j]) {
+          float t = tu[j]; tu[j] = tu[k]; tu[k] = t;
+          t = tv[j]; tv[j] = tv[k]; tv[k] = t;
+        }
+    float Au = tu[0], Av = tv[0], Bu = tu[1], Bv = tv[1], Cu = tu[2], Cv = tv[2];
+    float ABa = 0, ACa = 0, BCa = 0;
+    if ((int)Au != (int)Bu) ABa = (Av - Bv) / (Au - Bu);
+    if ((int)Au != (int)Cu) ACa = (Av - Cv) / (Au - Cu);
+    if ((int)Bu != (int)Cu) BCa = (Bv - Cv) / (Bu - Cu);
+    float ABb = Av - ABa * Au, ACb = Av - ACa * Au, BCb = Bv - BCa * Bu;
+    for (int half = 0; half < 2; half++) {
+      if (half == 0 ? (int)Au == (int)Bu : (int)Bu == (int)Cu) continue;
+      int u0 = IMAX((int)(half ? Bu : Au), 0), u1 = IMIN((int)(half ? Cu : Bu), w);
+      for (int u = u0; u < u1; u++) {
+        int v1 = f2u_lo32(ACa * (float)u + ACb);
+        int v2 = f2u_lo32(half ? BCa * (float)u + BCb : ABa * (float)u + ABb);
+        int vlo = IMAX(IMIN(v1, v2), 0), vhi = IMIN(IMAX(v1, v2), h);
+        for (int v = vlo; v < vhi; v++) {
+          size_t a = (size_t)v * w + u;
+          if (cnt[a] < 255) cnt[a]++;
+          if (v > vlo && v < vhi - 1) inter[a] = 1;
+        }
+      }
+    }
+  }
+  out[0] = out[1] = out[2] = out[3] = 0;
+  for (size_t a = 0; a < (size_t)w * h; a++) {
+    if (cnt[a]) out[0]++;
+    if (cnt[a] > 1) { out[1]++; if (inter[a]) out[2]++; }
+    if (cnt[a] > out[3]) out[3] = cnt[a];
+  }
+  free(cnt);
+  free(inter);
+}
+
 /* prior table as used by the dense stage, exported for the host-logic tests */
 void port_prior(const jn_elas_params* p, int32_t* P_out, int32_t* plane_radius_out) {
   int r;

@@ -139,3 +139,54 @@ def test_scan_port_matches_opencv_arithmetic():
     sub = np.zeros_like(z["dmap"]); sub[::3, ::3] = z["dmap"][::3, ::3]
     assert np.array_equal(sp.points(z["Qg"], z["XR"], z["XT"], sub, ox, oy), z["ptsg"])      # dense Q
     assert np.array_equal(sp.convert_u8(z["D"]), z["u8"])
+
+
+def test_raster_overlaps_stay_on_span_borders(port, synth):
+    """Design invariant behind raster_kernel's plain stores: where two scan-converted triangles of
+    computeDisparity (elas.cpp:843-903) cover the same pixel, the pixel is in the first or last row of
+    the column span of BOTH -- never strictly inside a span.  Pipeline triangulations (lattice support
+    points, left and right image) and adversarial random point sets."""
+    import ctypes as C
+    f = port.lib.port_raster_overlap_study
+    P = C.c_void_p
+
+    def study(W, H, sup3, tri, right):
+        out = (C.c_int64 * 4)()
+        f(W, H, np.ascontiguousarray(sup3, np.int32).ctypes.data_as(P),
+          np.ascontiguousarray(tri, np.int32).ctypes.data_as(P), len(tri), right, out)
+        return list(out)
+
+    multi = 0
+    for W, H, dm, seed, preset in ((320, 240, 64, 1, ol.robotics), (640, 480, 255, 21, ol.robotics),
+                                   (320, 240, 64, 4, ol.middlebury)):
+        I1, I2, _ = synth.synth_pair(W, H, dm, seed)
+        st = port.stages(preset(dm), I1, I2, want_desc=False, want_grid=False)
+        for right in (0, 1):
+            o = study(W, H, st["support"], st["tri2" if right else "tri1"], right)
+            assert o[2] == 0, (W, H, seed, right, o)
+            multi += o[1]
+    rng = np.random.default_rng(123)
+    for it in range(300):
+        W, H, n = int(rng.integers(40, 400)), int(rng.integers(30, 300)), int(rng.integers(3, 300))
+        if it % 3 == 0:
+            u, v = rng.integers(1, max(2, W // 5), n) * 5, rng.integers(1, max(2, H // 5), n) * 5
+        elif it % 3 == 1:
+            u, v = rng.integers(0, W, n), rng.integers(0, H, n)
+        else:
+            u, v = rng.integers(0, 12, n) * 3, rng.integers(0, 12, n) * 3
+        sup = np.unique(np.stack([u, v], 1), axis=0)
+        if len(sup) < 3:
+            continue
+        sup3 = np.concatenate([sup, rng.integers(0, 40, (len(sup), 1))], 1).astype(np.int32)
+        for right in (0, 1):
+            pts = sup3[:, :2].copy()
+            s_in = sup3.copy()
+            if right:
+                pts[:, 0] = sup3[:, 0] - sup3[:, 2] + 64
+                s_in[:, 0] += 64
+            tri = port.triangulate(np.ascontiguousarray(pts, np.int32))
+            if len(tri):
+                o = study(W + 128, H, s_in, tri, right)
+                assert o[2] == 0, (it, right, o)
+                multi += o[1]
+    assert multi > 0          # overlaps do occur (on span borders): the atomics there are needed
