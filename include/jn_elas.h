@@ -72,7 +72,7 @@ enum {
   JN_FEW_SUPPORT   = 1,
   JN_ERR_ARG       = -1,
   JN_ERR_CUDA      = -2,
-  JN_ERR_UNSUPPORTED = -3,  /* parameter combination not built yet (subsampling=1) */
+  JN_ERR_UNSUPPORTED = -3,  /* outside what the kernels cover (plane radius > 7, image >= 8192 px, ...) */
   JN_ERR_IO        = -4
 };
 
@@ -80,21 +80,23 @@ typedef struct jn_elas jn_elas;
 
 void jn_elas_params_default(jn_elas_params* p, int setting);
 
-/* device: CUDA ordinal.  max_batch: frames processed per launch wave
- * (workspace is sized for it lazily at the first process call). */
+/* device: CUDA ordinal.  The workspace is sized lazily at the first process call (and grown when a
+ * larger batch arrives).  NULL on error (no usable device: there is no CPU path). */
 jn_elas* jn_elas_create(const jn_elas_params* p, int device);
 void     jn_elas_destroy(jn_elas* e);
 const char* jn_last_error(void);
 
 /* Host pointers, synchronous.  dims = {width, height, bytes_per_line}.
- * D1, D2: caller-allocated width*height floats.  Returns JN_OK,
- * JN_FEW_SUPPORT (outputs untouched) or an error. */
+ * D1, D2: caller-allocated width*height floats, or (width/2)*(height/2) with
+ * params.subsampling (elas.h:159-161).  Returns JN_OK, JN_FEW_SUPPORT (outputs
+ * untouched) or an error. */
 int jn_elas_process(jn_elas* e, const uint8_t* I1, const uint8_t* I2,
                     float* D1, float* D2, const int32_t dims[3]);
 
 /* Batched, device-resident.  I1/I2: n frames, frame-major, device pointers,
  * each frame height rows of bytes_per_line bytes.  D1/D2: device pointers,
- * n*width*height floats (D2 may be NULL: right map not returned).
+ * n maps of width*height floats ((width/2)*(height/2) with subsampling), frame-major
+ * (D2 may be NULL: right map not returned).
  * status: device pointer to n int32 (JN_OK / JN_FEW_SUPPORT per frame), may be
  * NULL.  Work is enqueued on `stream` (a cudaStream_t passed as void*); the
  * call does not synchronise.  A frame with <3 support points leaves its
