@@ -106,6 +106,27 @@ def test_full_size_1920x1200_matches_oracle(jn, oracle, synth):
         e.close()
 
 
+@pytest.mark.parametrize("W,H,dm,seed,kw", [
+    (640, 480, 64, 1, {}),
+    (333, 251, 100, 7, {"filter_median": 1, "postprocess_only_left": 0}),
+    (480, 360, 128, 4, {"subsampling": 1}),
+    (1920, 1200, 255, 1000, {}),                       # > 9 000 support points: the large Delaunay path
+    (1920, 1200, 255, 1001, {"filter_median": 1, "postprocess_only_left": 0}),
+])
+def test_textured_scene_matches_oracle(jn, oracle, synth, W, H, dm, seed, kw):
+    """Second scene family: 1/f texture, sub-pixel disparities slanted in u and v, occluding boxes, a
+    textureless patch.  Every stage bit-exact, as on the random-dot scenes."""
+    I1, I2, gt = synth.textured_pair(W, H, dm, seed)
+    big = W * H > 10 ** 6
+    a = oracle.stages(ol.robotics(dm, **kw), I1, I2, want_desc=not big, want_grid=not big)
+    e = jn.Elas(jn.parameters(jn.ROBOTICS, disp_max=dm, **kw))
+    b = e.stages(I1, I2, want_desc=not big, want_grid=not big)
+    assert_stages_equal(a, b, [k for k in STAGES if not (big and k.startswith(("desc", "grid")))])
+    if big:
+        assert b["n_support"] > 8192
+    e.close()
+
+
 def test_delaunay_large_point_set_paths(jn, oracle, synth):
     """The Delaunay kernel has shared-memory fast paths (bitonic sort, u16 tables) and
     global-memory paths for large point sets; force the latter and compare again."""

@@ -48,6 +48,26 @@ def test_port_matches_compiled_reference_every_stage(ref, port, synth, W, H, dm,
         assert np.array_equal(a[k], b[k]), "%s: %d mismatches" % (k, int((a[k] != b[k]).sum()))
 
 
+@pytest.mark.parametrize("W,H,dm,seed,kw", [
+    (640, 480, 64, 1, {}),
+    (333, 251, 100, 7, {"filter_median": 1, "postprocess_only_left": 0}),
+    (480, 360, 128, 4, {"subsampling": 1}),
+])
+def test_port_matches_reference_on_textured_scene(ref, port, synth, W, H, dm, seed, kw):
+    """Second scene family (1/f texture, sub-pixel disparities slanted in u and v, occluding boxes,
+    textureless patch): more, less regular support points and real matching failures."""
+    I1, I2, gt = synth.textured_pair(W, H, dm, seed)
+    p = ol.robotics(dm, **kw)
+    a, b = ref.stages(p, I1, I2), port.stages(p, I1, I2)
+    assert a["rc"] == b["rc"] == 0
+    for k in STAGE_KEYS:
+        assert a[k].shape == b[k].shape, k
+        assert np.array_equal(a[k], b[k]), "%s: %d mismatches" % (k, int((a[k] != b[k]).sum()))
+    if W >= 640:
+        valid = a["D1"] >= 0
+        assert valid.mean() > 0.8 and (np.abs(a["D1"] - gt)[valid] <= 1).mean() > 0.97
+
+
 def test_port_middlebury_matches_reference(ref, port, synth):
     I1, I2, _ = synth.synth_pair(320, 240, 64, 3)
     p = ol.middlebury(64)
