@@ -5,7 +5,8 @@
 
 // In-place exclusive prefix sum of data[0..n) by the whole CTA; returns the total.
 // `part` is shared scratch of blockDim.x + 1 ints.  All threads must call.
-__device__ inline int block_exclusive_scan(int* data, int n, int* part) {
+template <typename E>
+__device__ inline int block_exclusive_scan(E* data, int n, int* part) {
   const int T = blockDim.x, t = threadIdx.x;
   const int chunk = (n + T - 1) / T;
   const int lo = min(t * chunk, n), hi = min(lo + chunk, n);
@@ -36,7 +37,7 @@ __device__ inline int block_exclusive_scan(int* data, int n, int* part) {
   __syncthreads();
   for (int i = lo; i < hi; i++) {
     int v = data[i];
-    data[i] = run;
+    data[i] = (E)run;
     run += v;
   }
   __syncthreads();

@@ -11,8 +11,8 @@
 // organised for a GPU:
 //
 //   * one CTA per (frame, image side); frames of a batch run concurrently;
-//   * ordering: a bitonic sort of 64-bit (coordinate, coordinate, index) keys in
-//     shared memory gives the (x,y) and (y,x) orders and drops duplicates; the
+//   * ordering: a stable LSD radix sort (7-bit digits, match.any ranking) of 27-bit (x,y) keys in
+//     shared memory gives the (x,y) order and drops duplicates, two more passes the (y,x) order; the
 //     alternating-axis median partition (a k-d tree build) is done level by
 //     level with stable CTA-wide partitions of the two presorted lists;
 //   * the recursion is unrolled into levels: all subproblems of one depth are
@@ -23,10 +23,19 @@
 //   * the triangle table (3 neighbour handles + 3 vertex ids per row) lives in
 //     shared memory as 6 x u16 per row (a handle = 4*row + orientation < 65536
 //     for up to 16384 rows): the merges are serial pointer chasing, and a shared
-//     memory access costs ~30 cycles against several hundred for L2.  Point
-//     sets too large for that (> SMEM_MAX_POINTS) use the same code on 32-bit
-//     tables in global memory;
+//     memory access costs ~30 cycles against several hundred for L2;
 //   * predicates are exact 64-bit integer determinants (coordinates < 2^13).
+//
+//   * point sets above SMEM_MAX_POINTS are cut at the D&C tree level whose subtrees fit: every
+//     subtree is built in shared memory (all its levels), written out as 32-bit rows, and only the
+//     few top-level merges (one, for up to 16 384 points) run on the table in global memory.
+//
+// merge_hulls() and leaf_case() below are a statement-for-statement transliteration of
+// Triangle's mergehulls() / the base cases of divconqrecurse() onto table rows with integer
+// predicates -- the same walk, the same strict comparisons, the same allocation order: the
+// ORDERED triangle list must equal Triangle's, and that leaves no freedom in these two
+// functions.  Everything around them (ordering, partition, level-synchronous scheduling, the
+// table layouts, the subtree tiling) is this kernel's own organisation.
 //
 // Known deviation: among duplicate right-image points (u-d,v) Triangle keeps
 // the one its randomized quicksort happens to put first; this kernel keeps the
@@ -37,11 +46,14 @@
 namespace {
 
 constexpr int DT = 512;
-constexpr int SMEM_MAX_POINTS = 7680;                      // 2n-2 rows * 12 B + n * 4 B <= ~210 KB
-constexpr int SORT_MAX = 8192;                             // bitonic sort capacity (64 KB of keys)
-// dynamic shared memory: sort keys (64 KB), then the partition lists (216 KB), then the triangle
-// table + packed coordinates (2*7680 rows * 12 B + 7680 * 4 B = 210 KB)
-constexpr size_t DELAUNAY_SMEM = 220 * 1024;
+constexpr int NW = DT / 32;
+constexpr int SMEM_MAX_POINTS = 8192;    // one table in shared memory: (2n-2 rows * 12 B + n * 4 B) = 224 KB;
+                                         // 2n-2 <= 16 382 rows keeps a handle (4*row + orientation) in 16 bits
+constexpr int SORT_MAX = 16384;          // ordering + partition in shared memory (16-bit indices, 216 KB)
+constexpr int RADIX_BITS = 7, RADIX = 1 << RADIX_BITS;
+// dynamic shared memory, in 32 KB regions R0..R5, R6 (16 KB), R7 (8 KB) during ordering/partition
+// (see delaunay_kernel), then the triangle table (192 KB) + packed coordinates (32 KB)
+constexpr size_t DELAUNAY_SMEM = 224 * 1024;
 
 struct Ot { int t, o; };
 
@@ -52,6 +64,8 @@ __device__ __forceinline__ Ot dec(int e) { Ot r; r.t = e >> 2; r.o = e & 3; retu
 __device__ __forceinline__ Ot lnext(Ot a) { a.o = p1(a.o); return a; }
 __device__ __forceinline__ Ot lprev(Ot a) { a.o = m1(a.o); return a; }
 
+// Mesh vertex ids are POSITIONS in Triangle's final sortarray (0..nu-1; a subtree built in shared
+// memory numbers its own points from 0); the emission maps them back to support indices.
 // Triangle table in global memory, 32-bit entries.
 struct MeshG {
   int* nb; int* vx; const int* x; const int* y;
@@ -307,9 +321,10 @@ __device__ void merge_hulls(const M& m, Ot& farleft, Ot innerleft, Ot innerright
 }
 
 // Base cases of divconqrecurse: 2 points = an edge (2 ghosts), 3 points = a
-// triangle + 3 ghosts or two edges (4 ghosts).
+// triangle + 3 ghosts or two edges (4 ghosts).  The points are vertex ids v0, v0+1[, v0+2].
 template <class M>
-__device__ void leaf_case(const M& m, const int* sa, int n, int row, Ot& farleft, Ot& farright) {
+__device__ void leaf_case(const M& m, int v0, int n, int row, Ot& farleft, Ot& farright) {
+  const int sa[3] = {v0, v0 + 1, v0 + 2};
   if (n == 2) {
     Ot a = newtri(m, row);
     setorg(m, a, sa[0]);
@@ -370,41 +385,54 @@ __device__ void leaf_case(const M& m, const int* sa, int n, int row, Ot& farleft
   }
 }
 
-// All merges of one triangulation, deepest level first, then the non-ghost rows in row
-// order (writeelements).  Returns the triangle count.
+// Node (d,k) of the D&C tree over nu points: follow the bits of k from the root.  Returns false
+// if the node does not exist (an ancestor was already a leaf).
+__device__ __forceinline__ bool locate_node(int nu, int d, int k, int& lo, int& cnt, int& row) {
+  lo = 0; cnt = nu; row = 0;
+  for (int b = d - 1; b >= 0; b--) {
+    if (cnt <= 3) return false;
+    const int dv = cnt >> 1;
+    if ((k >> b) & 1) { lo += dv; row += 2 * dv - 2; cnt -= dv; }
+    else cnt = dv;
+  }
+  return true;
+}
+
+// All merges of the levels dfrom (deepest) .. dto of the subtree rooted at node (L,s), one thread
+// per node, a CTA barrier between levels.  The mesh numbers rows and vertices relative to the
+// subtree (row_off, pos_off); nodeL/nodeR carry the far-left / far-right handles in that numbering.
 template <class M>
-__device__ int build_and_emit(const M& m, const int* sa, int nu, int depth, int* nodeL, int* nodeR, int* flag,
-                              int* tri, int* s_part) {
+__device__ void build_levels(const M& m, int nu, int dfrom, int dto, int L, int s, int row_off, int pos_off,
+                             int* nodeL, int* nodeR) {
   const int tid = threadIdx.x;
-  for (int d = depth; d >= 0; d--) {
-    const int nodes = 1 << d;
-    for (int k = tid; k < nodes; k += DT) {
-      // locate node (d,k): follow the bits of k from the root
-      int lo = 0, cnt = nu, row = 0;
-      bool exists = true;
-      for (int b = d - 1; b >= 0; b--) {
-        if (cnt <= 3) { exists = false; break; }
-        int dv = cnt >> 1;
-        if ((k >> b) & 1) { lo += dv; row += 2 * dv - 2; cnt -= dv; }
-        else cnt = dv;
-      }
-      if (!exists) continue;
+  for (int d = dfrom; d >= dto; d--) {
+    const int sub = 1 << (d - L);
+    for (int j = tid; j < sub; j += DT) {
+      const int k = (s << (d - L)) + j;
+      int lo, cnt, row;
+      if (!locate_node(nu, d, k, lo, cnt, row)) continue;
       Ot fl, fr;
       if (cnt <= 3) {
-        leaf_case(m, sa + lo, cnt, row, fl, fr);
+        leaf_case(m, lo - pos_off, cnt, row - row_off, fl, fr);
       } else {
-        int c0 = (1 << (d + 1)) + 2 * k;
+        const int c0 = (1 << (d + 1)) + 2 * k;
         fl = dec(nodeL[c0]);
         Ot il = dec(nodeR[c0]);
         Ot ir = dec(nodeL[c0 + 1]);
         fr = dec(nodeR[c0 + 1]);
-        merge_hulls(m, fl, il, ir, fr, d & 1, row + 2 * cnt - 4, row + 2 * cnt - 3);
+        merge_hulls(m, fl, il, ir, fr, d & 1, row - row_off + 2 * cnt - 4, row - row_off + 2 * cnt - 3);
       }
-      nodeL[nodes + k] = enc(fl);
-      nodeR[nodes + k] = enc(fr);
+      nodeL[(1 << d) + k] = enc(fl);
+      nodeR[(1 << d) + k] = enc(fr);
     }
     __syncthreads();
   }
+}
+
+// The non-ghost rows in row order (writeelements), vertex positions mapped back to support indices.
+template <class M>
+__device__ int emit_triangles(const M& m, const int* sa, int nu, int* flag, int* tri, int* s_part) {
+  const int tid = threadIdx.x;
   const int rows = 2 * nu - 2;
   for (int t = tid; t < rows; t += DT)
     flag[t] = (m.getvx(t, 0) >= 0 && m.getvx(t, 1) >= 0 && m.getvx(t, 2) >= 0);
@@ -414,29 +442,104 @@ __device__ int build_and_emit(const M& m, const int* sa, int nu, int depth, int*
     int v0 = m.getvx(t, 0), v1 = m.getvx(t, 1), v2 = m.getvx(t, 2);
     if (v0 >= 0 && v1 >= 0 && v2 >= 0) {
       int k = flag[t];
-      tri[3 * k] = v1;       // org
-      tri[3 * k + 1] = v2;   // dest
-      tri[3 * k + 2] = v0;   // apex
+      tri[3 * k] = sa[v1];       // org
+      tri[3 * k + 1] = sa[v2];   // dest
+      tri[3 * k + 2] = sa[v0];   // apex
     }
   }
   return nt;
 }
 
-// ascending bitonic sort of N (power of two) 64-bit keys in shared memory
-__device__ void bitonic_sort(unsigned long long* key, int N) {
-  const int tid = threadIdx.x;
-  for (int k = 2; k <= N; k <<= 1)
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = tid; i < N; i += DT) {
-        int ixj = i ^ j;
-        if (ixj > i) {
-          unsigned long long a = key[i], b = key[ixj];
-          bool asc = (i & k) == 0;
-          if ((a > b) == asc) { key[i] = b; key[ixj] = a; }
-        }
-      }
-      __syncthreads();
+// One stable LSD radix pass over n (key, index) pairs in shared memory, 7-bit digit at `shift`.
+// Warp w owns a contiguous slice; hist[digit * NW + w] counts its digits, an exclusive scan in
+// (digit, warp) order turns the counts into output offsets, and the scatter ranks equal digits
+// inside a 32-element step with match.any (earlier lanes first), so the pass is stable.
+template <typename K>
+__device__ void radix_pass(const K* key, const unsigned short* idx, K* okey, unsigned short* oidx, int n, int shift,
+                           int* hist, int* s_part) {
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int slice = ((n + DT - 1) / DT) * 32;
+  const int lo = min(w * slice, n), hi = min(lo + slice, n);
+  for (int i = tid; i < RADIX * NW; i += DT) hist[i] = 0;
+  __syncthreads();
+  for (int i = lo + lane; i < hi; i += 32) atomicAdd(&hist[(((unsigned)key[i] >> shift) & (RADIX - 1)) * NW + w], 1);
+  __syncthreads();
+  block_exclusive_scan(hist, RADIX * NW, s_part);
+  for (int base = lo; base < hi; base += 32) {
+    const int i = base + lane;
+    const bool act = i < hi;
+    K kv = 0;
+    unsigned short iv = 0;
+    if (act) { kv = key[i]; iv = idx[i]; }
+    const unsigned d = act ? (((unsigned)kv >> shift) & (RADIX - 1)) : (unsigned)RADIX;
+    const unsigned m = __match_any_sync(0xffffffffu, d);
+    const int leader = __ffs(m) - 1;
+    int old = 0;
+    if (act && lane == leader) {
+      old = hist[d * NW + w];
+      hist[d * NW + w] = old + __popc(m);
     }
+    old = __shfl_sync(0xffffffffu, old, leader);
+    if (act) {
+      const int pos = old + __popc(m & ((1u << lane) - 1u));
+      okey[pos] = kv;
+      oidx[pos] = iv;
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+}
+
+// Alternating-axis median partition (alternateaxes), level by level: at every level each segment
+// of >= 4 points is cut at its median along the level's axis; the list sorted along the other axis
+// is split stably to match.  Returns the number of levels that split something; the final order
+// (Triangle's sortarray) is left in xl.
+template <typename TI, typename TF>
+__device__ int partition_levels(TI*& xl, TI*& yl, TI*& sp, TI* scan, TI* seglo, TI* segn, TF* flag, int nu,
+                                int* s_part, int* s_flag) {
+  const int tid = threadIdx.x;
+  for (int i = tid; i < nu; i += DT) { seglo[i] = 0; segn[i] = (TI)nu; }
+  __syncthreads();
+  int depth = 0;
+  for (;; depth++) {
+    if (tid == 0) *s_flag = 0;
+    __syncthreads();
+    TI* prim = (depth & 1) ? yl : xl;
+    TI* sec = (depth & 1) ? xl : yl;
+    for (int i = tid; i < nu; i += DT) {
+      int ns = segn[i];
+      int r = 0;
+      if (ns >= 4) { r = (i - (int)seglo[i]) >= (ns >> 1); *s_flag = 1; }
+      flag[prim[i]] = (TF)r;
+    }
+    __syncthreads();
+    if (!*s_flag) break;
+    for (int i = tid; i < nu; i += DT) scan[i] = (TI)flag[sec[i]];
+    __syncthreads();
+    block_exclusive_scan(scan, nu, s_part);
+    for (int i = tid; i < nu; i += DT) {
+      int ns = segn[i], lo = seglo[i], id = sec[i];
+      int pos = i;
+      if (ns >= 4) {
+        int rb = (int)scan[i] - (int)scan[lo];
+        pos = flag[id] ? lo + (ns >> 1) + rb : lo + (i - lo - rb);
+      }
+      sp[pos] = (TI)id;
+    }
+    __syncthreads();
+    for (int i = tid; i < nu; i += DT) {
+      int ns = segn[i], lo = seglo[i];
+      if (ns >= 4) {
+        int dv = ns >> 1;
+        if (i - lo < dv) segn[i] = (TI)dv;
+        else { seglo[i] = (TI)(lo + dv); segn[i] = (TI)(ns - dv); }
+      }
+    }
+    // the partitioned copy becomes the secondary list
+    if (depth & 1) { TI* t = xl; xl = sp; sp = t; } else { TI* t = yl; yl = sp; sp = t; }
+    __syncthreads();
+  }
+  return depth;
 }
 
 __device__ __forceinline__ long long gtime() {
@@ -459,65 +562,77 @@ delaunay_kernel(Geo g, Workspace ws) {
   const size_t fo = (size_t)frame * g.cap_s;
   const int* px = ws.px[side] + fo;
   const int* py = ws.py + fo;
-  int* const xl_g = ws.xlist[side] + fo;
+  int* const sa_g = ws.xlist[side] + fo;                        // final sortarray (support indices)
   int* const flag_g = ws.tmpD[side] + (size_t)frame * g.cap_t;  // cap_t ints
-  int *xl = xl_g, *yl = ws.ylist[side] + fo, *sp = ws.tmpA[side] + fo;
-  int *seglo = ws.tmpB[side] + fo, *segn = ws.tmpC[side] + fo;
-  int* flag = flag_g;
-  int* scan = ws.nodeL[side] + (size_t)frame * g.cap_t;         // reused before the merge phase
-  const bool small = n <= g.dl_smem_max;
-  if (small) {
-    // ordering + partition arrays in shared memory (their passes are latency bound in HBM/L2):
-    //   [0,64K) sort keys, later flag + seglo | [64K,156K) xl, yl, sp | [156K,186K) scan | [186K,216K) segn
-    int* base = reinterpret_cast<int*>(dsm);
-    flag = base;
-    seglo = base + SMEM_MAX_POINTS;
-    xl = base + 16384;
-    yl = xl + SMEM_MAX_POINTS;
-    sp = yl + SMEM_MAX_POINTS;
-    scan = sp + SMEM_MAX_POINTS;
-    segn = scan + SMEM_MAX_POINTS;
-  }
+  int* const posx = ws.tmpB[side] + fo;                         // coordinates by sortarray position
+  int* const posy = ws.tmpC[side] + fo;
   if (tid == 0) info->dt[side][0] = gtime();
 
-  // ---- 1. (x,y) order without duplicates, then (y,x) order ------------------------------------
-  int nu;
+  int nu, depth;
+  const int* sa;
   if (n <= g.dl_sort_max) {
-    unsigned long long* key = reinterpret_cast<unsigned long long*>(dsm);
-    int N = 2;
-    while (N < n) N <<= 1;
-    for (int i = tid; i < N; i += DT)
-      key[i] = (i < n) ? (((unsigned long long)px[i] << 48) | ((unsigned long long)py[i] << 32) | (unsigned)i)
-                       : ~0ull;
-    __syncthreads();
-    bitonic_sort(key, N);
-    // first of every (x,y) run survives = lowest support index
-    for (int i = tid; i < n; i += DT) scan[i] = (i == 0) || ((key[i] >> 32) != (key[i - 1] >> 32));
-    __syncthreads();
-    nu = block_exclusive_scan(scan, n, s_part);
+    // ---- 1+2 in shared memory, 16-bit indices.  Regions (bytes): R0 [0,32K) R1 [32K,64K) R2 [64K,96K)
+    // R3 [96K,128K) R4 [128K,160K) R5 [160K,192K) R6 [192K,208K) R7 [208K,216K)
+    typedef unsigned short u16;
+    u16* const R0 = reinterpret_cast<u16*>(dsm);
+    u16* const R1 = R0 + SORT_MAX;
+    u16* const R2 = R1 + SORT_MAX;
+    u16* const R3 = R2 + SORT_MAX;
+    u16* const R4 = R3 + SORT_MAX;
+    u16* const R5 = R4 + SORT_MAX;
+    unsigned char* const R6 = reinterpret_cast<unsigned char*>(R5 + SORT_MAX);
+    int* const hist = reinterpret_cast<int*>(R6 + SORT_MAX);
+    // 1a. (x,y) order, stable in the support index: 4 passes over 27-bit keys x << 13 | y
+    unsigned* K0 = reinterpret_cast<unsigned*>(R2);
+    unsigned* K1 = reinterpret_cast<unsigned*>(R4);
     for (int i = tid; i < n; i += DT) {
-      bool first = (i == 0) || ((key[i] >> 32) != (key[i - 1] >> 32));
-      if (first) xl[scan[i]] = (int)(key[i] & 0xFFFFFFFFu);
+      K0[i] = ((unsigned)px[i] << 13) | (unsigned)py[i];
+      R0[i] = (u16)i;
     }
     __syncthreads();
-    for (int i = tid; i < N; i += DT) {
-      unsigned long long k = ~0ull;
-      if (i < nu) {
-        int id = xl[i];
-        k = ((unsigned long long)py[id] << 48) | ((unsigned long long)px[id] << 32) | (unsigned)id;
-      }
-      key[i] = k;
+    radix_pass(K0, R0, K1, R1, n, 0, hist, s_part);
+    radix_pass(K1, R1, K0, R0, n, RADIX_BITS, hist, s_part);
+    radix_pass(K0, R0, K1, R1, n, 2 * RADIX_BITS, hist, s_part);
+    radix_pass(K1, R1, K0, R0, n, 3 * RADIX_BITS, hist, s_part);
+    // 1b. the first of every (x,y) run survives = lowest support index (K1 is free: scan scratch)
+    int* scan32 = reinterpret_cast<int*>(K1);
+    for (int i = tid; i < n; i += DT) scan32[i] = (i == 0) || (K0[i] != K0[i - 1]);
+    __syncthreads();
+    nu = block_exclusive_scan(scan32, n, s_part);
+    u16* xl = R1;
+    for (int i = tid; i < n; i += DT)
+      if ((i == 0) || (K0[i] != K0[i - 1])) xl[scan32[i]] = R0[i];
+    __syncthreads();
+    if (nu < 2) {
+      if (tid == 0) info->n_tri[side] = 0;
+      return;
     }
+    // 1c. (y,x) order: stable sort of the (x,y)-ordered list by y alone, 2 passes over 13-bit keys
+    for (int i = tid; i < nu; i += DT) { R2[i] = (u16)py[xl[i]]; R4[i] = xl[i]; }
     __syncthreads();
-    bitonic_sort(key, N);
-    for (int i = tid; i < nu; i += DT) yl[i] = (int)(key[i] & 0xFFFFFFFFu);
-    __syncthreads();
+    radix_pass(R2, R4, R3, R5, nu, 0, hist, s_part);
+    radix_pass(R3, R5, R2, R4, nu, RADIX_BITS, hist, s_part);
+    u16* yl = R4;
+    if (tid == 0) info->dt[side][1] = gtime();
+    // 2. partition
+    u16* sp = R0;
+    depth = partition_levels<u16, unsigned char>(xl, yl, sp, R2, R3, R5, R6, nu, s_part, &s_flag);
+    for (int i = tid; i < nu; i += DT) {
+      const int id = xl[i];
+      sa_g[i] = id;
+      posx[i] = px[id];
+      posy[i] = py[id];
+    }
+    sa = sa_g;
   } else if (g.p.add_corners) {
     // corner points are off the lattice the occupancy grid is built on: not supported together
     if (tid == 0) { info->status = JN_ERR_UNSUPPORTED; info->n_tri[side] = 0; }
     return;
   } else {
-    // large point sets: ranks by prefix sums over an occupancy grid (preset to OCC_EMPTY)
+    // ---- very large point sets: everything in global memory; ranks by prefix sums over an
+    // occupancy grid (preset to OCC_EMPTY)
+    int *xl = sa_g, *yl = ws.ylist[side] + fo, *sp = ws.tmpA[side] + fo;
+    int* scan = ws.nodeL[side] + (size_t)frame * g.cap_t;         // reused before the merge phase
     const int step = g.p.candidate_stepsize;
     const int xdim = side ? g.W : g.Wc, xdiv = side ? 1 : step, Hc = g.Hc;
     const int cells = xdim * Hc;
@@ -546,83 +661,80 @@ delaunay_kernel(Geo g, Workspace ws) {
       if (id != OCC_EMPTY) yl[scanbig[j]] = id;
     }
     __syncthreads();
-  }
-  if (nu < 2) {
-    if (tid == 0) info->n_tri[side] = 0;
-    return;
-  }
-  if (tid == 0) info->dt[side][1] = gtime();
-
-  // ---- 2. alternating-axis median partition (alternateaxes), level by level -------------
-  for (int i = tid; i < nu; i += DT) { seglo[i] = 0; segn[i] = nu; }
-  __syncthreads();
-  int depth = 0;   // number of levels that split something = depth of the deepest leaves
-  for (;; depth++) {
-    if (tid == 0) s_flag = 0;
-    __syncthreads();
-    int* prim = (depth & 1) ? yl : xl;
-    int* sec = (depth & 1) ? xl : yl;
-    for (int i = tid; i < nu; i += DT) {
-      int ns = segn[i];
-      int r = 0;
-      if (ns >= 4) { r = (i - seglo[i]) >= (ns >> 1); s_flag = 1; }
-      flag[prim[i]] = r;
+    if (nu < 2) {
+      if (tid == 0) info->n_tri[side] = 0;
+      return;
     }
-    __syncthreads();
-    if (!s_flag) break;
-    for (int i = tid; i < nu; i += DT) scan[i] = flag[sec[i]];
-    __syncthreads();
-    block_exclusive_scan(scan, nu, s_part);
-    for (int i = tid; i < nu; i += DT) {
-      int ns = segn[i], lo = seglo[i], id = sec[i];
-      int pos = i;
-      if (ns >= 4) {
-        int rb = scan[i] - scan[lo];
-        pos = flag[id] ? lo + (ns >> 1) + rb : lo + (i - lo - rb);
-      }
-      sp[pos] = id;
+    if (tid == 0) info->dt[side][1] = gtime();
+    // seglo/segn/flag of the partition live in the arrays that later hold the positions' coordinates
+    // and the emission flags; the final order can end up in any of the three list buffers
+    depth = partition_levels<int, int>(xl, yl, sp, scan, posx, posy, flag_g, nu, s_part, &s_flag);
+    if (xl != sa_g) {
+      for (int i = tid; i < nu; i += DT) sa_g[i] = xl[i];
     }
     __syncthreads();
     for (int i = tid; i < nu; i += DT) {
-      int ns = segn[i], lo = seglo[i];
-      if (ns >= 4) {
-        int dv = ns >> 1;
-        if (i - lo < dv) segn[i] = dv;
-        else { seglo[i] = lo + dv; segn[i] = ns - dv; }
-      }
+      const int id = sa_g[i];
+      posx[i] = px[id];
+      posy[i] = py[id];
     }
-    // the partitioned copy becomes the secondary list
-    if (depth & 1) { int* t = xl; xl = sp; sp = t; } else { int* t = yl; yl = sp; sp = t; }
-    __syncthreads();
+    sa = sa_g;
   }
-  if (small) {
-    // the shared memory is recycled for the triangle table: keep the final order in HBM
-    for (int i = tid; i < nu; i += DT) xl_g[i] = xl[i];
-    xl = xl_g;
-  }
-  const int* sa = xl;   // Triangle's final sortarray
+  __syncthreads();   // the shared-memory lists are dead, sa_g / posx / posy are written
   if (tid == 0) { info->dt[side][2] = gtime(); info->dmerge_depth = depth; }
 
   // ---- 3. merges + emission --------------------------------------------------------------------
   int* nodeL = ws.nodeL[side] + (size_t)frame * g.cap_t;
   int* nodeR = ws.nodeR[side] + (size_t)frame * g.cap_t;
   int* tri = ws.tri[side] + (size_t)frame * g.cap_t * 3;
+  MeshS ms;
+  ms.rows = reinterpret_cast<unsigned short*>(dsm);
+  unsigned* xy = reinterpret_cast<unsigned*>(dsm + (size_t)(2 * SMEM_MAX_POINTS) * 12);
+  ms.xy = xy;
+  MeshG mg;
+  mg.nb = ws.nb[side] + (size_t)frame * g.cap_t * 3;
+  mg.vx = ws.vx[side] + (size_t)frame * g.cap_t * 3;
+  mg.x = posx; mg.y = posy;
+  const int smem_max = min(g.dl_smem_max, SMEM_MAX_POINTS);
   int nt;
-  __syncthreads();
-  if (n <= g.dl_smem_max) {
-    MeshS m;
-    m.rows = reinterpret_cast<unsigned short*>(dsm);
-    unsigned* xy = reinterpret_cast<unsigned*>(dsm + (size_t)(2 * SMEM_MAX_POINTS) * 12);
-    for (int i = tid; i < n; i += DT) xy[i] = ((unsigned)px[i] << 16) | (unsigned)py[i];
-    m.xy = xy;
+  if (nu <= smem_max) {
+    for (int i = tid; i < nu; i += DT) xy[i] = ((unsigned)posx[i] << 16) | (unsigned)posy[i];
     __syncthreads();
-    nt = build_and_emit(m, sa, nu, depth, nodeL, nodeR, flag_g, tri, s_part);
+    build_levels(ms, nu, depth, 0, 0, 0, 0, 0, nodeL, nodeR);
+    nt = emit_triangles(ms, sa, nu, flag_g, tri, s_part);
   } else {
-    MeshG m;
-    m.nb = ws.nb[side] + (size_t)frame * g.cap_t * 3;
-    m.vx = ws.vx[side] + (size_t)frame * g.cap_t * 3;
-    m.x = px; m.y = py;
-    nt = build_and_emit(m, sa, nu, depth, nodeL, nodeR, flag_g, tri, s_part);
+    // cut the tree at the first level L whose subtrees fit the shared-memory table (a node of c
+    // points has children of c/2 and c - c/2 points); a table needs at least 2 points per subtree
+    int L = 0;
+    for (int c = nu; c > smem_max && L < depth; c -= c >> 1) L++;
+    if (smem_max < 4) L = depth + 1;             // test hook: everything on the global table
+    if (L <= depth) {
+      for (int s = 0; s < (1 << L); s++) {
+        int lo, cnt, row;
+        if (!locate_node(nu, L, s, lo, cnt, row)) continue;
+        for (int i = tid; i < cnt; i += DT) xy[i] = ((unsigned)posx[lo + i] << 16) | (unsigned)posy[lo + i];
+        __syncthreads();
+        build_levels(ms, nu, depth, L, L, s, row, lo, nodeL, nodeR);
+        // write the subtree out: rows and vertex positions renumbered to the whole problem
+        const int nrows = (cnt <= 3) ? ((cnt == 2) ? 2 : 4) : 2 * cnt - 2;
+        for (int q = tid; q < nrows * 3; q += DT) {
+          const int t = q / 3, o = q - 3 * t;
+          mg.nb[3 * (row + t) + o] = ms.getnb(t, o) + 4 * row;
+          const int v = ms.getvx(t, o);
+          mg.vx[3 * (row + t) + o] = v < 0 ? -1 : v + lo;
+        }
+        if (tid == 0) {
+          nodeL[(1 << L) + s] += 4 * row;
+          nodeR[(1 << L) + s] += 4 * row;
+        }
+        __syncthreads();
+      }
+      if (tid == 0) info->dt[side][3] = gtime();
+      build_levels(mg, nu, L - 1, 0, 0, 0, 0, 0, nodeL, nodeR);
+    } else {
+      build_levels(mg, nu, depth, 0, 0, 0, 0, 0, nodeL, nodeR);
+    }
+    nt = emit_triangles(mg, sa, nu, flag_g, tri, s_part);
   }
   if (tid == 0) { info->n_tri[side] = nt; info->dt[side][4] = gtime(); }
 }
@@ -643,7 +755,7 @@ int launch_delaunay(const Geo& g_in, int B, Workspace& ws, cudaStream_t s) {
   // per device (context), not per process: set on every launch, it is a host-side table write
   JN_CUDA_CHECK(cudaFuncSetAttribute(delaunay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)DELAUNAY_SMEM));
-  // the occupancy grids (only used above SORT_MAX points) start "empty" = 0x7f7f7f7f
+  // the occupancy grids (only used above the sort limit) start "empty" = 0x7f7f7f7f
   if (g.cap_s > g.dl_sort_max)
     JN_CUDA_CHECK(cudaMemsetAsync(ws.occ, 0x7f, (size_t)B * 2 * g.W * g.Hc * sizeof(int32_t), s));
   delaunay_kernel<<<dim3(2, B), DT, DELAUNAY_SMEM, s>>>(g, ws);

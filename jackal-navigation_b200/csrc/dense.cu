@@ -41,8 +41,17 @@ __device__ __forceinline__ int f2u_lo32(float x) { return (int)(unsigned)(unsign
 // between belong to this triangle alone and take a plain store.  Checked on the CPU restatement
 // (tests/test_oracle_pin.py::test_raster_overlaps_stay_on_span_borders): 0 of 61 M covered pixels
 // over 3 000 random and 37 pipeline triangulations had a second cover strictly inside a span.
-__device__ __forceinline__ void write_span(int* __restrict__ map, int W, int u, int vlo, int vhi, int i) {
+// The argument needs the float edge evaluation a*u + b to be off by less than one row; its error grows
+// with the magnitude of the operands, so the plain stores are only used while the image is small
+// enough for that (`exact`: W, H <= 2048, where |a*u|, |b| < 2^23 keep the rounding error of the sum
+// below 1/4 row -- checked at 2048 x 2048 with steep hull edges by the same test); larger images
+// take atomicMax on every row.
+__device__ __forceinline__ void write_span(int* __restrict__ map, int W, int u, int vlo, int vhi, int i, bool exact) {
   if (vhi <= vlo) return;
+  if (!exact) {
+    for (int v = vlo; v < vhi; v++) atomicMax(&map[v * W + u], i);
+    return;
+  }
   atomicMax(&map[vlo * W + u], i);
   if (vhi - 1 > vlo) atomicMax(&map[(vhi - 1) * W + u], i);
   for (int v = vlo + 1; v < vhi - 1; v++) map[v * W + u] = i;
@@ -58,6 +67,7 @@ __global__ void raster_kernel(Geo g, Workspace ws) {
   const int* tri = ws.tri[side] + (size_t)frame * g.cap_t * 3;
   int* map = ws.trimap[side] + (size_t)frame * W * H;
   const int lane = threadIdx.x & 31;
+  const bool exact = W <= 2048 && H <= 2048;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   for (int i = warp; i < nt; i += nwarps) {
     float tu[3], tv[3];
@@ -86,13 +96,13 @@ __global__ void raster_kernel(Geo g, Workspace ws) {
       for (int u = max((int)Au, 0) + lane; u < min((int)Bu, W); u += 32) {
         int v1 = f2u_lo32(ACa * (float)u + ACb), v2 = f2u_lo32(ABa * (float)u + ABb);
         int vlo = max(min(v1, v2), 0), vhi = min(max(v1, v2), H);
-        write_span(map, W, u, vlo, vhi, i);
+        write_span(map, W, u, vlo, vhi, i, exact);
       }
     if ((int)Bu != (int)Cu)
       for (int u = max((int)Bu, 0) + lane; u < min((int)Cu, W); u += 32) {
         int v1 = f2u_lo32(ACa * (float)u + ACb), v2 = f2u_lo32(BCa * (float)u + BCb);
         int vlo = max(min(v1, v2), 0), vhi = min(max(v1, v2), H);
-        write_span(map, W, u, vlo, vhi, i);
+        write_span(map, W, u, vlo, vhi, i, exact);
       }
   }
 }

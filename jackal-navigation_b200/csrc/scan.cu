@@ -317,6 +317,8 @@ struct jn_scan {
   // single-frame scratch
   float* dD; double* dRanges; jn_scan_meta* dMeta; uint8_t* dU8;
   int* dCol; int* dTotal; double* dPts;
+  // -g path scratch, allocated on first use and kept (no cudaMalloc per frame)
+  uint8_t* dImg; size_t img_bytes; float* dXyz;
 };
 
 static int ensure_acc(jn_scan* s, int n) {
@@ -366,6 +368,8 @@ extern "C" jn_scan* jn_scan_create(const jn_calib* cal, int width, int height, i
 
 extern "C" void jn_scan_destroy(jn_scan* s) {
   if (!s) return;
+  cudaSetDevice(s->device);
+  cudaFree(s->dImg); cudaFree(s->dXyz);
   cudaFree(s->gate); cudaFree(s->acc); cudaFree(s->dD); cudaFree(s->dRanges); cudaFree(s->dMeta);
   cudaFree(s->dU8); cudaFree(s->dCol); cudaFree(s->dTotal); cudaFree(s->dPts);
   delete s;
@@ -373,6 +377,7 @@ extern "C" void jn_scan_destroy(jn_scan* s) {
 
 extern "C" int jn_scan_gate_cache(jn_scan* s, uint8_t* out) {
   if (!s || !out) return JN_ERR_ARG;
+  JN_CUDA_CHECK(cudaSetDevice(s->device));
   JN_CUDA_CHECK(cudaMemcpy(out, s->gate, 2 * (size_t)s->c.W * s->c.H, cudaMemcpyDeviceToHost));
   return JN_OK;
 }
@@ -381,6 +386,7 @@ extern "C" int jn_scan_from_disparity_batch(jn_scan* s, int n, const float* D, d
                                             uint8_t* dmap_u8, void* stream) {
   if (!s || n <= 0 || !D || !ranges || !meta) return JN_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
+  JN_CUDA_CHECK(cudaSetDevice(s->device));
   int rc = ensure_acc(s, n);
   if (rc) return rc;
   acc_reset_kernel<<<(n * ACC_WORDS + 255) / 256, 256, 0, st>>>(s->acc, n);
@@ -397,6 +403,7 @@ extern "C" int jn_scan_from_disparity(jn_scan* s, const float* D, double ranges[
                                       uint8_t* dmap_u8) {
   if (!s || !D || !ranges || !meta) return JN_ERR_ARG;
   size_t n = (size_t)s->c.W * s->c.H;
+  JN_CUDA_CHECK(cudaSetDevice(s->device));
   JN_CUDA_CHECK(cudaMemcpy(s->dD, D, n * sizeof(float), cudaMemcpyHostToDevice));
   int rc = jn_scan_from_disparity_batch(s, 1, s->dD, s->dRanges, s->dMeta, dmap_u8 ? s->dU8 : nullptr, 0);
   if (rc) return rc;
@@ -410,6 +417,7 @@ extern "C" int jn_points_from_disparity(jn_scan* s, const float* D, double* poin
                                         double ranges[JN_SCAN_BINS], jn_scan_meta* meta) {
   if (!s || !D || !points || !n_points || !ranges || !meta) return JN_ERR_ARG;
   size_t n = (size_t)s->c.W * s->c.H;
+  JN_CUDA_CHECK(cudaSetDevice(s->device));
   int rc = ensure_acc(s, 1);
   if (rc) return rc;
   JN_CUDA_CHECK(cudaMemcpy(s->dD, D, n * sizeof(float), cudaMemcpyHostToDevice));
@@ -438,13 +446,18 @@ extern "C" int jn_pointcloud_from_disparity(jn_scan* s, const float* D, const ui
     return JN_ERR_ARG;
   }
   const size_t n = (size_t)s->c.W * s->c.H, ibytes = (size_t)image_stride * s->c.H;
+  JN_CUDA_CHECK(cudaSetDevice(s->device));
   int rc = ensure_acc(s, 1);
   if (rc) return rc;
-  JN_CUDA_CHECK(cudaSetDevice(s->device));
-  uint8_t* dImg = nullptr;
-  float* dXyz = nullptr;
-  JN_CUDA_CHECK(cudaMalloc(&dImg, ibytes));
-  if (cudaMalloc(&dXyz, n * 4 * sizeof(float)) != cudaSuccess) { cudaFree(dImg); jn_set_error("cudaMalloc failed"); return JN_ERR_CUDA; }
+  if (s->img_bytes < ibytes) {
+    cudaFree(s->dImg);
+    s->dImg = nullptr; s->img_bytes = 0;
+    JN_CUDA_CHECK(cudaMalloc(&s->dImg, ibytes));
+    s->img_bytes = ibytes;
+  }
+  if (!s->dXyz) JN_CUDA_CHECK(cudaMalloc(&s->dXyz, n * 4 * sizeof(float)));
+  uint8_t* dImg = s->dImg;
+  float* dXyz = s->dXyz;
   float* dRgb = dXyz + n * 3;
   cudaMemcpy(dImg, image, ibytes, cudaMemcpyHostToDevice);
   cudaMemcpy(s->dD, D, n * sizeof(float), cudaMemcpyHostToDevice);
@@ -462,8 +475,6 @@ extern "C" int jn_pointcloud_from_disparity(jn_scan* s, const float* D, const ui
   if (e == cudaSuccess) e = cudaMemcpy(rgb, dRgb, (size_t)total * sizeof(float), cudaMemcpyDeviceToHost);
   if (e == cudaSuccess) e = cudaMemcpy(ranges, s->dRanges, JN_SCAN_BINS * sizeof(double), cudaMemcpyDeviceToHost);
   if (e == cudaSuccess) e = cudaMemcpy(meta, s->dMeta, sizeof(jn_scan_meta), cudaMemcpyDeviceToHost);
-  cudaFree(dImg);
-  cudaFree(dXyz);
   if (e != cudaSuccess) { jn_set_error("jn_pointcloud_from_disparity: %s", cudaGetErrorString(e)); return JN_ERR_CUDA; }
   *n_points = total;
   return JN_OK;

@@ -101,6 +101,46 @@ def test_delaunay_random(jn, oracle, mode):
     e.close()
 
 
+@pytest.mark.parametrize("smem_max", [6, 40, 333, 2000])
+def test_delaunay_subtree_tiling(jn, oracle, smem_max):
+    """Point sets above the shared-memory table limit are cut into subtrees of the D&C tree that are
+    built in shared memory one after the other, the top merges run on the global table.  Force small
+    limits so that 1 to 9 levels end up on the global side; then one real case: 15 000 points."""
+    rng = np.random.default_rng(900 + smem_max)
+    e = jn.Elas(jn.parameters(jn.ROBOTICS))
+    try:
+        jn.lib().jn_debug_delaunay_limits(-1, smem_max)
+        for it in range(8):
+            n = int(rng.integers(smem_max + 1, 6000))
+            if it % 2:
+                pts = np.stack([rng.integers(1, 380, size=n) * 5 - rng.integers(0, 60, size=n) + 64,
+                                rng.integers(1, 240, size=n) * 5], 1)
+            else:
+                pts = rng.integers(1, 120, size=(n, 2)) * 5
+            pts = np.unique(pts, axis=0)
+            rng.shuffle(pts)
+            ref = oracle.triangulate(pts)
+            got = jn.debug_triangulate(e, pts, 1920, 1200)
+            assert got.shape == ref.shape and np.array_equal(got, ref), (smem_max, it, len(pts))
+    finally:
+        jn.lib().jn_debug_delaunay_limits(-1, -1)
+    e.close()
+
+
+def test_delaunay_15000_points(jn, oracle):
+    """Above 8 192 points: two subtrees in shared memory, the root merge on the global table."""
+    rng = np.random.default_rng(77)
+    u = rng.integers(1, 384, size=40000) * 5; v = rng.integers(1, 240, size=40000) * 5
+    pts = np.unique(np.stack([u, v], 1), axis=0)
+    rng.shuffle(pts)
+    pts = pts[:15000]
+    e = jn.Elas(jn.parameters(jn.ROBOTICS))
+    ref = oracle.triangulate(pts)
+    got = jn.debug_triangulate(e, pts, 1920, 1200)
+    assert got.shape == ref.shape and np.array_equal(got, ref)
+    e.close()
+
+
 def random_disparity_maps(rng, H, W, mode):
     yy, xx = np.mgrid[0:H, 0:W]
     surf = np.floor(10 + 0.08 * yy + 0.01 * xx)

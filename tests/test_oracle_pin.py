@@ -210,3 +210,16 @@ def test_raster_overlaps_stay_on_span_borders(port, synth):
                 assert o[2] == 0, (it, right, o)
                 multi += o[1]
     assert multi > 0          # overlaps do occur (on span borders): the atomics there are needed
+    # the largest size the plain-store path is used for (raster_kernel: W, H <= 2048), with few points
+    # = long, thin triangles and steep hull edges, where the float edge evaluation is least accurate
+    for it in range(6):
+        W = H = 2048
+        n = (12, 60, 400)[it % 3]
+        u, v = rng.integers(0, W, n), rng.integers(0, H, n)
+        if it >= 3:
+            u[: n // 3] = rng.integers(0, 4, n // 3) + (0, W // 2, W - 4)[it - 3]    # near-vertical edges
+        sup = np.unique(np.stack([u, v], 1), axis=0)
+        sup3 = np.concatenate([sup, np.zeros((len(sup), 1), np.int64)], 1).astype(np.int32)
+        tri = port.triangulate(np.ascontiguousarray(sup3[:, :2]))
+        o = study(W, H, sup3, tri, 0)
+        assert o[2] == 0, ("2048", it, o)
