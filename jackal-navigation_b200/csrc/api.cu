@@ -176,6 +176,8 @@ static int make_geo(const jn_elas_params& p, const int32_t dims[3], Geo* out) {
   if (g.plane_radius > 7) { jn_set_error("plane radius %d > 7 not supported", g.plane_radius); return JN_ERR_UNSUPPORTED; }
   for (int dd = 0; dd <= g.plane_radius; dd++)
     g.P[dd] = (int32_t)((-logf(p.gamma + expf(-dd * dd / two_sigma_squared)) + logf(p.gamma)) / p.beta);
+  // bits of the d_plane field of a plane map entry: values -(r+1) .. disp_max + r + 1, biased by r + 1
+  for (g.pm_dbits = 1; (1 << g.pm_dbits) < p.disp_max + 2 * (g.plane_radius + 1) + 1; g.pm_dbits++) {}
   for (int dd = 0; dd <= g.plane_radius; dd++)
     if (g.P[dd] < -2000 || g.P[dd] > 1900) { jn_set_error("prior table out of the packed-key range"); return JN_ERR_UNSUPPORTED; }
   *out = g;

@@ -9,7 +9,8 @@
 //   tri tables per side    3 neighbour handles + 3 vertex ids per row, 2*n rows
 //   tri_out / planes       compacted triangles (c1,c2,c3) + 6 plane floats
 //   gridmask  [2][gh*gw][GW] u32  per-cell disparity bit sets (createGrid)
-//   trimap    [2][H*W] i32  index of the last triangle covering each pixel
+//   trimap    [2][H*W] u32  plane map: last triangle covering each pixel + its plane prior there
+//                          ((tri + 1) << (pm_dbits + 1) | valid << pm_dbits | d_plane + radius + 1; 0 = none)
 //   D*        Hd*Wd f32    disparity maps / post-processing ping-pong buffers (Hd x Wd = H x W, or
 //                          H/2 x W/2 with subsampling; frame slots are Hd*Wd floats apart)
 #pragma once
@@ -33,7 +34,9 @@ extern long long g_jn_launches;   // kernels launched by this library (bench.py 
 // Right-image x coordinates (u - d) are stored with this bias so that they stay non-negative
 // (corner support points reach u - d = -d); the Delaunay predicates are translation invariant.
 constexpr int JN_XBIAS = 4096;
-constexpr int GRID_LIST = 16;    // entries of the compact per-cell candidate list
+constexpr int GRID_LIST = 16;    // u16 units per cell of the compact candidate form (= 32 bytes)
+constexpr int GRID_WORDS = 4;    // non-zero 32-bit words of a cell's disparity set kept in the compact form
+constexpr int GRID_OVERFLOW = 255;   // word count marker: decode the full bit set instead
 
 // Per-call geometry + parameters, passed to kernels by value.
 struct Geo {
@@ -49,7 +52,8 @@ struct Geo {
   int cap_t;            // triangle-table rows per side (2*cap_s)
   int plane_radius;     // elas.cpp:806
   int P[8];             // prior table entries 0..plane_radius (elas.cpp:802-805)
-  int grid_list_limit;  // cells with more candidates than this use the bit-set path (<= GRID_LIST)
+  int grid_list_limit;  // cells with more non-zero set words than this use the bit-set path (<= GRID_WORDS)
+  int pm_dbits;         // plane map entry: [tri index + 1 | plane valid | d_plane + plane_radius + 1 (pm_dbits bits)]
   int dl_sort_max, dl_smem_max;   // Delaunay: point-count limits of the shared-memory paths
   jn_elas_params p;
 };
@@ -92,7 +96,7 @@ struct Workspace {
   float*   planes[2];          // B * cap_t*6
   uint32_t* gridtmp[2];        // B * gh*gw*gwords
   uint32_t* gridmask[2];
-  uint16_t* gridlist[2];       // B * gh*gw*GRID_LIST  sorted candidate list per cell (0xFFFF padded)
+  uint16_t* gridlist[2];       // B * gh*gw*32 bytes  non-zero words of each cell's set (grid_words_kernel)
   int32_t* trimap[2];          // B * H*W
   float* Draw[2];              // B * H*W
   float* Dlr[2];

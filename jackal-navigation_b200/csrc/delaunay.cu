@@ -385,6 +385,12 @@ __device__ void leaf_case(const M& m, int v0, int n, int row, Ot& farleft, Ot& f
   }
 }
 
+__device__ __forceinline__ long long gtime() {
+  long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
 // Node (d,k) of the D&C tree over nu points: follow the bits of k from the root.  Returns false
 // if the node does not exist (an ancestor was already a leaf).
 __device__ __forceinline__ bool locate_node(int nu, int d, int k, int& lo, int& cnt, int& row) {
@@ -404,10 +410,14 @@ __device__ __forceinline__ bool locate_node(int nu, int d, int k, int& lo, int& 
 template <class M>
 __device__ void build_levels(const M& m, int nu, int dfrom, int dto, int L, int s, int row_off, int pos_off,
                              int* nodeL, int* nodeR) {
+  // Merges are serial pointer chasing with data-dependent control flow: threads of one warp that
+  // run different merges serialise each other.  Nodes are therefore dealt to warps first (node j of a
+  // round -> lane j / NW of warp j % NW): the top levels run one merge per warp.
   const int tid = threadIdx.x;
+  const int spread = (tid & 31) * NW + (tid >> 5);
   for (int d = dfrom; d >= dto; d--) {
     const int sub = 1 << (d - L);
-    for (int j = tid; j < sub; j += DT) {
+    for (int j = spread; j < sub; j += DT) {
       const int k = (s << (d - L)) + j;
       int lo, cnt, row;
       if (!locate_node(nu, d, k, lo, cnt, row)) continue;
@@ -426,6 +436,9 @@ __device__ void build_levels(const M& m, int nu, int dfrom, int dto, int L, int 
       nodeR[(1 << d) + k] = enc(fr);
     }
     __syncthreads();
+#ifdef JN_DL_LEVEL_TIMES
+    if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) printf("level %d (L %d s %d) done at %lld ns\n", d, L, s, gtime());
+#endif
   }
 }
 
@@ -542,11 +555,6 @@ __device__ int partition_levels(TI*& xl, TI*& yl, TI*& sp, TI* scan, TI* seglo, 
   return depth;
 }
 
-__device__ __forceinline__ long long gtime() {
-  long long t;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-  return t;
-}
 
 constexpr int OCC_EMPTY = 0x7f7f7f7f;   // cudaMemset(0x7f) pattern
 

@@ -6,27 +6,35 @@
 // one.  Here that is two passes, both in image order:
 //
 //   raster_kernel  one warp per triangle replays the reference scan converter
-//                  (same float operations, same truncations) and
-//                  records, per pixel, the HIGHEST triangle index covering it
-//                  (atomicMax = "the later triangle wins");
-//   dense_kernel   one thread per column walking 8 rows, a warp = a run of 32 pixels
-//                  of one row: plane prior of the recorded triangle, candidate set =
-//                  the cell's sorted candidate list (bit set for overflowing cells)
-//                  outside the plane range, then the plane range with the
-//                  integer prior P, 16-byte SAD per candidate on the integer
-//                  pipe (4 x VABSDIFF4.U8.ACC), strict '<' in the reference's
-//                  evaluation order (H7).  Left descriptors are read once, fully
-//                  coalesced (512 B per warp); the right descriptors of one
-//                  candidate disparity form one contiguous 512-byte span per
-//                  warp and neighbouring disparities overlap in L1.
+//                  (same float operations, same truncations).  Everything
+//                  that is per triangle is finished here: each covered pixel gets one
+//                  32-bit "plane map" entry
+//                      (triangle index + 1) << (dbits + 1) | plane valid << dbits | d_plane + r + 1
+//                  with d_plane = (int)(a*u + b*v + c) of this triangle at this pixel
+//                  (elas.cpp:722; clamped to [-(r+1), disp_max + r + 1], which keeps every
+//                  in-range candidate and the emptiness of the range).  atomicMax on the
+//                  entry = "the later triangle wins", and the winner's prior travels with it.
+//   dense_kernel   one thread per column walking DENSE_ROWS rows, a warp = a run of 32
+//                  pixels of one row.  Per pixel: one map entry (no triangle -> plane ->
+//                  d_plane chain of dependent loads), the own descriptor, then the
+//                  candidates: the cell's disparity set minus the plane range, then the
+//                  plane range with the integer prior P.  The set comes as its few non-zero
+//                  32-bit words (grid_words_kernel), loaded once per cell row into registers;
+//                  "minus the plane range" is a mask operation and the survivors are walked
+//                  with find-leading-one.  16-byte SAD per candidate on the integer pipe
+//                  (4 x VABSDIFF4.U8.ACC), folded into an order-preserving key so that the
+//                  reference's "first minimum in evaluation order" (H7) is a plain min.
+//                  A warp whose 32 columns cannot leave the image for any disparity and whose
+//                  plane ranges are all inside [0, disp_max] takes a path without any
+//                  per-candidate test (the 2R+1 plane-range descriptors are then consecutive:
+//                  one address, immediate offsets); other warps take the checked path.
+//                  Left descriptors are read once, fully coalesced (512 B per warp); the
+//                  right descriptors of one candidate disparity form one contiguous
+//                  512-byte span per warp and neighbouring disparities overlap in L1.
 //
 // Roofline: HBM (72 N bytes per frame: 2 passes x (2 descriptor images 32 N +
-// 4 N written)), second roofline the integer pipe (16 byte-absdiffs = 4
-// instructions per candidate).  Measured: DRAM 35 % busy, issue slots 81 % with
-// all 64 warps per SM resident at 32 registers: bound by instruction issue and
-// the dependent loads triangle id -> plane -> candidates of every row (variants
-// with more registers per thread, prefetches or streaming loads were all slower,
-// see DESIGN.md section 3).  Compiled with -fmad=false: d_plane and the edge
+// 4 N written)), second roofline the integer pipe / issue slots (16 byte-absdiffs = 4
+// instructions per candidate).  Compiled with -fmad=false: d_plane and the edge
 // equations must round exactly as the reference's SSE code does.
 #include "common.cuh"
 
@@ -34,11 +42,12 @@ namespace {
 
 __device__ __forceinline__ int f2u_lo32(float x) { return (int)(unsigned)(unsigned long long)__float2ll_rz(x); }
 
-// One column span [vlo, vhi) of triangle i.  Scan-converted triangles of a planar triangulation only
-// ever overlap in the first or last row of a span (neighbours evaluate the same edge function, so
-// spans abut exactly; what overlaps there is comes from edges meeting at a vertex and float
-// rounding): "the later triangle wins" (atomicMax) is needed for those two rows only, the rows in
-// between belong to this triangle alone and take a plain store.  Checked on the CPU restatement
+// One column span [vlo, vhi) of triangle i, plane d = a*u + b*v + c.
+// Scan-converted triangles of a planar triangulation only ever overlap in the first or last row of
+// a span (neighbours evaluate the same edge function, so spans abut exactly; what overlaps there
+// is comes from edges meeting at a vertex and float rounding): "the later triangle wins"
+// (atomicMax) is needed for those two rows only, the rows in between belong to this triangle alone
+// and take a plain store.  Checked on the CPU restatement
 // (tests/test_oracle_pin.py::test_raster_overlaps_stay_on_span_borders): 0 of 61 M covered pixels
 // over 3 000 random and 37 pipeline triangulations had a second cover strictly inside a span.
 // The argument needs the float edge evaluation a*u + b to be off by less than one row; its error grows
@@ -46,28 +55,42 @@ __device__ __forceinline__ int f2u_lo32(float x) { return (int)(unsigned)(unsign
 // enough for that (`exact`: W, H <= 2048, where |a*u|, |b| < 2^23 keep the rounding error of the sum
 // below 1/4 row -- checked at 2048 x 2048 with steep hull edges by the same test); larger images
 // take atomicMax on every row.
-__device__ __forceinline__ void write_span(int* __restrict__ map, int W, int u, int vlo, int vhi, int i, bool exact) {
+struct SpanPlane {
+  float au, b, c;        // a * (float)u, b, c of this image's plane
+  unsigned hi;           // (i + 1) << (dbits + 1) | valid << dbits
+  int dmin, dmax, bias;  // clamp range of d_plane, bias
+};
+__device__ __forceinline__ unsigned span_entry(const SpanPlane& p, int v) {
+  const int d = (int)(p.au + p.b * (float)v + p.c);            // elas.cpp:722, same operation order
+  return p.hi | (unsigned)(min(max(d, p.dmin), p.dmax) + p.bias);
+}
+__device__ __forceinline__ void write_span(unsigned* __restrict__ map, int W, int u, int vlo, int vhi,
+                                           const SpanPlane& p, bool exact) {
   if (vhi <= vlo) return;
   if (!exact) {
-    for (int v = vlo; v < vhi; v++) atomicMax(&map[v * W + u], i);
+    for (int v = vlo; v < vhi; v++) atomicMax(&map[v * W + u], span_entry(p, v));
     return;
   }
-  atomicMax(&map[vlo * W + u], i);
-  if (vhi - 1 > vlo) atomicMax(&map[(vhi - 1) * W + u], i);
-  for (int v = vlo + 1; v < vhi - 1; v++) map[v * W + u] = i;
+  atomicMax(&map[vlo * W + u], span_entry(p, vlo));
+  if (vhi - 1 > vlo) atomicMax(&map[(vhi - 1) * W + u], span_entry(p, vhi - 1));
+  for (int v = vlo + 1; v < vhi - 1; v++) map[v * W + u] = span_entry(p, v);
 }
 
 __global__ void raster_kernel(Geo g, Workspace ws) {
   const int side = blockIdx.y, frame = blockIdx.z;
-  const FrameInfo* info = ws.info + frame;
+  FrameInfo* info = ws.info + frame;
   if (info->status != JN_OK) return;
   const int nt = info->n_tri[side];
   const int W = g.W, H = g.H;
+  const int dbits = g.pm_dbits;
+  if (nt + 1 >= (1 << (31 - dbits))) return;      // does not fit the map entry: rejected by the guard kernel
   const int4* sup = reinterpret_cast<const int4*>(ws.sup) + (size_t)frame * g.cap_s;
   const int* tri = ws.tri[side] + (size_t)frame * g.cap_t * 3;
-  int* map = ws.trimap[side] + (size_t)frame * W * H;
+  const float* planes = ws.planes[side] + (size_t)frame * g.cap_t * 6;
+  unsigned* map = reinterpret_cast<unsigned*>(ws.trimap[side]) + (size_t)frame * W * H;
   const int lane = threadIdx.x & 31;
   const bool exact = W <= 2048 && H <= 2048;
+  const int po = side ? 3 : 0;              // this image's plane, the other image's slope
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   for (int i = warp; i < nt; i += nwarps) {
     float tu[3], tv[3];
@@ -77,6 +100,17 @@ __global__ void raster_kernel(Geo g, Workspace ws) {
       tu[k] = side ? (float)(s.x - s.z) : (float)s.x;
       tv[k] = (float)s.y;
     }
+    const float* pl = planes + 6 * i;
+    const float pa = pl[po], pd = pl[3 - po];
+    SpanPlane sp;
+    sp.b = pl[po + 1];
+    sp.c = pl[po + 2];
+    // (double)|x| < 0.7  <=>  |x| <= 0.7f  (0.7f is the largest float below 0.7), elas.cpp:872
+    const unsigned valid = (fabsf(pa) <= 0.7f && fabsf(pd) <= 0.7f) ? 1u : 0u;
+    sp.hi = ((unsigned)(i + 1) << (dbits + 1)) | (valid << dbits);
+    sp.bias = g.plane_radius + 1;
+    sp.dmin = -sp.bias;
+    sp.dmax = g.p.disp_max + sp.bias;
     // the reference's 3-element exchange sort on u (elas.cpp:847-854)
 #pragma unroll
     for (int j = 0; j < 3; j++)
@@ -96,178 +130,289 @@ __global__ void raster_kernel(Geo g, Workspace ws) {
       for (int u = max((int)Au, 0) + lane; u < min((int)Bu, W); u += 32) {
         int v1 = f2u_lo32(ACa * (float)u + ACb), v2 = f2u_lo32(ABa * (float)u + ABb);
         int vlo = max(min(v1, v2), 0), vhi = min(max(v1, v2), H);
-        write_span(map, W, u, vlo, vhi, i, exact);
+        sp.au = pa * (float)u;
+        write_span(map, W, u, vlo, vhi, sp, exact);
       }
     if ((int)Bu != (int)Cu)
       for (int u = max((int)Bu, 0) + lane; u < min((int)Cu, W); u += 32) {
         int v1 = f2u_lo32(ACa * (float)u + ACb), v2 = f2u_lo32(BCa * (float)u + BCb);
         int vlo = max(min(v1, v2), 0), vhi = min(max(v1, v2), H);
-        write_span(map, W, u, vlo, vhi, i, exact);
+        sp.au = pa * (float)u;
+        write_span(map, W, u, vlo, vhi, sp, exact);
       }
   }
 }
 
-// Tile shape: columns per CTA x rows per thread.  Swept on the B200 at the end of round 1
-// (64..256 x 4..16): all within 3 %, 256 x 8 best (wider tiles re-read less of the searched rows).
+// A frame whose triangle count does not fit the index field of a map entry is rejected (status
+// JN_ERR_UNSUPPORTED, outputs untouched) before the raster kernel runs.  At 1920x1200 the field
+// holds 2^21 triangles against at most 184 336.
+__global__ void raster_guard_kernel(Geo g, Workspace ws, int B) {
+  const int frame = blockIdx.x * blockDim.x + threadIdx.x;
+  if (frame >= B) return;
+  FrameInfo* info = ws.info + frame;
+  if (info->status != JN_OK) return;
+  const int lim = 1 << (31 - g.pm_dbits);
+  if (info->n_tri[0] + 1 >= lim || info->n_tri[1] + 1 >= lim) info->status = JN_ERR_UNSUPPORTED;
+}
+
+// Tile shape: columns per CTA x rows per thread.  The cell's candidate words are reloaded whenever the
+// thread crosses into the next grid row (10 rows = half a grid row of both presets).  Swept on the B200:
+// 64..512 columns x 10..40 rows are within 5 %, 128 x 10 is the best.
 #ifndef JN_DENSE_THREADS
-#define JN_DENSE_THREADS 256
+#define JN_DENSE_THREADS 128
 #endif
 #ifndef JN_DENSE_ROWS
-#define JN_DENSE_ROWS 8
+#define JN_DENSE_ROWS 10
 #endif
 constexpr int DENSE_THREADS = JN_DENSE_THREADS;
 constexpr int DENSE_ROWS = JN_DENSE_ROWS;         // image rows per thread (amortises the per-thread setup)
 constexpr unsigned KEY_NONE = 0xFFFFFFFFu;
+constexpr unsigned KEY_BIAS = 2048u << 13;        // keeps cost + prior non-negative
+constexpr unsigned KEY_PLANE = 1u << 12;          // class bit: plane-range candidates come second
 
-// One candidate: 16-byte SAD (+ prior), folded into a packed key
-//   (cost + 2048) << 13 | class << 12 | d      class 0 = grid candidate, 1 = plane range
+// Candidate keys:  (cost + 2048) << 13 | class << 12 | d      class 0 = grid candidate, 1 = plane range.
 // The reference keeps the FIRST minimum in its evaluation order (grid candidates outside the
 // plane range ascending, then the plane range ascending; strict '<', H7) = the smallest key.
-// Bf = descriptors of the searched image (frame base), rowoff = first pixel of the row:
-// 32-bit index arithmetic, one IMAD.WIDE per address.
+
+__device__ __forceinline__ unsigned shl_clamp(unsigned x, unsigned s) {   // shifts >= 32 give 0
+  unsigned r;
+  asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(s));
+  return r;
+}
+// bits of one set word (disparities wbase ..) that are outside [lo, hi]; an empty range removes nothing
+__device__ __forceinline__ unsigned outside_range(unsigned bits, int wbase, int lo, int hi) {
+  const unsigned ge_lo = shl_clamp(0xFFFFFFFFu, (unsigned)max(lo - wbase, 0));
+  const unsigned gt_hi = shl_clamp(0xFFFFFFFFu, (unsigned)max(hi + 1 - wbase, 0));
+  return bits & ~(ge_lo & ~gt_hi);
+}
+
+// base + idx * (+-16 bytes): one IMAD.WIDE
+template <int DIR>
+__device__ __forceinline__ const uint4* step16(const uint4* base, int idx) {
+  const uint4* r;
+  asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(r) : "r"(idx), "n"(16 * DIR), "l"(base));
+  return r;
+}
+// index of the highest set bit (FLO)
+__device__ __forceinline__ int top_bit(unsigned x) {
+  int r;
+  asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(x));
+  return r;
+}
+
+// checked evaluation of one candidate (image bounds): Bf = descriptors of the searched image
 __device__ __forceinline__ void eval_candidate(unsigned& best, const uint4& a, const uint4* __restrict__ Bf,
                                                unsigned rowoff, int u, int dir, int d, unsigned addend,
                                                unsigned wm4) {
   const int uw = u + dir * d;
-  if ((unsigned)(uw - 2) < wm4) {   // u_warp in [2, W-3] (a branch-free variant measured slower)
+  if ((unsigned)(uw - 2) < wm4) {   // u_warp in [2, W-3]
     const uint4 b = __ldg(Bf + (rowoff + (unsigned)uw));
     best = min(best, sad16(a, b, 0u) * 8192u + (addend + (unsigned)d));
   }
 }
-
-__device__ __forceinline__ void eval_word(unsigned& best, unsigned bits, int w, int lo, int hi, const uint4& a,
-                                          const uint4* __restrict__ Bf, unsigned rowoff, int u, int dir,
-                                          unsigned wm4) {
-  if (bits == 0u) return;
-  const int l = lo - 32 * w, h = hi - 32 * w;     // plane range relative to this word
-  if (h >= 0 && l <= 31) bits &= ~((0xFFFFFFFFu << max(l, 0)) & (0xFFFFFFFFu >> (31 - min(h, 31))));
+__device__ __forceinline__ void eval_bits_checked(unsigned& best, unsigned bits, int wbase, const uint4& a,
+                                                  const uint4* __restrict__ Bf, unsigned rowoff, int u, int dir,
+                                                  unsigned wm4) {
   while (bits) {
-    const int b = __ffs(bits) - 1;
-    bits &= bits - 1;
-    eval_candidate(best, a, Bf, rowoff, u, dir, 32 * w + b, 2048u << 13, wm4);
+    const int b = top_bit(bits);
+    bits ^= 1u << b;
+    eval_candidate(best, a, Bf, rowoff, u, dir, wbase + b, KEY_BIAS, wm4);
   }
 }
 
 // R = plane radius known at compile time (2: ROBOTICS, 3: MIDDLEBURY), 0 = run-time radius.
 // SUB = subsampling: only pixels with even u and v are matched (elas.cpp:877-896) and the result
 // goes to (u/2, v/2) of the W/2 x H/2 map (elas.cpp:693); everything else is unchanged.
-template <int R, bool SUB>
-__global__ void __launch_bounds__(DENSE_THREADS)
-dense_kernel(Geo g, Workspace ws) {
-  const int side = blockIdx.z & 1, frame = blockIdx.z >> 1;
-  if (ws.info[frame].status != JN_OK) return;
+// DIR = -1: left image searches the right one at u - d; +1: right image searches the left one at u + d
+// (compile-time so that candidate addresses are one IMAD.WIDE with an immediate).
+#ifndef JN_DENSE_MINB
+#define JN_DENSE_MINB (2048 / JN_DENSE_THREADS)   // 32 registers: all 64 warps of an SM resident
+#endif
+
+template <int R, bool SUB, int DIR>
+__device__ __forceinline__ void dense_body(const Geo& g, const Workspace& ws) {
+  constexpr int side = DIR > 0 ? 1 : 0;
+  const int frame = blockIdx.z >> 1;
   const int W = g.W, H = g.H;
   const int um = blockIdx.x * DENSE_THREADS + threadIdx.x;     // map column
+  const unsigned am = __ballot_sync(0xffffffffu, um < g.Wd);   // lanes that stay
   if (um >= g.Wd) return;
   const int u = SUB ? 2 * um : um;
   // frame-level bases once per thread; everything below is 32-bit offsets from them
   const size_t fpix = (size_t)frame * W * H;
   const uint4* __restrict__ Af = reinterpret_cast<const uint4*>(ws.desc[side] + fpix * 16);
   const uint4* __restrict__ Bf = reinterpret_cast<const uint4*>(ws.desc[side ^ 1] + fpix * 16);
-  const int* __restrict__ tmap = ws.trimap[side] + fpix;
+  const unsigned* __restrict__ pmap = reinterpret_cast<const unsigned*>(ws.trimap[side]) + fpix;
   float* __restrict__ outp = ws.Draw[side] + (SUB ? (size_t)frame * g.Wd * g.Hd : fpix);
-  const float* __restrict__ planes = ws.planes[side] + (size_t)frame * g.cap_t * 6;
   const uint32_t* __restrict__ masks = ws.gridmask[side] + (size_t)frame * g.gw * g.gh * g.gwords;
-  const uint16_t* __restrict__ lists = ws.gridlist[side] + (size_t)frame * g.gw * g.gh * GRID_LIST;
+  const uint4* __restrict__ cells =
+      reinterpret_cast<const uint4*>(ws.gridlist[side] + (size_t)frame * g.gw * g.gh * GRID_LIST);
+  // Per-column pointers.  The compiler rebuilds them from the kernel parameters in every row instead
+  // of keeping them in registers; that costs ~40 instructions per row but keeps the kernel at 32
+  // registers = 64 resident warps per SM, and the latency tolerance of full occupancy is worth more
+  // here than the instructions (pinned pointers, a two-row software pipeline with prefetch, and
+  // batched grid loads were all measured: 48-64 registers, 1.8-2.0 ms against 1.43 ms per 32 frames).
+  const unsigned* pm_u = pmap + u;
+  const uint4* A_u = Af + u;
+  const uint4* B_u = Bf + u;
+  float* o_u = outp + (SUB ? um : u);
   const unsigned gx = __umulhi((unsigned)u, g.gs_magic);
-  const int dir = side ? 1 : -1;
+  constexpr int dir = DIR;
+  const int dmax = g.p.disp_max;
   const unsigned wm4 = (unsigned)(W - 4);
   const bool u_ok = u >= 2 && u < W - 2;
-  const int po = side ? 3 : 0;              // this image's plane, the other image's slope
-  const int P0 = g.P[0], P1 = g.P[1], P2 = g.P[2], P3 = g.P[3];
-  const int v0 = blockIdx.y * DENSE_ROWS;
-#pragma unroll 1
-  for (int vm = v0; vm < min(v0 + DENSE_ROWS, g.Hd); vm++) {
-    const int v = SUB ? 2 * vm : vm;
-    const unsigned pix = (unsigned)(v * W + u);
-    const unsigned rowoff = (unsigned)(max(min(v, H - 3), 2) * W);
-    // independent loads first: triangle id, own descriptor
-    const int t = __ldg(tmap + pix);
-    const uint4 a = __ldg(Af + (rowoff + (unsigned)u));
-    float out = -10.f;
-    if (t >= 0 && u_ok && (int)texture16(a) >= g.p.match_texture) {
-      const float* pl = planes + (unsigned)t * 6u;
-      const float pa = __ldg(pl + po), pb = __ldg(pl + po + 1), pc = __ldg(pl + po + 2), pd = __ldg(pl + 3 - po);
+  const int r = R ? R : g.plane_radius;
+  const int dbits = g.pm_dbits;
+  const unsigned dmask = (1u << dbits) - 1u;
+  // no candidate of this column can leave the image: u_warp = u + dir*d in [2, W-3] for all d in [0, disp_max]
+  const bool col_free = side ? (u >= 2 && u + dmax <= W - 3) : (u - dmax >= 2 && u <= W - 3);
+  const bool warp_free = R != 0 && __all_sync(am, col_free);
+  // key addends of the plane range per |k|: (2048 + prior) << 13 | class bit, with and without the prior
+  const unsigned addv0 = ((unsigned)(2048 + g.P[0]) << 13) | KEY_PLANE;
+  const unsigned addv1 = ((unsigned)(2048 + g.P[1]) << 13) | KEY_PLANE;
+  const unsigned addv2 = ((unsigned)(2048 + g.P[2]) << 13) | KEY_PLANE;
+  const unsigned addv3 = ((unsigned)(2048 + g.P[3]) << 13) | KEY_PLANE;
+  const unsigned addn = KEY_BIAS | KEY_PLANE;
+  const int vm_end = min((int)(blockIdx.y + 1) * DENSE_ROWS, g.Hd);
+  int vm = blockIdx.y * DENSE_ROWS;
+  uint4 cw = make_uint4(0u, 0u, 0u, 0u), cm = make_uint4(0u, 0u, 0u, 0u);
+  unsigned ci = 0u, gy_cur = 0xFFFFFFFFu;
+  int nwords = 0;
+  auto load_row = [&](int vmr, unsigned& e, uint4& a) {
+    const int v = SUB ? 2 * vmr : vmr;
+    e = __ldg(pm_u + (unsigned)(v * W));
+    a = __ldg(A_u + (unsigned)(max(min(v, H - 3), 2) * W));
+  };
+  auto match_row = [&](const int vm, const unsigned e, const uint4& a) {
+      const int v = SUB ? 2 * vm : vm;
+      // rows inside one grid row share the cell: (re)load its candidate words when the grid row changes
       const unsigned gy = __umulhi((unsigned)v, g.gs_magic);
-      const int d_plane = (int)(pa * (float)u + pb * (float)v + pc);
-      const int r = R ? R : g.plane_radius;
-      const int lo = max(d_plane - r, 0), hi = min(d_plane + r, g.p.disp_max);
-      // (double)|x| < 0.7  <=>  |x| <= 0.7f  (0.7f is the largest float below 0.7)
-      const bool valid = fabsf(pa) <= 0.7f && fabsf(pd) <= 0.7f;
-      unsigned best = KEY_NONE;
-      // grid candidates outside the plane range: compact sorted list, 2 x 128-bit loads
-      const unsigned ci = gy * (unsigned)g.gw + gx;
-      const uint4* lst = reinterpret_cast<const uint4*>(lists + ci * GRID_LIST);
-      const uint4 l0 = __ldg(lst);
-      if (l0.x != 0xFFFEFFFEu) {
-        const uint4 l1 = __ldg(lst + 1);
-        const unsigned wv[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
-        // "d < lo || d > hi" as one unsigned compare; an empty plane range (hi < lo: the plane
-        // extrapolates outside [0, disp_max]) excludes nothing
-        const int lo2 = (hi < lo) ? 0x7fffffff : lo;
-        const unsigned span = (hi < lo) ? 0u : (unsigned)(hi - lo);
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-          if (wv[k] == 0xFFFFFFFFu) break;          // sorted: only padding follows
-          const int d0 = (int)(wv[k] & 0xFFFFu), d1 = (int)(wv[k] >> 16);
-          if ((unsigned)(d0 - lo2) > span) eval_candidate(best, a, Bf, rowoff, u, dir, d0, 2048u << 13, wm4);
-          // a 0xFFFF pad in the upper half fails the image-bounds test inside eval_candidate
-          if ((unsigned)(d1 - lo2) > span) eval_candidate(best, a, Bf, rowoff, u, dir, d1, 2048u << 13, wm4);
-        }
-      } else {
-        // overflowing cell: decode the bit set
-        const uint4* cell = reinterpret_cast<const uint4*>(masks + ci * (unsigned)g.gwords);
-        for (int q = 0; q < (g.gwords >> 2); q++) {
-          const uint4 m = __ldg(cell + q);
-          eval_word(best, m.x, 4 * q + 0, lo, hi, a, Bf, rowoff, u, dir, wm4);
-          eval_word(best, m.y, 4 * q + 1, lo, hi, a, Bf, rowoff, u, dir, wm4);
-          eval_word(best, m.z, 4 * q + 2, lo, hi, a, Bf, rowoff, u, dir, wm4);
-          eval_word(best, m.w, 4 * q + 3, lo, hi, a, Bf, rowoff, u, dir, wm4);
-        }
+      if (gy != gy_cur) {
+        gy_cur = gy;
+        ci = gy * (unsigned)g.gw + gx;
+        cw = __ldg(cells + 2u * ci);
+        cm = __ldg(cells + 2u * ci + 1u);
+        nwords = (int)cm.y;
       }
-      if (R) {
-        // key addend per |k|: (2048 + prior) << 13 | class bit
-        const unsigned a0 = ((unsigned)(2048 + (valid ? P0 : 0)) << 13) | (1u << 12);
-        const unsigned a1 = ((unsigned)(2048 + (valid ? P1 : 0)) << 13) | (1u << 12);
-        const unsigned a2 = ((unsigned)(2048 + (valid ? P2 : 0)) << 13) | (1u << 12);
-        const unsigned a3 = ((unsigned)(2048 + (valid ? P3 : 0)) << 13) | (1u << 12);
-        // The 2R+1 plane-range candidates are consecutive descriptors of the searched row: issue
-        // all loads first (clamped addresses, memory-level parallelism), then score and discard
-        // the ones outside [0, disp_max] or outside the image.
-        uint4 bb[2 * R + 1];
+      const unsigned rowoff = (unsigned)(max(min(v, H - 3), 2) * W);
+      const bool act = e != 0u && u_ok && (int)texture16(a) >= g.p.match_texture;
+      const int d_plane = (int)(e & dmask) - (r + 1);
+      const bool valid = (e >> dbits) & 1u;
+      const bool inside = d_plane - r >= 0 && d_plane + r <= dmax;       // whole plane range in [0, disp_max]
+      const bool quick = warp_free && __all_sync(am, inside || !act);
+      float out = -10.f;
+      if (act) {
+        unsigned best = KEY_NONE;
+        if (R != 0 && quick) {
+          // ---- no per-candidate test anywhere
+          const uint4* __restrict__ Brow = B_u + rowoff;                   // candidate d at Brow[dir * d]
+          const int lo = d_plane - R, hi = d_plane + R;
+          const uint4* __restrict__ Bp = step16<DIR>(Brow, d_plane);
+          unsigned bestg = KEY_NONE;
+          if (nwords != GRID_OVERFLOW) {
 #pragma unroll
-        for (int k = -R; k <= R; k++) {
-          const int uw = u + dir * (d_plane + k);
-          bb[k + R] = __ldg(Bf + (rowoff + (unsigned)min(max(uw, 2), (int)wm4 + 1)));
-        }
+            for (int j = 0; j < GRID_WORDS; j++) {
+              if (j < nwords) {
+                const int wbase = 32 * (int)((cm.x >> (8 * j)) & 0xFFu);
+                unsigned bits =
+                    outside_range(j == 0 ? cw.x : (j == 1 ? cw.y : (j == 2 ? cw.z : cw.w)), wbase, lo, hi);
+                if (bits) {
+                  const uint4* __restrict__ Bw = step16<DIR>(Brow, wbase);
+                  unsigned bw = KEY_NONE;
+                  do {
+                    const int b = top_bit(bits);
+                    bits ^= 1u << b;
+                    const uint4 c = __ldg(step16<DIR>(Bw, b));
+                    bw = min(bw, sad16(a, c, 0u) * 8192u + (unsigned)b);
+                  } while (bits);
+                  bestg = min(bestg, bw + (unsigned)wbase);
+                }
+              }
+            }
+          } else {
+            const uint32_t* cell = masks + ci * (unsigned)g.gwords;
+            for (int w = 0; w < g.gwords; w++) {
+              unsigned bits = outside_range(__ldg(cell + w), 32 * w, lo, hi);
+              while (bits) {
+                const int b = top_bit(bits);
+                bits ^= 1u << b;
+                const int d = 32 * w + b;
+                const uint4 c = __ldg(step16<DIR>(Brow, d));
+                bestg = min(bestg, sad16(a, c, 0u) * 8192u + (unsigned)d);
+              }
+            }
+          }
+          if (bestg != KEY_NONE) best = bestg + KEY_BIAS;
+          // the 2R+1 plane-range descriptors are consecutive: one address, immediate offsets, all loads
+          // issued before the first SAD (after the grid walk: 20 registers that must not be live during it)
+          uint4 bb[2 * R + 1];
 #pragma unroll
-        for (int k = -R; k <= R; k++) {
-          const int d = d_plane + k, uw = u + dir * d;
-          const int ak = k < 0 ? -k : k;
-          const unsigned add = ak == 0 ? a0 : (ak == 1 ? a1 : (ak == 2 ? a2 : a3));
-          const unsigned key = sad16(a, bb[k + R], 0u) * 8192u + (add + (unsigned)d);
-          const bool okc = (unsigned)d <= (unsigned)g.p.disp_max && (unsigned)(uw - 2) < wm4;
-          best = min(best, okc ? key : KEY_NONE);
+          for (int q = -R; q <= R; q++) bb[q + R] = __ldg(Bp + q);        // disparity d_plane + dir * q
+          const unsigned k0 = (valid ? addv0 : addn) + (unsigned)d_plane;
+          const unsigned k1 = (valid ? addv1 : addn) + (unsigned)d_plane;
+          const unsigned k2 = (valid ? addv2 : addn) + (unsigned)d_plane;
+          const unsigned k3 = (valid ? addv3 : addn) + (unsigned)d_plane;
+#pragma unroll
+          for (int q = -R; q <= R; q++) {
+            const int aq = q < 0 ? -q : q;
+            const unsigned kq = (aq == 0 ? k0 : (aq == 1 ? k1 : (aq == 2 ? k2 : k3))) + (unsigned)(dir * q);
+            best = min(best, sad16(a, bb[q + R], 0u) * 8192u + kq);
+          }
+        } else {
+          // ---- checked path: image borders, plane ranges clipped by [0, disp_max], run-time radius
+          const int lo = max(d_plane - r, 0), hi = min(d_plane + r, dmax);
+          if (nwords != GRID_OVERFLOW) {
+#pragma unroll
+            for (int j = 0; j < GRID_WORDS; j++) {
+              if (j < nwords) {
+                const int wbase = 32 * (int)((cm.x >> (8 * j)) & 0xFFu);
+                const unsigned bits =
+                    outside_range(j == 0 ? cw.x : (j == 1 ? cw.y : (j == 2 ? cw.z : cw.w)), wbase, lo, hi);
+                eval_bits_checked(best, bits, wbase, a, Bf, rowoff, u, dir, wm4);
+              }
+            }
+          } else {
+            const uint32_t* cell = masks + ci * (unsigned)g.gwords;
+            for (int w = 0; w < g.gwords; w++)
+              eval_bits_checked(best, outside_range(__ldg(cell + w), 32 * w, lo, hi), 32 * w, a, Bf, rowoff, u,
+                                dir, wm4);
+          }
+          for (int d = lo; d <= hi; d++) {
+            const int ad = abs(d - d_plane);
+            const unsigned add = valid ? (((unsigned)(2048 + g.P[ad]) << 13) | KEY_PLANE) : addn;
+            eval_candidate(best, a, Bf, rowoff, u, dir, d, add, wm4);
+          }
         }
-      } else {
-        for (int d = lo; d <= hi; d++)
-          eval_candidate(best, a, Bf, rowoff, u, dir, d,
-                         ((unsigned)(2048 + (valid ? g.P[abs(d - d_plane)] : 0)) << 13) | (1u << 12), wm4);
+        out = (best != KEY_NONE) ? (float)(best & 0xFFFu) : -1.f;
       }
-      out = (best != KEY_NONE) ? (float)(best & 0xFFFu) : -1.f;
-    }
-    outp[SUB ? (unsigned)(vm * g.Wd + um) : pix] = out;
+      o_u[(unsigned)(vm * g.Wd)] = out;
+  };
+#pragma unroll 1
+  for (; vm < vm_end; vm++) {
+    unsigned e;
+    uint4 a;
+    load_row(vm, e, a);
+    match_row(vm, e, a);
   }
+}
+
+template <int R, bool SUB>
+__global__ void __launch_bounds__(DENSE_THREADS, JN_DENSE_MINB)
+dense_kernel(Geo g, Workspace ws) {
+  if (ws.info[blockIdx.z >> 1].status != JN_OK) return;
+  if (blockIdx.z & 1) dense_body<R, SUB, 1>(g, ws);
+  else dense_body<R, SUB, -1>(g, ws);
 }
 
 }  // namespace
 
 void launch_raster(const Geo& g, int B, Workspace& ws, cudaStream_t s) {
   size_t mbytes = (size_t)B * g.W * g.H * sizeof(int32_t);
-  cudaMemsetAsync(ws.trimap[0], 0xff, mbytes, s);   // -1 = no triangle
-  cudaMemsetAsync(ws.trimap[1], 0xff, mbytes, s);
+  cudaMemsetAsync(ws.trimap[0], 0, mbytes, s);   // 0 = no triangle
+  cudaMemsetAsync(ws.trimap[1], 0, mbytes, s);
+  raster_guard_kernel<<<(B + 127) / 128, 128, 0, s>>>(g, ws, B);
   raster_kernel<<<dim3(64, 2, B), 256, 0, s>>>(g, ws);
-  g_jn_launches += 1;
+  g_jn_launches += 2;
 }
 
 void launch_dense_match(const Geo& g, int B, Workspace& ws, cudaStream_t s) {

@@ -114,45 +114,40 @@ __global__ void grid_dilate_kernel(Geo g, Workspace ws) {
   }
 }
 
-// Compact form of a cell's bit set for the dense matcher: up to GRID_LIST disparities as sorted
-// u16 (= the reference's candidate list, elas.cpp:642-652), padded with 0xFFFF.  A cell with
-// more candidates stores the overflow marker 0xFFFE everywhere and is decoded from the bit set.
-__global__ void grid_list_kernel(Geo g, Workspace ws) {
+// Compact form of a cell's bit set for the dense matcher: the (at most GRID_WORDS) non-zero 32-bit
+// words of the set.  32 bytes per cell: uint4 {bits of word 0..3}, uint4 {word indices packed as
+// bytes, count, 0, 0}.  A support point marks d-1..d+1 and the dilation ORs 9 cells, so the set is a
+// few short runs: one or two words for a cell on one surface, more across a depth edge.  A cell with
+// more non-zero words (or word indices that do not fit a byte) stores count = GRID_OVERFLOW and is
+// decoded from the full bit set.
+__global__ void grid_words_kernel(Geo g, Workspace ws) {
   const int side = blockIdx.y, frame = blockIdx.z;
   const int cells = g.gw * g.gh, gwords = g.gwords;
   const uint32_t* mask = ws.gridmask[side] + (size_t)frame * cells * gwords;
-  uint16_t* list = ws.gridlist[side] + (size_t)frame * cells * GRID_LIST;
+  uint4* out = reinterpret_cast<uint4*>(ws.gridlist[side] + (size_t)frame * cells * GRID_LIST);
   for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < cells; c += gridDim.x * blockDim.x) {
-    uint16_t e[GRID_LIST];
+    uint32_t bits[GRID_WORDS] = {0u, 0u, 0u, 0u};
+    uint32_t wpack = 0;
     int n = 0;
     for (int w = 0; w < gwords; w++) {
-      uint32_t bits = mask[(size_t)c * gwords + w];
-      while (bits) {
-        int b = __ffs(bits) - 1;
-        bits &= bits - 1;
-        if (n < GRID_LIST) e[n] = (uint16_t)(32 * w + b);
+      const uint32_t b = mask[(size_t)c * gwords + w];
+      if (b) {
+        if (n < GRID_WORDS) { bits[n] = b; wpack |= (uint32_t)(w & 0xFF) << (8 * n); }
         n++;
       }
     }
-    uint4* out = reinterpret_cast<uint4*>(list + (size_t)c * GRID_LIST);
-    uint32_t words[GRID_LIST / 2];
-#pragma unroll
-    for (int k = 0; k < GRID_LIST / 2; k++) {
-      uint32_t lo = (n > g.grid_list_limit) ? 0xFFFEu : (2 * k < n ? e[2 * k] : 0xFFFFu);
-      uint32_t hi = (n > g.grid_list_limit) ? 0xFFFEu : (2 * k + 1 < n ? e[2 * k + 1] : 0xFFFFu);
-      words[k] = lo | (hi << 16);
-    }
-    out[0] = make_uint4(words[0], words[1], words[2], words[3]);
-    out[1] = make_uint4(words[4], words[5], words[6], words[7]);
+    if (n > g.grid_list_limit || gwords > 256) n = GRID_OVERFLOW;
+    out[2 * c] = make_uint4(bits[0], bits[1], bits[2], bits[3]);
+    out[2 * c + 1] = make_uint4(wpack, (uint32_t)n, 0u, 0u);
   }
 }
 
 }  // namespace
 
-// test hook: cells with more than `limit` candidates take the bit-set path of the dense matcher
-static int g_list_limit = GRID_LIST;
+// test hook: cells with more than `limit` non-zero set words take the bit-set path of the dense matcher
+static int g_list_limit = GRID_WORDS;
 extern "C" void jn_debug_grid_list_limit(int limit) {
-  g_list_limit = (limit < 0 || limit > GRID_LIST) ? GRID_LIST : limit;
+  g_list_limit = (limit < 0 || limit > GRID_WORDS) ? GRID_WORDS : limit;
 }
 
 void launch_planes_grid(const Geo& g_in, int B, Workspace& ws, cudaStream_t s) {
@@ -165,6 +160,6 @@ void launch_planes_grid(const Geo& g_in, int B, Workspace& ws, cudaStream_t s) {
   grid_scatter_kernel<<<dim3(16, 2, B), 256, 0, s>>>(g, ws);
   int cw = g.gw * g.gh * g.gwords;
   grid_dilate_kernel<<<dim3((cw + 255) / 256, 2, B), 256, 0, s>>>(g, ws);
-  grid_list_kernel<<<dim3((g.gw * g.gh + 127) / 128, 2, B), 128, 0, s>>>(g, ws);
+  grid_words_kernel<<<dim3((g.gw * g.gh + 127) / 128, 2, B), 128, 0, s>>>(g, ws);
   g_jn_launches += 4;
 }
