@@ -2,24 +2,31 @@
 """bench.py -- stereo-to-obstacle-scan throughput at 1920x1200, disp_max 255 (BASELINE.json).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+                    [--scene random_dot|textured] [--config robotics|c5] [--total-frames T]
 
 A "step" is one pass of the whole hot path (Elas::process pipeline + fused
-convert/reproject/transform/scan) over one batch of B synthetic random-dot stereo pairs.
+convert/reproject/transform/scan) over one batch of B synthetic stereo pairs.
 One process per GPU; for N > 1 launch under torchrun (the frames are independent, so ranks
-share nothing: weak scaling, no collective on the data path -- NCCL is used for the barrier
-and the max-over-ranks of the device time only).
+share nothing: no collective on the data path -- NCCL is used for the barrier and the
+max-over-ranks of the device time only).  Default: B distinct pairs per GPU per step ("weak").
+--total-frames T: BASELINE config C4 as written -- T pairs (seeds 1000..1000+T-1) split contiguously
+over the ranks, every rank works through its shard in batches of B ("strong").
 
 Prints ONE JSON line (rank 0):
   value            frames/s over all ranks, inputs resident in HBM, CUDA-event timed
-  e2e              same metric through the C ABI with HOST (pinned) buffers: H2D of the
-                   image pairs and D2H of the scan + u8 disparity map inside the timed region
+  e2e              same metric through the C ABI's host-buffer entry point
+                   (jn_stereo_scan_submit / _wait): pinned host image pairs in, scans + u8 maps out,
+                   H2D and D2H inside the timed region
   roofline         dense-matching kernel: algorithmic bytes (72*W*H per frame) / its event time
+  parity           frames of the timed batch re-computed by the CPU checker: maps and scans equal
+  scenes, c5       the same measurement on the second scene family / BASELINE config C5 (short runs)
   cpu_baseline     the reference's own ELAS (oracle/_ref, built from /root/reference) on the
                    host cores, one frame per core in separate processes
 --impl reference times that CPU arm alone, same metric / config.
 """
 import argparse
 import ctypes as C
+import hashlib
 import importlib
 import json
 import multiprocessing as mp
@@ -34,6 +41,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 METRIC = "elas_stereo_to_obstacle_scan_throughput"
 UNIT = "frames/s"
+SEED0 = 1000          # seeds 1000 + global frame index
 
 
 def parse():
@@ -46,21 +54,72 @@ def parse():
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1200)
     ap.add_argument("--disp-max", type=int, default=255)
+    ap.add_argument("--scene", default="random_dot", choices=["random_dot", "textured"])
+    ap.add_argument("--config", default="robotics", choices=["robotics", "c5"])
+    ap.add_argument("--total-frames", type=int, default=0, help="strong scaling: total pairs split over the ranks")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the second scene / C5 / latency sections")
     ap.add_argument("--cpu-frames-per-core", type=int, default=2)
     return ap.parse_args()
 
 
-def workload_name(a):
-    return "%dx%d disp_max=%d ROBOTICS(postprocess_only_left) ELAS + C920xK3 reproject/XR,XT/90-bin scan" % (
-        a.width, a.height, a.disp_max)
+def config_kw(cfg):
+    # C5: all five post-processing stages on both images (left/right check, small segments, gap
+    # interpolation, adaptive mean, median)
+    return {"filter_median": 1, "postprocess_only_left": 0} if cfg == "c5" else {}
+
+
+def workload_name(a, scene=None, cfg=None):
+    cfg = cfg or a.config
+    return "%dx%d disp_max=%d %s ELAS + C920xK3 reproject/XR,XT/90-bin scan, %s scene" % (
+        a.width, a.height, a.disp_max,
+        "ROBOTICS(postprocess_only_left)" if cfg == "robotics" else "ROBOTICS+median, both images post-processed (C5)",
+        scene or a.scene)
+
+
+def q_matrix(W, H):
+    import numpy as np
+    import scan_lib
+    fx = scan_lib.fixtures()
+    return np.array(fx["Q"]["1920x1200_Kx3"] if (W, H) == (1920, 1200) else fx["Q"]["640x480"])
+
+
+def digest(a):
+    return hashlib.sha1(memoryview(a).cast("B")).hexdigest()
+
+
+# ----------------------------------------------------------------------------- inputs
+def _gen_worker(args):
+    scene, W, H, dm, seed = args
+    synth = importlib.import_module("jackal-navigation_b200.synth")
+    I1, I2, _ = synth.SCENES[scene](W, H, dm, seed)
+    return I1, I2
+
+
+def make_frames(scene, W, H, dm, seeds, procs):
+    """Distinct synthetic pairs, generated in parallel (1.3-1.7 s per 1920x1200 pair on one core)."""
+    import numpy as np
+    L = np.empty((len(seeds), H, W), np.uint8)
+    R = np.empty((len(seeds), H, W), np.uint8)
+    jobs = [(scene, W, H, dm, s) for s in seeds]
+    if procs > 1 and len(seeds) > 2:
+        with mp.get_context("fork").Pool(min(procs, len(seeds))) as pool:
+            for i, (a, b) in enumerate(pool.imap(_gen_worker, jobs, chunksize=1)):
+                L[i], R[i] = a, b
+    else:
+        for i, j in enumerate(jobs):
+            L[i], R[i] = _gen_worker(j)
+    return L, R
 
 
 # ----------------------------------------------------------------------------- CPU arm
+_GATE = {}
+
+
 def _cpu_worker(args):
-    """One process = one core: runs the reference ELAS on `n` frames (Triangle keeps mutable
-    file-scope state, so cores are separate processes)."""
-    W, H, dm, seeds, kind = args
+    """One process = one core: runs the reference ELAS + the scan restatement on its frames (Triangle
+    keeps mutable file-scope state, so cores are separate processes)."""
+    W, H, dm, seeds, kind, scene, cfg = args
     import numpy as np
     import oracle_lib as ol
     synth = importlib.import_module("jackal-navigation_b200.synth")
@@ -70,27 +129,38 @@ def _cpu_worker(args):
         o.lib.ref_set_deterministic_heap(0)   # timing run: default allocator
     sp = scan_lib.ScanPort()
     fx = scan_lib.fixtures()
-    Q = np.array(fx["Q"]["1920x1200_Kx3"] if (W, H) == (1920, 1200) else fx["Q"]["640x480"])
+    Q = q_matrix(W, H)
     XR = np.array(fx["calib"]["XR"]); XT = np.array(fx["calib"]["XT"])
-    frames = [synth.synth_pair(W, H, dm, s)[:2] for s in seeds]
-    gate = np.zeros((H, W, 2), np.uint8)
-    gate[..., 0] = 3
-    gate[..., 1] = 255   # init-time cache is not part of the per-frame path
-    p = ol.robotics(dm)
+    frames = [synth.SCENES[scene](W, H, dm, s)[:2] for s in seeds]
+    gate = _GATE.get((W, H))       # computed once by the parent (cacheDisparityValues is init-time work)
+    if gate is None:
+        gate = sp.gate(Q, XR, XT, W, H)
+    p = ol.robotics(dm, **config_kw(cfg))
+    out = []
     t0 = time.perf_counter()
     for I1, I2 in frames:
         D1, _ = o.process(p, I1, I2)
-        sp.scan(Q, XR, XT, gate, sp.convert_u8(D1))
-    return time.perf_counter() - t0, len(frames)
+        r, m = sp.scan(Q, XR, XT, gate, sp.convert_u8(D1))
+        out.append((digest(D1), r.copy(), int(m.n_points)))
+    return time.perf_counter() - t0, len(frames), out
 
 
-def cpu_arm(a, frames_per_core, cores=None):
+def cpu_arm(a, frames_per_core, cores=None, scene=None, cfg=None):
+    import numpy as np
     import oracle_lib as ol
+    import scan_lib
     kind = "ref" if os.path.exists(ol.REF_SO) else "port"
     cores = cores or (os.cpu_count() or 1)
+    scene = scene or a.scene
+    cfg = cfg or a.config
+    W, H, dm = a.width, a.height, a.disp_max
+    if (W, H) not in _GATE:
+        fx = scan_lib.fixtures()
+        _GATE[(W, H)] = scan_lib.ScanPort().gate(q_matrix(W, H), np.array(fx["calib"]["XR"]), np.array(fx["calib"]["XT"]), W, H)
     # single frame on one core
-    t1, n1 = _cpu_worker((a.width, a.height, a.disp_max, [5000], kind))
-    jobs = [(a.width, a.height, a.disp_max, [6000 + c * 16 + k for k in range(frames_per_core)], kind)
+    t1, n1, _ = _cpu_worker((W, H, dm, [5000], kind, scene, cfg))
+    # frame k of the pool = seed SEED0 + k: the frames the GPU arm's rank 0 processes
+    jobs = [(W, H, dm, [SEED0 + c * frames_per_core + k for k in range(frames_per_core)], kind, scene, cfg)
             for c in range(cores)]
     t0 = time.perf_counter()
     with mp.get_context("fork").Pool(cores) as pool:
@@ -98,12 +168,13 @@ def cpu_arm(a, frames_per_core, cores=None):
     wall = time.perf_counter() - t0
     busy = max(r[0] for r in res)
     nfr = sum(r[1] for r in res)
+    frames = [x for r in res for x in r[2]]      # in seed order
     return {"value": nfr / busy, "unit": UNIT, "cores": cores,
             "kind": "reference" if kind == "ref" else "port",
             "sample": "%d frames (%d per core, one process per core), max worker time %.2fs, pool wall %.2fs; "
-                      "single frame on one core: %.3fs (%.3f frames/s); ELAS built -O3 -msse3" % (
-                          nfr, frames_per_core, busy, wall, t1 / n1, n1 / t1),
-            "single_core_frames_per_s": n1 / t1}
+                      "single frame on one core: %.3fs (%.3f frames/s); ELAS built -O3 -msse3, scan with the "
+                      "real gate cache" % (nfr, frames_per_core, busy, wall, t1 / n1, n1 / t1),
+            "single_core_frames_per_s": n1 / t1}, frames
 
 
 def run_reference(a):
@@ -113,13 +184,14 @@ def run_reference(a):
     vals = []
     cb = None
     for i in range(a.warmup + a.steps):
-        cb = cpu_arm(a, 1)
+        cb, _ = cpu_arm(a, 1)
         if i >= a.warmup:
             vals.append(cb["value"])
     v = sum(vals) / len(vals)
     cb["value"] = v
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
-            "warmup": a.warmup, "ms_per_step": 1000.0 * cb["cores"] / v, "higher_is_better": True, "scaling": "weak",
+            "warmup": a.warmup, "ms_per_step": 1000.0 * cb["cores"] / v, "higher_is_better": True,
+            "scaling": "strong" if a.total_frames else "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": workload_name(a), "step": "one frame per host core (%d cores)" % cb["cores"]},
             "cpu_baseline": cb,
@@ -164,178 +236,260 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+STAGES = ["descriptor", "support", "delaunay", "planes_grid", "raster", "dense_match", "post"]
+
+
+class Runner:
+    """One (scene, config) workload on this rank's GPU: device-resident and end-to-end timing."""
+
+    def __init__(self, a, jn, torch, dist, rank, world, local, scene, cfg, B, L, R):
+        import numpy as np
+        self.a, self.jn, self.torch, self.dist = a, jn, torch, dist
+        self.rank, self.world, self.local = rank, world, local
+        self.B, self.W, self.H = B, a.width, a.height
+        self.dims = (a.width, a.height, a.width)
+        self.dev = torch.device("cuda", local)
+        n = self.W * self.H
+        self.L, self.R = L, R
+        self.hL = torch.from_numpy(L).pin_memory()
+        self.hR = torch.from_numpy(R).pin_memory()
+        nb = L.shape[0] // B                                   # batches held by this rank
+        self.nb = nb
+        self.dL = self.hL.to(self.dev); self.dR = self.hR.to(self.dev)
+        self.dD1 = torch.empty((B, self.H, self.W), dtype=torch.float32, device=self.dev)
+        self.dStatus = torch.zeros(B, dtype=torch.int32, device=self.dev)
+        self.dRanges = torch.empty((B, 90), dtype=torch.float64, device=self.dev)
+        self.dMeta = torch.empty((B, 5), dtype=torch.float64, device=self.dev)   # jn_scan_meta = 40 bytes
+        self.dU8 = torch.empty((B, self.H, self.W), dtype=torch.uint8, device=self.dev)
+        # host result buffers of the end-to-end path, one set per in-flight submission
+        self.hRanges = [torch.empty((B, 90), dtype=torch.float64).pin_memory() for _ in range(2)]
+        self.hMeta = [torch.empty((B, 5), dtype=torch.float64).pin_memory() for _ in range(2)]
+        self.hStatus = [torch.zeros(B, dtype=torch.int32).pin_memory() for _ in range(2)]
+        self.hU8 = [torch.empty((B, self.H, self.W), dtype=torch.uint8).pin_memory() for _ in range(2)]
+        self.elas = jn.Elas(jn.parameters(jn.ROBOTICS, disp_max=a.disp_max, **config_kw(cfg)), device=local)
+        import scan_lib
+        cal = jn.Calibration(scan_lib.CALIB_YML)
+        cal.set_q_matrix(q_matrix(self.W, self.H))
+        self.scan = jn.ObstacleScan(cal, self.W, self.H, device=local)
+        self.stream = torch.cuda.Stream(device=self.dev)
+        self.h2d = 2 * B * n
+        self.d2h = B * (n + 90 * 8 + 40 + 4)
+        self.it = 0
+
+    def step_resident(self, k=0):
+        B, n = self.B, self.W * self.H
+        self.elas.process_batch(self.dL.data_ptr() + k * B * n, self.dR.data_ptr() + k * B * n, self.dD1.data_ptr(), 0,
+                                self.dStatus.data_ptr(), self.dims, B, self.stream.cuda_stream)
+        self.scan.from_disparity_batch(B, self.dD1.data_ptr(), self.dRanges.data_ptr(), self.dMeta.data_ptr(),
+                                       self.dU8.data_ptr(), self.stream.cuda_stream)
+
+    def step_e2e(self, k=0):
+        """The call a user of the C ABI makes: host image pairs in, scans + u8 maps out (asynchronous;
+        up to two submissions overlap inside the library)."""
+        B, n = self.B, self.W * self.H
+        j = self.it & 1
+        self.it += 1
+        self.elas.stereo_scan_submit(self.scan, B, self.hL.data_ptr() + k * B * n, self.hR.data_ptr() + k * B * n,
+                                     self.dims, self.hRanges[j].data_ptr(), self.hMeta[j].data_ptr(),
+                                     self.hStatus[j].data_ptr(), self.hU8[j].data_ptr())
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def timed(self, fn, steps, finish=None):
+        torch = self.torch
+        self.barrier()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(self.stream):
+            e0.record(self.stream)
+            for s in range(steps):
+                fn(s % self.nb)
+            if finish:
+                finish()                    # host-blocking: every queued batch has landed
+            e1.record(self.stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if self.world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=self.dev)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    def measure(self, steps, warmup):
+        jn, torch = self.jn, self.torch
+        with torch.cuda.stream(self.stream):
+            for s in range(max(warmup, 3)):
+                self.step_resident(s % self.nb)
+        torch.cuda.synchronize()
+        l0 = jn.launch_count()
+        ms = self.timed(self.step_resident, steps)
+        launches = jn.launch_count() - l0
+        for s in range(3):
+            self.step_e2e(s % self.nb)
+        self.elas.stereo_scan_wait()
+        ms_e2e = self.timed(self.step_e2e, steps, self.elas.stereo_scan_wait)
+        return ms, ms_e2e, launches
+
+    def stage_times(self, reps=3):
+        import numpy as np
+        lib = self.jn.lib()
+        lib.jn_elas_profile.argtypes = [C.c_void_p, C.c_int]
+        lib.jn_elas_profile_read.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+        lib.jn_elas_profile(self.elas._h, 1)
+        acc = np.zeros(7, np.float64)
+        for _ in range(reps):
+            with self.torch.cuda.stream(self.stream):
+                self.step_resident(0)
+            self.torch.cuda.synchronize()
+            buf = (C.c_float * 7)()
+            lib.jn_elas_profile_read(self.elas._h, buf)
+            acc += np.array(list(buf))
+        lib.jn_elas_profile(self.elas._h, 0)
+        return acc / reps
+
+    def close(self):
+        self.elas.close(); self.scan.close()
+
+
+def latency_section(a, jn, torch, local, L, R):
+    """The reference-shaped single-frame call (Elas::process, host buffers, synchronous)."""
+    import numpy as np
+    W, H, dm = a.width, a.height, a.disp_max
+    dims = (W, H, W)
+    out = {}
+
+    def med(fn, reps=12):
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter(); fn(); ts.append(time.perf_counter() - t0)
+        ts = sorted(ts[2:])
+        return 1000.0 * ts[len(ts) // 2]
+
+    p = jn.parameters(jn.ROBOTICS, disp_max=dm)
+    e1 = jn.Elas(p, device=local)
+    D1 = np.zeros((H, W), np.float32); D2 = np.zeros((H, W), np.float32)
+    out["pageable_D1_D2_ms"] = med(lambda: e1.process(L[0], R[0], D1, D2, dims))
+    out["pageable_D1_only_ms"] = med(lambda: e1.process(L[0], R[0], D1, None, dims))
+    pL = torch.from_numpy(L[0].copy()).pin_memory().numpy(); pR = torch.from_numpy(R[0].copy()).pin_memory().numpy()
+    pD1 = torch.zeros((H, W)).pin_memory().numpy()
+    out["pinned_D1_only_ms"] = med(lambda: e1.process(pL, pR, pD1, None, dims))
+    e1.close()
+
+    def fresh():
+        e = jn.Elas(p, device=local)                # point_cloud.cpp:416-419: a new Elas for every frame
+        e.process(pL, pR, pD1, None, dims)
+        e.close()
+    out["fresh_elas_per_frame_pinned_D1_only_ms"] = med(fresh)
+    # per-stage device times of a one-frame batch
+    lib = jn.lib()
+    e2 = jn.Elas(p, device=local)
+    dL = torch.from_numpy(L[:1]).cuda(local); dR = torch.from_numpy(R[:1]).cuda(local)
+    dD = torch.empty((1, H, W), dtype=torch.float32, device=dL.device); dS = torch.zeros(1, dtype=torch.int32, device=dL.device)
+    lib.jn_elas_profile(e2._h, 1)
+    acc = np.zeros(7)
+    for i in range(5):
+        e2.process_batch(dL.data_ptr(), dR.data_ptr(), dD.data_ptr(), 0, dS.data_ptr(), dims, 1, 0)
+        torch.cuda.synchronize()
+        buf = (C.c_float * 7)(); lib.jn_elas_profile_read(e2._h, buf)
+        if i >= 2:
+            acc += np.array(list(buf))
+    lib.jn_elas_profile(e2._h, 0)
+    e2.close()
+    out["stage_ms_one_frame"] = {k: float(v / 3) for k, v in zip(STAGES, acc)}
+    return out
+
+
 def run_ours(a):
     import numpy as np
     import torch
     import torch.distributed as dist
     jn = importlib.import_module("jackal-navigation_b200")
-    synth = importlib.import_module("jackal-navigation_b200.synth")
-    import scan_lib
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; this benchmark has no CPU path (use --impl reference)")
+    W, H, dm, B = a.width, a.height, a.disp_max, a.batch
+    n = W * H
+    procs = max(1, (os.cpu_count() or 1) // world)
+
+    # ---- synthetic inputs (worker processes are forked before CUDA / NCCL are initialised)
+    if a.total_frames:                       # C4: contiguous shard of seeds SEED0 .. SEED0 + T - 1
+        sharding = importlib.import_module("jackal-navigation_b200.sharding")
+        lo, hi = sharding.frame_shard(a.total_frames, rank, world)
+        cnt = ((hi - lo) // B) * B
+        if cnt == 0:
+            raise SystemExit("--total-frames: every rank needs at least one batch of %d frames" % B)
+        seeds = [SEED0 + lo + i for i in range(cnt)]
+    else:                                    # B distinct pairs per rank
+        seeds = [SEED0 + rank * B + i for i in range(B)]
+    t_gen = time.perf_counter()
+    L, R = make_frames(a.scene, W, H, dm, seeds, procs)
+    t_gen = time.perf_counter() - t_gen
+    extras_on = not a.no_extras and not a.total_frames
+    other_scene = "textured" if a.scene == "random_dot" else "random_dot"
+    nd2 = min(16, B)
+    if extras_on:
+        l2, r2 = make_frames(other_scene, W, H, dm, [SEED0 + rank * B + i for i in range(nd2)], procs)
+        L2o = np.concatenate([l2] * (B // nd2)); R2o = np.concatenate([r2] * (B // nd2))
+
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    W, H, dm, B = a.width, a.height, a.disp_max, a.batch
-    n = W * H
 
-    # ---- synthetic inputs: B distinct pairs per rank (seeds as SURVEY C4: 1000 + global index)
-    L, R = synth.synth_batch(W, H, dm, [1000 + rank * B + i for i in range(B)])
-    hL = torch.from_numpy(L).pin_memory()
-    hR = torch.from_numpy(R).pin_memory()
-    dL = hL.to(dev); dR = hR.to(dev)
-    dD1 = torch.empty((B, H, W), dtype=torch.float32, device=dev)
-    dStatus = torch.zeros(B, dtype=torch.int32, device=dev)
-    dRanges = torch.empty((B, 90), dtype=torch.float64, device=dev)
-    dMeta = torch.empty((B, 5), dtype=torch.float64, device=dev)   # jn_scan_meta = 40 bytes
-    dU8 = torch.empty((B, H, W), dtype=torch.uint8, device=dev)
-    hRanges = torch.empty((B, 90), dtype=torch.float64).pin_memory()
-    hMeta = torch.empty((B, 5), dtype=torch.float64).pin_memory()
-    hU8 = torch.empty((B, H, W), dtype=torch.uint8).pin_memory()
-
-    elas = jn.Elas(jn.parameters(jn.ROBOTICS, disp_max=dm), device=local)
-    cal = jn.Calibration(scan_lib.CALIB_YML)
-    fx = scan_lib.fixtures()
-    cal.set_q_matrix(fx["Q"]["1920x1200_Kx3"] if (W, H) == (1920, 1200) else fx["Q"]["640x480"])
-    scan = jn.ObstacleScan(cal, W, H, device=local)
-    dims = (W, H, W)
-    stream = torch.cuda.Stream(device=dev)
-    copy_stream = torch.cuda.Stream(device=dev)
-
-    def step_resident():
-        elas.process_batch(dL.data_ptr(), dR.data_ptr(), dD1.data_ptr(), 0, dStatus.data_ptr(), dims, B,
-                           stream.cuda_stream)
-        scan.from_disparity_batch(B, dD1.data_ptr(), dRanges.data_ptr(), dMeta.data_ptr(), dU8.data_ptr(),
-                                  stream.cuda_stream)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps, finish=None):
-        barrier()
-        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-        with torch.cuda.stream(stream):
-            e0.record(stream)
-            for _ in range(steps):
-                fn()
-            if finish:
-                finish()
-            e1.record(stream)
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
-
-    # ---- device-resident throughput
-    with torch.cuda.stream(stream):
-        for _ in range(max(a.warmup, 3)):
-            step_resident()
-    torch.cuda.synchronize()
+    run = Runner(a, jn, torch, dist, rank, world, local, a.scene, a.config, B, L, R)
     sampler = ClockSampler(local) if rank == 0 else None
-    l0 = jn.launch_count()
-    ms = timed(step_resident, a.steps)
-    launches = jn.launch_count() - l0
-    status = dStatus.cpu().numpy()
-    value = world * B * a.steps / (ms / 1000.0)
+    steps = a.steps if not a.total_frames else run.nb      # strong scaling: one pass over the shard
+    ms, ms_e2e, launches = run.measure(steps, a.warmup)
+    clocks = sampler.stop() if sampler else None            # sampled over both timed regions
+    frames_done = B * steps if not a.total_frames else a.total_frames // world // B * B
+    value = world * frames_done / (ms / 1000.0)
+    e2e = world * frames_done / (ms_e2e / 1000.0)
+    stages = run.stage_times()
 
-    # ---- end to end with host buffers: H2D + pipeline + D2H every step (double-buffered inputs)
-    dL2 = [torch.empty_like(dL) for _ in range(2)]
-    dR2 = [torch.empty_like(dR) for _ in range(2)]
-    ev_in = [torch.cuda.Event() for _ in range(2)]
-    ev_done = [torch.cuda.Event() for _ in range(2)]
-    it = [0]
-
-    out_stream = torch.cuda.Stream(device=dev)
-    dRanges2 = [torch.empty_like(dRanges) for _ in range(2)]
-    dMeta2 = [torch.empty_like(dMeta) for _ in range(2)]
-    dU82 = [torch.empty_like(dU8) for _ in range(2)]
-    ev_out = [torch.cuda.Event() for _ in range(2)]
-    ev_copied = [torch.cuda.Event() for _ in range(2)]
-
-    def step_e2e():
-        # three streams: H2D of step i+1, compute of step i and D2H of step i-1 overlap;
-        # inputs and outputs are double-buffered on the device
-        k = it[0] & 1
-        it[0] += 1
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(ev_done[k])        # input buffer k free again
-            dL2[k].copy_(hL, non_blocking=True)
-            dR2[k].copy_(hR, non_blocking=True)
-            ev_in[k].record(copy_stream)
-        stream.wait_event(ev_in[k])
-        stream.wait_event(ev_copied[k])               # output buffer k already read back
-        elas.process_batch(dL2[k].data_ptr(), dR2[k].data_ptr(), dD1.data_ptr(), 0, dStatus.data_ptr(), dims, B,
-                           stream.cuda_stream)
-        scan.from_disparity_batch(B, dD1.data_ptr(), dRanges2[k].data_ptr(), dMeta2[k].data_ptr(),
-                                  dU82[k].data_ptr(), stream.cuda_stream)
-        ev_done[k].record(stream)
-        ev_out[k].record(stream)
-        with torch.cuda.stream(out_stream):
-            out_stream.wait_event(ev_out[k])
-            hRanges.copy_(dRanges2[k], non_blocking=True)
-            hMeta.copy_(dMeta2[k], non_blocking=True)
-            hU8.copy_(dU82[k], non_blocking=True)
-            ev_copied[k].record(out_stream)
-
-    def drain_e2e():
-        for k in range(2):                            # the timed region ends when the last D2H has landed
-            stream.wait_event(ev_copied[k])
-
-    for k in range(2):
-        ev_done[k].record(stream)
-        ev_copied[k].record(stream)
-    with torch.cuda.stream(stream):
-        for _ in range(3):
-            step_e2e()
-        drain_e2e()
+    # ---- outputs of the first batch for the parity check (device-resident path and host path)
+    with torch.cuda.stream(run.stream):
+        run.step_resident(0)
     torch.cuda.synchronize()
-    ms_e2e = timed(step_e2e, a.steps, drain_e2e)
-    clocks = sampler.stop() if sampler else None     # sampled over both timed regions
-    e2e = world * B * a.steps / (ms_e2e / 1000.0)
-    h2d = 2 * B * n
-    d2h = B * (n + 90 * 8 + 40)
+    status = run.dStatus.cpu().numpy()
+    nchk = min(B, (os.cpu_count() or 1) * a.cpu_frames_per_core, 32)
+    gD1 = run.dD1[:nchk].cpu().numpy()
+    gRanges = run.dRanges[:nchk].cpu().numpy()
+    run.it = 0
+    run.step_e2e(0); run.elas.stereo_scan_wait()
+    hostRanges = run.hRanges[0][:nchk].numpy().copy()
 
-    # ---- per-stage device times (CUDA events on the launching stream) for the roofline
-    lib = jn.lib()
-    lib.jn_elas_profile.argtypes = [C.c_void_p, C.c_int]
-    lib.jn_elas_profile_read.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
-    lib.jn_elas_profile(elas._h, 1)
-    stages = np.zeros(7, np.float64)
-    reps = 3
-    for _ in range(reps):
-        with torch.cuda.stream(stream):
-            step_resident()
-        torch.cuda.synchronize()
-        buf = (C.c_float * 7)()
-        lib.jn_elas_profile_read(elas._h, buf)
-        stages += np.array(list(buf))
-    stages /= reps
-    lib.jn_elas_profile(elas._h, 0)
-    names = ["descriptor", "support", "delaunay", "planes_grid", "raster", "dense_match", "post"]
+    extras = {}
+    if rank == 0 and extras_on:
+        extras["single_frame"] = latency_section(a, jn, torch, local, L, R)
+    run.close()
 
-    # ---- latency of the reference-facing single-frame call (host numpy buffers, synchronous)
-    lat = None
-    if rank == 0:
-        e1 = jn.Elas(jn.parameters(jn.ROBOTICS, disp_max=dm), device=local)
-        D1h = np.zeros((H, W), np.float32); D2h = np.zeros((H, W), np.float32)
-        ts = []
-        for i in range(8):
-            t0 = time.perf_counter()
-            e1.process(L[0], R[0], D1h, D2h, dims)
-            ts.append(time.perf_counter() - t0)
-        lat = 1000.0 * sorted(ts[2:])[len(ts[2:]) // 2]
-        e1.close()
+    # ---- second scene family and BASELINE config C5: short runs of the same measurement
+    if extras_on:
+        others = [("scenes", other_scene, a.config)]
+        if a.config != "c5":
+            others.append(("c5", a.scene, "c5"))
+        for key, scene, cfg in others:
+            nd = nd2 if scene != a.scene else B      # distinct pairs (the rest of the batch repeats them)
+            La, Ra = (L, R) if scene == a.scene else (L2o, R2o)
+            r2 = Runner(a, jn, torch, dist, rank, world, local, scene, cfg, B, La, Ra)
+            m2, m2e, _ = r2.measure(10, 3)
+            st2 = r2.stage_times(2)
+            ent = {"workload": workload_name(a, scene, cfg), "value": world * B * 10 / (m2 / 1000.0), "unit": UNIT,
+                   "e2e": world * B * 10 / (m2e / 1000.0), "ms_per_step": m2 / 10, "steps": 10,
+                   "distinct_pairs_per_gpu": nd,
+                   "stage_ms_per_step": {k: float(v) for k, v in zip(STAGES, st2)},
+                   "frames_ok": int((r2.dStatus.cpu().numpy() == 0).sum())}
+            if cfg == "c5":
+                ent["algorithmic_bytes_per_frame"] = 251 * n
+            extras[key] = ent if key == "c5" else {scene: ent}
+            r2.close()
+            del r2
 
     if world > 1:
         dist.barrier()
@@ -353,38 +507,56 @@ def run_ours(a):
     dense_ms = float(stages[5])
     achieved = 72.0 * n * B / (dense_ms / 1000.0) / 1e9
     traffic = None
+    tsrc = None
     tpath = os.path.join(ROOT, "profiles", "dense_traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("dram_bytes_per_frame") * B   # per launch of B frames, like `achieved`
+            tj = json.load(open(tpath))
+            traffic = tj.get("dram_bytes_per_frame") * B   # per launch of B frames, like `achieved`
+            tsrc = tj.get("source")
         except Exception:
             traffic = None
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
-        "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u8", "data": "synthetic",
-        "config": {"workload": workload_name(a), "frames_per_step_per_gpu": B, "pairs": "distinct random-dot pairs, "
-                   "seeds 1000+", "l2": "inputs per step (%.0f MB) and working set (>4 GB) exceed the 126 MB L2" % (
-                       2 * B * n / 1e6), "parallelism": "frames sharded across %d GPU(s), no data-path collective" % world},
-        "mpix_per_s": value * n / 1e6, "ms_per_frame": ms / a.steps / B,
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": max(a.warmup, 3),
+        "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "strong" if a.total_frames else "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": workload_name(a), "frames_per_step_per_gpu": B,
+                   "pairs": "%d distinct pairs per GPU, seeds %d+ (generated in %.0f s)" % (len(seeds), SEED0, t_gen),
+                   "l2": "inputs per step (%.0f MB) and working set (>4 GB) exceed the 126 MB L2" % (2 * B * n / 1e6),
+                   "parallelism": "frames sharded across %d GPU(s), no data-path collective" % world,
+                   "total_frames": a.total_frames or None},
+        "mpix_per_s": value * n / 1e6, "ms_per_frame": ms / steps / B,
         "frames_ok": int((status == 0).sum()), "frames_few_support": int((status == 1).sum()),
-        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": ms_e2e / a.steps,
-                "what": "pinned host image pairs -> H2D -> jn_elas_process_batch + jn_scan_from_disparity_batch -> "
-                        "D2H of 90-bin scans, scan meta and the u8 disparity maps (copies on their own streams, "
-                        "double-buffered, all inside the timed region)"},
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": run.h2d, "d2h_bytes_per_step": run.d2h,
+                "ms_per_step": ms_e2e / steps,
+                "what": "C ABI jn_stereo_scan_submit/_wait: pinned host image pairs -> H2D -> ELAS + scan kernels -> "
+                        "D2H of 90-bin scans, scan meta, status and the u8 disparity maps into pinned host buffers; "
+                        "copies on the library's own streams, double-buffered, all inside the timed region"},
         "gpu_launches": int(launches),
-        "single_frame_latency_ms": lat,   # jn_elas_process: H2D + pipeline + D2H of both maps, one frame
-        "stage_ms_per_step": {k: float(v) for k, v in zip(names, stages)},
+        "stage_ms_per_step": {k: float(v) for k, v in zip(STAGES, stages)},
         "roofline": {"bound": "hbm", "kernel": "dense_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic,
+                     "frac": achieved / peak, "traffic": traffic, "traffic_source": tsrc,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
                      "algorithmic_bytes_per_launch": 72.0 * n * B, "kernel_ms": dense_ms},
         "clocks": clocks,
     }
+    line.update(extras)
+    if "single_frame" in extras:
+        line["single_frame_latency_ms"] = extras["single_frame"]["pinned_D1_only_ms"]
     if not a.no_cpu_baseline and world == 1:
         try:
-            line["cpu_baseline"] = cpu_arm(a, a.cpu_frames_per_core)
+            cb, frames = cpu_arm(a, a.cpu_frames_per_core)
+            line["cpu_baseline"] = cb
+            # ---- parity inside the bench: the CPU checker re-computes frames of the timed batch
+            k = min(nchk, len(frames))
+            d1_ok = sum(digest(np.ascontiguousarray(gD1[i])) == frames[i][0] for i in range(k))
+            occ_ok = sum(bool(np.array_equal(gRanges[i] < 1e9 - 1, frames[i][1] < 1e9 - 1)) for i in range(k))
+            rng_err = max(float(np.abs(np.where(gRanges[i] < 1e9 - 1, gRanges[i] - frames[i][1], 0)).max()) for i in range(k))
+            host_ok = sum(bool(np.array_equal(hostRanges[i], gRanges[i])) for i in range(k))
+            line["parity"] = {"frames_checked": k, "checker": cb["kind"], "d1_maps_bit_equal": d1_ok,
+                              "scan_bins_equal": occ_ok, "scan_range_max_abs_err_m": rng_err,
+                              "host_path_equals_device_path": host_ok,
+                              "ok": bool(d1_ok == k and occ_ok == k and rng_err <= 1e-9 and host_ok == k)}
         except Exception as ex:   # the checker is optional for the GPU arm
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(ex)}
     print(json.dumps(line))

@@ -11,6 +11,9 @@
  *   jn_elas_process          <- Elas::process               src/elas/elas.h:162, elas.cpp:32-151
  *   jn_elas_process_batch    <- the per-frame call site     src/obstacle_avoidance/point_cloud.cpp:416-419
  *                               (one call per left frame), batched over independent frames
+ *   jn_stereo_scan_batch_host / _submit / _wait
+ *                            <- imageCallbackLeft's compute  point_cloud.cpp:448 (generateDisparityMap)
+ *                               + :465 (publishPointCloud -> publishObstacleScan), host buffers in and out
  *   jn_calib_load_yaml       <- cv::FileStorage reads       point_cloud.cpp:530-538
  *   jn_calib_set_q           <- stereoRectify -> Q          point_cloud.cpp:543-544
  *   jn_scan_cache_gate       <- cacheDisparityValues        point_cloud.cpp:104-147
@@ -81,15 +84,30 @@ typedef struct jn_elas jn_elas;
 void jn_elas_params_default(jn_elas_params* p, int setting);
 
 /* device: CUDA ordinal.  The workspace is sized lazily at the first process call (and grown when a
- * larger batch arrives).  NULL on error (no usable device: there is no CPU path). */
+ * larger batch arrives).  NULL on error (no usable device: there is no CPU path).
+ *
+ * Creating and destroying handles is cheap: jn_elas_destroy parks the device resources (workspace,
+ * streams, staging) in a small per-process cache and the next jn_elas_create on the same device
+ * takes them over, so the reference's pattern of a fresh `Elas` per frame (point_cloud.cpp:416-419)
+ * does not allocate.  jn_cache_clear releases what the cache holds.
+ *
+ * Concurrency: a handle owns ONE workspace -- one call in flight at a time.  The asynchronous entry
+ * points order their work on the stream they are given; do not issue calls on the same handle from
+ * two host threads or on two unordered streams.  Use one handle per thread / per stream. */
 jn_elas* jn_elas_create(const jn_elas_params* p, int device);
 void     jn_elas_destroy(jn_elas* e);
+void     jn_cache_clear(void);
 const char* jn_last_error(void);
+
+/* Page-locked host memory (cudaHostAlloc) for callers that do not link the CUDA runtime: image and
+ * map buffers allocated here make every host<->device copy of this library a DMA transfer. */
+void* jn_host_alloc(size_t bytes);
+void  jn_host_free(void* p);
 
 /* Host pointers, synchronous.  dims = {width, height, bytes_per_line}.
  * D1, D2: caller-allocated width*height floats, or (width/2)*(height/2) with
- * params.subsampling (elas.h:159-161).  Returns JN_OK, JN_FEW_SUPPORT (outputs
- * untouched) or an error. */
+ * params.subsampling (elas.h:159-161).  D2 may be NULL (right map not wanted, as in
+ * point_cloud.cpp:419-421).  Returns JN_OK, JN_FEW_SUPPORT (outputs untouched) or an error. */
 int jn_elas_process(jn_elas* e, const uint8_t* I1, const uint8_t* I2,
                     float* D1, float* D2, const int32_t dims[3]);
 
@@ -153,6 +171,27 @@ int jn_scan_from_disparity_batch(jn_scan* s, int n, const float* D,
 /* Host-pointer, synchronous single frame. */
 int jn_scan_from_disparity(jn_scan* s, const float* D, double ranges[JN_SCAN_BINS],
                            jn_scan_meta* meta, uint8_t* dmap_u8);
+
+/* Host buffers in, obstacle scans out: n independent frames through ELAS and the scan in one call
+ * (I1/I2: n frames of height rows x bytes_per_line; ranges: n*90 doubles; meta: n; optional per frame:
+ * status (n int32), dmap_u8 (n*W*H, the convertTo(CV_8U) map), D1 (n*W*H floats)).  Host<->device
+ * copies run on their own streams with double-buffered device staging.
+ *   jn_stereo_scan_batch_host  synchronous.
+ *   jn_stereo_scan_submit      queues the batch and returns; up to two submissions overlap (copy-in
+ *                              of the next with the kernels of the current and copy-out of the
+ *                              previous one).  All buffers belong to the library until
+ *   jn_stereo_scan_wait        returns (every submitted batch has landed).
+ * Pinned buffers (jn_host_alloc) are needed for the overlap; pageable ones work, serialised.
+ * A frame with <3 support points reports JN_FEW_SUPPORT in status and returns an all-zero map and an
+ * empty scan: what the reference's caller, which zeroes its maps before the call
+ * (point_cloud.cpp:413-414), is left with. */
+int jn_stereo_scan_batch_host(jn_elas* e, jn_scan* s, int n, const uint8_t* I1, const uint8_t* I2,
+                              const int32_t dims[3], float* D1, int32_t* status, double* ranges,
+                              jn_scan_meta* meta, uint8_t* dmap_u8);
+int jn_stereo_scan_submit(jn_elas* e, jn_scan* s, int n, const uint8_t* I1, const uint8_t* I2,
+                          const int32_t dims[3], float* D1, int32_t* status, double* ranges,
+                          jn_scan_meta* meta, uint8_t* dmap_u8);
+int jn_stereo_scan_wait(jn_elas* e);
 
 /* -g path: every pixel with u8 disparity >= 2 -> robot-frame XYZ (double,
  * 3 per point, pixel order columns-outer like the reference) and the scan

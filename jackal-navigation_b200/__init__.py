@@ -115,6 +115,14 @@ def lib():
         l.jn_scan_compact.argtypes = [_P, _P]
         l.jn_pointcloud_from_disparity.argtypes = [_P, _P, _P, C.c_int32, C.c_int32, _P, _P, C.POINTER(C.c_int32), _P,
                                                    C.POINTER(ScanMeta)]
+        l.jn_cache_clear.restype = None
+        l.jn_host_alloc.restype = _P
+        l.jn_host_alloc.argtypes = [C.c_size_t]
+        l.jn_host_free.argtypes = [_P]
+        _ss = [_P, _P, C.c_int, _P, _P, C.POINTER(C.c_int32), _P, _P, _P, _P, _P]
+        l.jn_stereo_scan_batch_host.argtypes = _ss
+        l.jn_stereo_scan_submit.argtypes = _ss
+        l.jn_stereo_scan_wait.argtypes = [_P]
         l.jn_rectify_create.restype = _P
         l.jn_rectify_create.argtypes = [_P, _P, C.c_int32, C.c_int32, C.c_int32]
         l.jn_rectify_destroy.argtypes = [_P]
@@ -169,17 +177,34 @@ class Elas:
         Returns JN_OK or JN_FEW_SUPPORT; in the latter case D1/D2 are untouched and the
         reference's message is printed (elas.cpp:66-71).  With param.subsampling the maps are
         (H/2) x (W/2) (elas.h:160-162)."""
-        for a, dt in ((I1, np.uint8), (I2, np.uint8), (D1, np.float32), (D2, np.float32)):
+        for a, dt in ((I1, np.uint8), (I2, np.uint8), (D1, np.float32)) + (((D2, np.float32),) if D2 is not None else ()):
             if not (isinstance(a, np.ndarray) and a.dtype == dt and a.flags["C_CONTIGUOUS"]):
                 raise TypeError("process expects C-contiguous numpy arrays (uint8 images, float32 maps)")
         d = (C.c_int32 * 3)(*[int(x) for x in dims])
+        if d[2] < d[0] or d[0] <= 0 or d[1] <= 0:
+            raise ValueError("dims = (width, height, bytes_per_line) with bytes_per_line >= width")
+        if I1.size < d[2] * d[1] or I2.size < d[2] * d[1]:
+            raise ValueError("images must hold height * bytes_per_line = %d bytes" % (d[2] * d[1]))
         Hd, Wd = self.map_shape(d[0], d[1])
-        if D1.size < Hd * Wd or D2.size < Hd * Wd:
+        if D1.size < Hd * Wd or (D2 is not None and D2.size < Hd * Wd):
             raise ValueError("disparity maps must hold %d x %d floats" % (Hd, Wd))
         rc = _check(lib().jn_elas_process(self._h, _ptr(I1), _ptr(I2), _ptr(D1), _ptr(D2), d), "jn_elas_process")
         if rc == JN_FEW_SUPPORT:
             print("ERROR: Need at least 3 support points!")
         return rc
+
+    def stereo_scan_submit(self, scan, n, I1, I2, dims, ranges, meta, status=0, dmap_u8=0, D1=0, wait=False):
+        """n frames from HOST buffers (addresses as ints, ideally pinned: jn_host_alloc or
+        torch.Tensor.pin_memory) through ELAS + obstacle scan; results land in host buffers.
+        Asynchronous unless wait=True; see jn_stereo_scan_submit in include/jn_elas.h."""
+        d = (C.c_int32 * 3)(*[int(x) for x in dims])
+        f = lib().jn_stereo_scan_batch_host if wait else lib().jn_stereo_scan_submit
+        P = lambda x: _P(int(x)) if x else None
+        return _check(f(self._h, scan._h, int(n), P(I1), P(I2), d, P(D1), P(status), P(ranges), P(meta), P(dmap_u8)),
+                      "jn_stereo_scan_submit")
+
+    def stereo_scan_wait(self):
+        return _check(lib().jn_stereo_scan_wait(self._h), "jn_stereo_scan_wait")
 
     def map_shape(self, W, H):
         """(rows, cols) of the disparity maps for W x H images."""

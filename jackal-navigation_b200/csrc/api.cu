@@ -11,10 +11,11 @@
 #include <string.h>
 #include <string>
 #include <vector>
+#include <atomic>
 #include "common.cuh"
 #include "../../include/jn_elas_debug.h"
 
-long long g_jn_launches = 0;
+std::atomic<long long> g_jn_launches{0};
 static thread_local char g_err[512] = "";
 
 void jn_set_error(const char* fmt, ...) {
@@ -34,31 +35,54 @@ void post_copy(const Geo& g, int B, Workspace& ws, const float* in, float* out, 
 
 constexpr int JN_MAX_PARTS = 4;
 
-struct jn_elas {
-  jn_elas_params p;
+// Device-side resources of one handle: workspace arenas, streams, events, single-frame staging.
+// They outlive the handle: jn_elas_destroy parks them in a small per-process cache and the next
+// jn_elas_create on the same device picks them up again, so the reference's call pattern -- a fresh
+// `Elas elas(param)` for every frame (point_cloud.cpp:416-419) -- costs no cudaMalloc / cudaFree.
+struct DevRes {
   int device;
   Geo g;            // geometry the workspace was built for
   Workspace ws;     // frame slots for a whole batch (part 0 in split mode)
   void* arena;      // one cudaMalloc
+  size_t arena_bytes;
   Workspace wsx[JN_MAX_PARTS - 1];   // frame slots of parts 1.. (split mode)
   void* arenax[JN_MAX_PARTS - 1];
-  int parts;        // > 1: run a batch as `parts` sub-batches on as many streams so that the
-                    // latency-bound kernels (Delaunay, support filter: a CTA or two per frame) of
-                    // one part overlap the bandwidth-bound kernels of the others
+  size_t arenax_bytes[JN_MAX_PARTS - 1];
   cudaStream_t aux[JN_MAX_PARTS - 1];
   cudaEvent_t ev_fork, ev_join[JN_MAX_PARTS - 1];
-  // single-frame staging for the host-pointer entry point
+  // single-frame staging for the host-pointer entry point + its stream
   uint8_t* dI[2];
   float* dD[2];
   int32_t* dStatus;
   size_t stage_pixels, stage_bytes;
+  cudaStream_t own;
+  // host-batch pipeline (jn_stereo_scan_batch_host): double-buffered chunks
+  uint8_t* cI[2][2];      // [buffer][image]
+  float* cD[2];
+  int32_t* cStatus[2];
+  double* cRanges[2];
+  jn_scan_meta* cMeta[2];
+  uint8_t* cU8[2];
+  size_t chunk_frames, chunk_img_bytes, chunk_pixels;
+  unsigned long long submits;   // buffer parity of the next submission
+  cudaStream_t s_in, s_out;
+  cudaEvent_t ev_in[2], ev_done[2], ev_out[2], ev_copied[2];
   // optional per-stage timing with CUDA events on the launching stream
-  int profile;
   cudaEvent_t ev[JN_PROFILE_STAGES + 1];
 };
 
+struct jn_elas {
+  jn_elas_params p;
+  int device;
+  int parts;        // > 1: run a batch as `parts` sub-batches on as many streams so that the
+                    // latency-bound kernels (Delaunay, support filter: a CTA or two per frame) of
+                    // one part overlap the bandwidth-bound kernels of the others
+  int profile;
+  DevRes* r;
+};
+
 extern "C" const char* jn_last_error(void) { return g_err; }
-extern "C" long long jn_launch_count(void) { return g_jn_launches; }
+extern "C" long long jn_launch_count(void) { return g_jn_launches.load(); }
 
 extern "C" void jn_elas_params_default(jn_elas_params* p, int setting) {
   // Elas::parameters(setting), elas.h:87-144
@@ -99,6 +123,73 @@ extern "C" void jn_elas_params_default(jn_elas_params* p, int setting) {
   }
 }
 
+// ---- device-resource cache ------------------------------------------------------------------
+#include <mutex>
+static std::mutex g_cache_mu;
+static std::vector<DevRes*> g_cache;           // parked resources, most recently used last
+constexpr size_t JN_CACHE_MAX = 4;
+
+static void devres_free(DevRes* r) {
+  if (!r) return;
+  cudaSetDevice(r->device);
+  if (r->arena) cudaFree(r->arena);
+  for (int k = 0; k < JN_MAX_PARTS - 1; k++) {
+    if (r->arenax[k]) cudaFree(r->arenax[k]);
+    if (r->aux[k]) { cudaStreamDestroy(r->aux[k]); cudaEventDestroy(r->ev_join[k]); }
+  }
+  for (int k = 0; k < 2; k++) {
+    cudaFree(r->dI[k]); cudaFree(r->dD[k]);
+    cudaFree(r->cI[k][0]); cudaFree(r->cI[k][1]); cudaFree(r->cD[k]); cudaFree(r->cStatus[k]);
+    cudaFree(r->cRanges[k]); cudaFree(r->cMeta[k]); cudaFree(r->cU8[k]);
+    if (r->ev_in[k]) { cudaEventDestroy(r->ev_in[k]); cudaEventDestroy(r->ev_done[k]);
+                       cudaEventDestroy(r->ev_out[k]); cudaEventDestroy(r->ev_copied[k]); }
+  }
+  cudaFree(r->dStatus);
+  if (r->ev[0])
+    for (int i = 0; i <= JN_PROFILE_STAGES; i++) cudaEventDestroy(r->ev[i]);
+  if (r->ev_fork) cudaEventDestroy(r->ev_fork);
+  if (r->own) cudaStreamDestroy(r->own);
+  if (r->s_in) cudaStreamDestroy(r->s_in);
+  if (r->s_out) cudaStreamDestroy(r->s_out);
+  delete r;
+}
+
+static DevRes* devres_acquire(int device) {
+  {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    for (size_t i = g_cache.size(); i-- > 0;)
+      if (g_cache[i]->device == device) {
+        DevRes* r = g_cache[i];
+        g_cache.erase(g_cache.begin() + i);
+        return r;
+      }
+  }
+  DevRes* r = new DevRes();
+  memset(r, 0, sizeof(*r));
+  r->device = device;
+  return r;
+}
+
+static void devres_release(DevRes* r) {
+  DevRes* evict = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    g_cache.push_back(r);
+    if (g_cache.size() > JN_CACHE_MAX) { evict = g_cache.front(); g_cache.erase(g_cache.begin()); }
+  }
+  devres_free(evict);
+}
+
+// Frees everything the cache holds (process shutdown, tests).
+extern "C" void jn_cache_clear(void) {
+  std::vector<DevRes*> all;
+  {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    all.swap(g_cache);
+  }
+  for (DevRes* r : all) devres_free(r);
+}
+
 extern "C" jn_elas* jn_elas_create(const jn_elas_params* p, int device) {
   if (!p) { jn_set_error("jn_elas_create: null parameters"); return nullptr; }
   int ndev = 0;
@@ -114,31 +205,17 @@ extern "C" jn_elas* jn_elas_create(const jn_elas_params* p, int device) {
   e->parts = sp ? atoi(sp) : 2;
   if (e->parts < 1) e->parts = 1;
   if (e->parts > JN_MAX_PARTS) e->parts = JN_MAX_PARTS;
+  e->r = devres_acquire(device);
   return e;
 }
 
-static void free_workspace(jn_elas* e) {
-  if (e->arena) cudaFree(e->arena);
-  e->arena = nullptr;
-  memset(&e->ws, 0, sizeof(e->ws));
-  for (int k = 0; k < JN_MAX_PARTS - 1; k++) {
-    if (e->arenax[k]) cudaFree(e->arenax[k]);
-    e->arenax[k] = nullptr;
-    memset(&e->wsx[k], 0, sizeof(e->wsx[k]));
-  }
-}
-
+// The handle goes away, its device resources are parked for the next handle on this device
+// (a fresh Elas per frame as in point_cloud.cpp:416-419 allocates nothing).  Work still queued on
+// the caller's streams keeps using the buffers; like any reuse of a handle, the next user must be
+// ordered after it (same stream, or a synchronisation in between).
 extern "C" void jn_elas_destroy(jn_elas* e) {
   if (!e) return;
-  cudaSetDevice(e->device);
-  free_workspace(e);
-  for (int k = 0; k < 2; k++) { cudaFree(e->dI[k]); cudaFree(e->dD[k]); }
-  cudaFree(e->dStatus);
-  if (e->ev[0])
-    for (int i = 0; i <= JN_PROFILE_STAGES; i++) cudaEventDestroy(e->ev[i]);
-  if (e->ev_fork) cudaEventDestroy(e->ev_fork);
-  for (int k = 0; k < JN_MAX_PARTS - 1; k++)
-    if (e->aux[k]) { cudaStreamDestroy(e->aux[k]); cudaEventDestroy(e->ev_join[k]); }
+  devres_release(e->r);
   delete e;
 }
 
@@ -234,38 +311,56 @@ static void layout(const Geo& g, int B, Workspace& ws, char* base) {
   ws.bytes = (size_t)(cur - base);
 }
 
+// Same buffer layout <=> same image size, lattice, grid and map resolution.
+static bool same_layout(const Geo& a, const Geo& b) {
+  return a.W == b.W && a.H == b.H && a.Wc == b.Wc && a.Hc == b.Hc && a.gw == b.gw && a.gh == b.gh &&
+         a.gwords == b.gwords && a.Wd == b.Wd && a.Hd == b.Hd;
+}
+
 static int ensure_workspace(jn_elas* e, const int32_t dims[3], int B) {
   Geo g;
   int rc = make_geo(e->p, dims, &g);
   if (rc) return rc;
   JN_CUDA_CHECK(cudaSetDevice(e->device));
+  DevRes* r = e->r;
   // sub-batches: parts 1.. take B / K frames each, part 0 the rest
   const int K = (e->parts < B) ? e->parts : B, Bx = (K > 1) ? B / K : 0;
-  bool fits = e->arena && e->g.W == g.W && e->g.H == g.H && e->ws.B >= B;
-  for (int k = 0; k + 1 < K; k++) fits = fits && e->wsx[k].B >= Bx;
+  bool fits = r->arena && same_layout(r->g, g) && r->ws.B >= B;
+  for (int k = 0; k + 1 < K; k++) fits = fits && r->wsx[k].B >= Bx;
   if (fits) {
-    e->g = g;  // stride may differ between calls
+    r->g = g;  // stride and parameters may differ between calls
     return JN_OK;
   }
-  free_workspace(e);
+  // (re)build: keep an arena that is large enough (zeroed again), else allocate
   Workspace probe;
   memset(&probe, 0, sizeof(probe));
   layout(g, B, probe, nullptr);
-  JN_CUDA_CHECK(cudaMalloc(&e->arena, probe.bytes));
-  JN_CUDA_CHECK(cudaMemset(e->arena, 0, probe.bytes));
-  layout(g, B, e->ws, (char*)e->arena);
+  if (r->arena_bytes < probe.bytes) {
+    if (r->arena) cudaFree(r->arena);
+    r->arena = nullptr; r->arena_bytes = 0;
+    JN_CUDA_CHECK(cudaMalloc(&r->arena, probe.bytes));
+    r->arena_bytes = probe.bytes;
+  }
+  JN_CUDA_CHECK(cudaMemset(r->arena, 0, probe.bytes));
+  layout(g, B, r->ws, (char*)r->arena);
+  for (int k = 0; k < JN_MAX_PARTS - 1; k++) memset(&r->wsx[k], 0, sizeof(r->wsx[k]));
   for (int k = 0; k + 1 < K; k++) {
     layout(g, Bx, probe, nullptr);
-    JN_CUDA_CHECK(cudaMalloc(&e->arenax[k], probe.bytes));
-    JN_CUDA_CHECK(cudaMemset(e->arenax[k], 0, probe.bytes));
-    layout(g, Bx, e->wsx[k], (char*)e->arenax[k]);
-    if (!e->aux[k]) {
-      JN_CUDA_CHECK(cudaStreamCreateWithFlags(&e->aux[k], cudaStreamNonBlocking));
-      JN_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_join[k], cudaEventDisableTiming));
+    if (r->arenax_bytes[k] < probe.bytes) {
+      if (r->arenax[k]) cudaFree(r->arenax[k]);
+      r->arenax[k] = nullptr; r->arenax_bytes[k] = 0;
+      JN_CUDA_CHECK(cudaMalloc(&r->arenax[k], probe.bytes));
+      r->arenax_bytes[k] = probe.bytes;
+    }
+    JN_CUDA_CHECK(cudaMemset(r->arenax[k], 0, probe.bytes));
+    layout(g, Bx, r->wsx[k], (char*)r->arenax[k]);
+    if (!r->aux[k]) {
+      JN_CUDA_CHECK(cudaStreamCreateWithFlags(&r->aux[k], cudaStreamNonBlocking));
+      JN_CUDA_CHECK(cudaEventCreateWithFlags(&r->ev_join[k], cudaEventDisableTiming));
     }
   }
-  if (K > 1 && !e->ev_fork) JN_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
-  e->g = g;
+  if (K > 1 && !r->ev_fork) JN_CUDA_CHECK(cudaEventCreateWithFlags(&r->ev_fork, cudaEventDisableTiming));
+  r->g = g;
   return JN_OK;
 }
 
@@ -284,39 +379,40 @@ static int run_stage(int stage, const Geo& g, int B, Workspace& ws, const uint8_
 }
 
 // Elas::process for B frames.  Single stream: everything on `s`.  Split mode: the batch is cut
-// into K sub-batches; part 0 runs on `s` with e->ws, part k on auxiliary stream k with e->wsx[k-1],
+// into K sub-batches; part 0 runs on `s` with e->r->ws, part k on auxiliary stream k with e->r->wsx[k-1],
 // stage launches interleaved; the auxiliary streams fork from and join back into `s`.
 static int run_pipeline(jn_elas* e, int B, const uint8_t* I1, const uint8_t* I2, float* D1, float* D2,
                         int32_t* status, cudaStream_t s) {
-  const Geo& g = e->g;
+  const Geo& g = e->r->g;
   const bool prof = e->profile != 0;
   int K = (e->parts < B) ? e->parts : B;
   if (prof) K = 1;
   const int Bx = (K > 1) ? B / K : 0;
   for (int k = 0; k + 1 < K; k++)
-    if (e->wsx[k].B < Bx) K = 1;
+    if (e->r->wsx[k].B < Bx) K = 1;
   const int B0 = B - (K - 1) * Bx;
   const size_t n = (size_t)g.Wd * g.Hd, ibytes = (size_t)g.bpl * g.H;
   if (K > 1) {
-    JN_CUDA_CHECK(cudaEventRecord(e->ev_fork, s));
-    for (int k = 0; k + 1 < K; k++) JN_CUDA_CHECK(cudaStreamWaitEvent(e->aux[k], e->ev_fork, 0));
+    JN_CUDA_CHECK(cudaEventRecord(e->r->ev_fork, s));
+    for (int k = 0; k + 1 < K; k++) JN_CUDA_CHECK(cudaStreamWaitEvent(e->r->aux[k], e->r->ev_fork, 0));
   }
-  for (int stage = 0; stage < JN_PROFILE_STAGES; stage++) {
-    if (prof) cudaEventRecord(e->ev[stage], s);
-    int rc = run_stage(stage, g, B0, e->ws, I1, I2, D1, D2, status, s);
-    if (rc) return rc;
-    for (int k = 0; k + 1 < K; k++) {
+  int rc = JN_OK;
+  for (int stage = 0; stage < JN_PROFILE_STAGES && rc == JN_OK; stage++) {
+    if (prof) cudaEventRecord(e->r->ev[stage], s);
+    rc = run_stage(stage, g, B0, e->r->ws, I1, I2, D1, D2, status, s);
+    for (int k = 0; k + 1 < K && rc == JN_OK; k++) {
       const size_t f0 = (size_t)B0 + (size_t)k * Bx;   // first frame of part k+1
-      rc = run_stage(stage, g, Bx, e->wsx[k], I1 + f0 * ibytes, I2 + f0 * ibytes, D1 + f0 * n,
-                     D2 ? D2 + f0 * n : nullptr, status ? status + f0 : nullptr, e->aux[k]);
-      if (rc) return rc;
+      rc = run_stage(stage, g, Bx, e->r->wsx[k], I1 + f0 * ibytes, I2 + f0 * ibytes, D1 + f0 * n,
+                     D2 ? D2 + f0 * n : nullptr, status ? status + f0 : nullptr, e->r->aux[k]);
     }
   }
-  if (prof) cudaEventRecord(e->ev[JN_PROFILE_STAGES], s);
+  if (prof) cudaEventRecord(e->r->ev[JN_PROFILE_STAGES], s);
+  // the auxiliary streams always join back into `s`, also after a failed stage launch
   for (int k = 0; k + 1 < K; k++) {
-    JN_CUDA_CHECK(cudaEventRecord(e->ev_join[k], e->aux[k]));
-    JN_CUDA_CHECK(cudaStreamWaitEvent(s, e->ev_join[k], 0));
+    JN_CUDA_CHECK(cudaEventRecord(e->r->ev_join[k], e->r->aux[k]));
+    JN_CUDA_CHECK(cudaStreamWaitEvent(s, e->r->ev_join[k], 0));
   }
+  if (rc) return rc;
   JN_CUDA_CHECK(cudaGetLastError());
   return JN_OK;
 }
@@ -326,15 +422,15 @@ static int run_pipeline(jn_elas* e, int B, const uint8_t* I1, const uint8_t* I2,
 extern "C" int jn_elas_profile(jn_elas* e, int enable) {
   if (!e) return JN_ERR_ARG;
   JN_CUDA_CHECK(cudaSetDevice(e->device));
-  if (enable && !e->ev[0])
-    for (int i = 0; i <= JN_PROFILE_STAGES; i++) JN_CUDA_CHECK(cudaEventCreate(&e->ev[i]));
+  if (enable && !e->r->ev[0])
+    for (int i = 0; i <= JN_PROFILE_STAGES; i++) JN_CUDA_CHECK(cudaEventCreate(&e->r->ev[i]));
   e->profile = enable;
   return JN_OK;
 }
 extern "C" int jn_elas_profile_read(jn_elas* e, float ms[JN_PROFILE_STAGES]) {
-  if (!e || !e->ev[0]) return JN_ERR_ARG;
-  JN_CUDA_CHECK(cudaEventSynchronize(e->ev[JN_PROFILE_STAGES]));
-  for (int i = 0; i < JN_PROFILE_STAGES; i++) JN_CUDA_CHECK(cudaEventElapsedTime(&ms[i], e->ev[i], e->ev[i + 1]));
+  if (!e || !e->r->ev[0]) return JN_ERR_ARG;
+  JN_CUDA_CHECK(cudaEventSynchronize(e->r->ev[JN_PROFILE_STAGES]));
+  for (int i = 0; i < JN_PROFILE_STAGES; i++) JN_CUDA_CHECK(cudaEventElapsedTime(&ms[i], e->r->ev[i], e->r->ev[i + 1]));
   return JN_OK;
 }
 
@@ -348,40 +444,181 @@ extern "C" int jn_elas_process_batch(jn_elas* e, int n, const uint8_t* I1, const
 
 static int ensure_staging(jn_elas* e, const int32_t dims[3]) {
   size_t npix = (size_t)dims[0] * dims[1], nbytes = (size_t)dims[2] * dims[1];
-  if (e->stage_pixels >= npix && e->stage_bytes >= nbytes) return JN_OK;
-  for (int k = 0; k < 2; k++) { cudaFree(e->dI[k]); cudaFree(e->dD[k]); e->dI[k] = nullptr; e->dD[k] = nullptr; }
-  cudaFree(e->dStatus);
-  e->dStatus = nullptr;
+  if (e->r->stage_pixels >= npix && e->r->stage_bytes >= nbytes) return JN_OK;
+  for (int k = 0; k < 2; k++) { cudaFree(e->r->dI[k]); cudaFree(e->r->dD[k]); e->r->dI[k] = nullptr; e->r->dD[k] = nullptr; }
+  cudaFree(e->r->dStatus);
+  e->r->dStatus = nullptr;
   for (int k = 0; k < 2; k++) {
-    JN_CUDA_CHECK(cudaMalloc(&e->dI[k], nbytes));
-    JN_CUDA_CHECK(cudaMalloc(&e->dD[k], npix * sizeof(float)));
+    JN_CUDA_CHECK(cudaMalloc(&e->r->dI[k], nbytes));
+    JN_CUDA_CHECK(cudaMalloc(&e->r->dD[k], npix * sizeof(float)));
   }
-  JN_CUDA_CHECK(cudaMalloc(&e->dStatus, sizeof(int32_t)));
-  e->stage_pixels = npix;
-  e->stage_bytes = nbytes;
+  JN_CUDA_CHECK(cudaMalloc(&e->r->dStatus, sizeof(int32_t)));
+  e->r->stage_pixels = npix;
+  e->r->stage_bytes = nbytes;
   return JN_OK;
 }
 
+// Host-batch path: the map slot of a frame that was not matched (<3 support points, rejected) holds
+// whatever the staging buffer held before.  The reference's caller zeroes its maps right before the
+// call (point_cloud.cpp:413-414) and finds them untouched = zero afterwards; give it exactly that.
+__global__ void zero_unmatched_kernel(float* D, const int32_t* status, size_t pix) {
+  if (status[blockIdx.y] == JN_OK) return;
+  float4* d = reinterpret_cast<float4*>(D + (size_t)blockIdx.y * pix);
+  const size_t n4 = pix / 4;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x)
+    d[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (blockIdx.x == 0 && threadIdx.x < (pix & 3)) D[(size_t)blockIdx.y * pix + n4 * 4 + threadIdx.x] = 0.f;
+}
+
+static int ensure_own_stream(DevRes* r) {
+  if (!r->own) JN_CUDA_CHECK(cudaStreamCreateWithFlags(&r->own, cudaStreamNonBlocking));
+  return JN_OK;
+}
+
+// Elas::process: host pointers, synchronous.  Everything runs on the handle's own stream (not the
+// legacy default stream).  D2 may be NULL: the right map is then neither post-processed further nor
+// copied back (the reference's caller, point_cloud.cpp:419-421, never looks at it).  Pinned caller
+// buffers (jn_host_alloc) make both copies DMA transfers; pageable ones go through the driver's staging.
 extern "C" int jn_elas_process(jn_elas* e, const uint8_t* I1, const uint8_t* I2, float* D1, float* D2,
                                const int32_t dims[3]) {
-  if (!e || !I1 || !I2 || !D1 || !D2 || !dims) { jn_set_error("jn_elas_process: bad arguments"); return JN_ERR_ARG; }
+  if (!e || !I1 || !I2 || !D1 || !dims) { jn_set_error("jn_elas_process: bad arguments"); return JN_ERR_ARG; }
   int rc = ensure_workspace(e, dims, 1);
   if (rc) return rc;
   rc = ensure_staging(e, dims);
   if (rc) return rc;
-  const size_t npix = (size_t)e->g.Wd * e->g.Hd, nbytes = (size_t)dims[2] * dims[1];
-  JN_CUDA_CHECK(cudaMemcpyAsync(e->dI[0], I1, nbytes, cudaMemcpyHostToDevice, 0));
-  JN_CUDA_CHECK(cudaMemcpyAsync(e->dI[1], I2, nbytes, cudaMemcpyHostToDevice, 0));
-  rc = run_pipeline(e, 1, e->dI[0], e->dI[1], e->dD[0], e->dD[1], e->dStatus, 0);
+  DevRes* r = e->r;
+  if ((rc = ensure_own_stream(r))) return rc;
+  cudaStream_t s = r->own;
+  const size_t npix = (size_t)r->g.Wd * r->g.Hd, nbytes = (size_t)dims[2] * dims[1];
+  JN_CUDA_CHECK(cudaMemcpyAsync(r->dI[0], I1, nbytes, cudaMemcpyHostToDevice, s));
+  JN_CUDA_CHECK(cudaMemcpyAsync(r->dI[1], I2, nbytes, cudaMemcpyHostToDevice, s));
+  rc = run_pipeline(e, 1, r->dI[0], r->dI[1], r->dD[0], D2 ? r->dD[1] : nullptr, r->dStatus, s);
   if (rc) return rc;
   int32_t st = 0;
-  JN_CUDA_CHECK(cudaMemcpy(&st, e->dStatus, sizeof(st), cudaMemcpyDeviceToHost));
+  JN_CUDA_CHECK(cudaMemcpyAsync(&st, r->dStatus, sizeof(st), cudaMemcpyDeviceToHost, s));
+  JN_CUDA_CHECK(cudaStreamSynchronize(s));
   if (st < 0) jn_set_error("frame rejected on the device (status %d): parameter combination not supported", st);
   if (st == JN_OK) {  // "<3 support points": outputs untouched (elas.cpp:66-71)
-    JN_CUDA_CHECK(cudaMemcpy(D1, e->dD[0], npix * sizeof(float), cudaMemcpyDeviceToHost));
-    JN_CUDA_CHECK(cudaMemcpy(D2, e->dD[1], npix * sizeof(float), cudaMemcpyDeviceToHost));
+    JN_CUDA_CHECK(cudaMemcpyAsync(D1, r->dD[0], npix * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (D2) JN_CUDA_CHECK(cudaMemcpyAsync(D2, r->dD[1], npix * sizeof(float), cudaMemcpyDeviceToHost, s));
+    JN_CUDA_CHECK(cudaStreamSynchronize(s));
   }
   return st;
+}
+
+// Page-locked host memory for callers that do not link the CUDA runtime themselves.
+extern "C" void* jn_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+    jn_set_error("jn_host_alloc(%zu): %s", bytes, cudaGetErrorString(cudaGetLastError()));
+    return nullptr;
+  }
+  return p;
+}
+extern "C" void jn_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+// ---- host-pointer batch: image pairs in, obstacle scans out -----------------------------------
+// The per-frame sequence of point_cloud.cpp (generateDisparityMap :406-429 -> publishObstacleScan
+// :213-296) for n independent frames with HOST buffers.  Copies and compute run on three streams
+// with double-buffered device staging, so consecutive submissions overlap: H2D of call i+1, the
+// kernels of call i and D2H of call i-1.  submit() returns as soon as the work is queued; the
+// caller's buffers belong to the library until wait() returns.
+static int ensure_chunks(jn_elas* e, const int32_t dims[3], int n) {
+  DevRes* r = e->r;
+  const size_t img = (size_t)dims[2] * dims[1], pix = (size_t)r->g.Wd * r->g.Hd;
+  if (!r->s_in) {
+    JN_CUDA_CHECK(cudaStreamCreateWithFlags(&r->s_in, cudaStreamNonBlocking));
+    JN_CUDA_CHECK(cudaStreamCreateWithFlags(&r->s_out, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; k++) {
+      JN_CUDA_CHECK(cudaEventCreateWithFlags(&r->ev_in[k], cudaEventDisableTiming));
+      JN_CUDA_CHECK(cudaEventCreateWithFlags(&r->ev_done[k], cudaEventDisableTiming));
+      JN_CUDA_CHECK(cudaEventCreateWithFlags(&r->ev_out[k], cudaEventDisableTiming));
+      JN_CUDA_CHECK(cudaEventCreateWithFlags(&r->ev_copied[k], cudaEventDisableTiming));
+    }
+  }
+  if (r->chunk_frames >= (size_t)n && r->chunk_img_bytes == img && r->chunk_pixels == pix) return JN_OK;
+  JN_CUDA_CHECK(cudaDeviceSynchronize());
+  for (int k = 0; k < 2; k++) {
+    cudaFree(r->cI[k][0]); cudaFree(r->cI[k][1]); cudaFree(r->cD[k]); cudaFree(r->cStatus[k]);
+    cudaFree(r->cRanges[k]); cudaFree(r->cMeta[k]); cudaFree(r->cU8[k]);
+    r->cI[k][0] = r->cI[k][1] = nullptr; r->cD[k] = nullptr; r->cStatus[k] = nullptr;
+    r->cRanges[k] = nullptr; r->cMeta[k] = nullptr; r->cU8[k] = nullptr;
+  }
+  r->chunk_frames = 0;
+  for (int k = 0; k < 2; k++) {
+    JN_CUDA_CHECK(cudaMalloc(&r->cI[k][0], img * n));
+    JN_CUDA_CHECK(cudaMalloc(&r->cI[k][1], img * n));
+    JN_CUDA_CHECK(cudaMalloc(&r->cD[k], pix * n * sizeof(float)));
+    JN_CUDA_CHECK(cudaMalloc(&r->cStatus[k], n * sizeof(int32_t)));
+    JN_CUDA_CHECK(cudaMalloc(&r->cRanges[k], (size_t)n * JN_SCAN_BINS * sizeof(double)));
+    JN_CUDA_CHECK(cudaMalloc(&r->cMeta[k], (size_t)n * sizeof(jn_scan_meta)));
+    JN_CUDA_CHECK(cudaMalloc(&r->cU8[k], pix * n));
+    // a never-used buffer is "free" and "read back": record its events once
+    JN_CUDA_CHECK(cudaEventRecord(r->ev_done[k], r->own));
+    JN_CUDA_CHECK(cudaEventRecord(r->ev_copied[k], r->own));
+  }
+  r->chunk_frames = n; r->chunk_img_bytes = img; r->chunk_pixels = pix;
+  return JN_OK;
+}
+
+struct jn_scan;
+extern "C" int jn_stereo_scan_submit(jn_elas* e, jn_scan* sc, int n, const uint8_t* I1, const uint8_t* I2,
+                                     const int32_t dims[3], float* D1, int32_t* status, double* ranges,
+                                     jn_scan_meta* meta, uint8_t* dmap_u8) {
+  if (!e || !sc || n <= 0 || !I1 || !I2 || !dims || !ranges || !meta) {
+    jn_set_error("jn_stereo_scan_submit: bad arguments");
+    return JN_ERR_ARG;
+  }
+  if (e->p.subsampling) { jn_set_error("jn_stereo_scan_submit: the obstacle scan takes full-resolution maps"); return JN_ERR_UNSUPPORTED; }
+  int rc = ensure_workspace(e, dims, n);
+  if (rc) return rc;
+  DevRes* r = e->r;
+  if ((rc = ensure_own_stream(r))) return rc;
+  if ((rc = ensure_chunks(e, dims, n))) return rc;
+  const int k = (int)(r->submits++ & 1);
+  const size_t img = (size_t)dims[2] * dims[1], pix = (size_t)r->g.Wd * r->g.Hd;
+  // H2D of this call's frames as soon as buffer k is free again (the kernels of call i-2 are done with it)
+  JN_CUDA_CHECK(cudaStreamWaitEvent(r->s_in, r->ev_done[k], 0));
+  JN_CUDA_CHECK(cudaMemcpyAsync(r->cI[k][0], I1, img * n, cudaMemcpyHostToDevice, r->s_in));
+  JN_CUDA_CHECK(cudaMemcpyAsync(r->cI[k][1], I2, img * n, cudaMemcpyHostToDevice, r->s_in));
+  JN_CUDA_CHECK(cudaEventRecord(r->ev_in[k], r->s_in));
+  // compute: inputs arrived, outputs of call i-2 already read back
+  JN_CUDA_CHECK(cudaStreamWaitEvent(r->own, r->ev_in[k], 0));
+  JN_CUDA_CHECK(cudaStreamWaitEvent(r->own, r->ev_copied[k], 0));
+  rc = run_pipeline(e, n, r->cI[k][0], r->cI[k][1], r->cD[k], nullptr, r->cStatus[k], r->own);
+  if (rc) return rc;
+  zero_unmatched_kernel<<<dim3(64, n), 256, 0, r->own>>>(r->cD[k], r->cStatus[k], pix);
+  g_jn_launches += 1;
+  rc = jn_scan_from_disparity_batch(sc, n, r->cD[k], r->cRanges[k], r->cMeta[k], dmap_u8 ? r->cU8[k] : nullptr, r->own);
+  if (rc) return rc;
+  JN_CUDA_CHECK(cudaEventRecord(r->ev_done[k], r->own));
+  JN_CUDA_CHECK(cudaEventRecord(r->ev_out[k], r->own));
+  // D2H of the results
+  JN_CUDA_CHECK(cudaStreamWaitEvent(r->s_out, r->ev_out[k], 0));
+  JN_CUDA_CHECK(cudaMemcpyAsync(ranges, r->cRanges[k], (size_t)n * JN_SCAN_BINS * sizeof(double), cudaMemcpyDeviceToHost, r->s_out));
+  JN_CUDA_CHECK(cudaMemcpyAsync(meta, r->cMeta[k], (size_t)n * sizeof(jn_scan_meta), cudaMemcpyDeviceToHost, r->s_out));
+  if (status) JN_CUDA_CHECK(cudaMemcpyAsync(status, r->cStatus[k], n * sizeof(int32_t), cudaMemcpyDeviceToHost, r->s_out));
+  if (dmap_u8) JN_CUDA_CHECK(cudaMemcpyAsync(dmap_u8, r->cU8[k], pix * n, cudaMemcpyDeviceToHost, r->s_out));
+  if (D1) JN_CUDA_CHECK(cudaMemcpyAsync(D1, r->cD[k], pix * n * sizeof(float), cudaMemcpyDeviceToHost, r->s_out));
+  JN_CUDA_CHECK(cudaEventRecord(r->ev_copied[k], r->s_out));
+  return JN_OK;
+}
+
+// Blocks until every submitted batch has landed in the caller's buffers.
+extern "C" int jn_stereo_scan_wait(jn_elas* e) {
+  if (!e || !e->r->s_out) return JN_ERR_ARG;
+  JN_CUDA_CHECK(cudaSetDevice(e->device));
+  JN_CUDA_CHECK(cudaStreamSynchronize(e->r->s_out));
+  JN_CUDA_CHECK(cudaStreamSynchronize(e->r->own));
+  return JN_OK;
+}
+
+extern "C" int jn_stereo_scan_batch_host(jn_elas* e, jn_scan* sc, int n, const uint8_t* I1, const uint8_t* I2,
+                                         const int32_t dims[3], float* D1, int32_t* status, double* ranges,
+                                         jn_scan_meta* meta, uint8_t* dmap_u8) {
+  int rc = jn_stereo_scan_submit(e, sc, n, I1, I2, dims, D1, status, ranges, meta, dmap_u8);
+  if (rc) return rc;
+  return jn_stereo_scan_wait(e);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -411,15 +648,15 @@ static int dump_grid(const Geo& g, const uint32_t* dmask, int32_t* out) {
 
 // diagnostics: raw FrameInfo of frame slot `frame` after the last call (caller synchronises)
 extern "C" int jn_elas_frameinfo(jn_elas* e, int frame, void* out, int bytes) {
-  if (!e || !e->arena || frame < 0 || frame >= e->ws.B || bytes > (int)sizeof(FrameInfo)) return JN_ERR_ARG;
-  JN_CUDA_CHECK(cudaMemcpy(out, e->ws.info + frame, bytes, cudaMemcpyDeviceToHost));
+  if (!e || !e->r->arena || frame < 0 || frame >= e->r->ws.B || bytes > (int)sizeof(FrameInfo)) return JN_ERR_ARG;
+  JN_CUDA_CHECK(cudaMemcpy(out, e->r->ws.info + frame, bytes, cudaMemcpyDeviceToHost));
   return JN_OK;
 }
 
 // Runs the post-processing chain on ws.Draw of frame slot 0 step by step, copying every stage out.
 static int dump_post(jn_elas* e, jn_stage_dump* o) {
-  const Geo& g = e->g;
-  Workspace& ws = e->ws;
+  const Geo& g = e->r->g;
+  Workspace& ws = e->r->ws;
   const size_t n = (size_t)g.Wd * g.Hd;
   cudaStream_t s = 0;
   int rc;
@@ -443,8 +680,8 @@ static int dump_post(jn_elas* e, jn_stage_dump* o) {
   if ((rc = d2h(o->D2_mean, cur[1], n))) return rc;
   if (g.p.filter_median)
     for (int k = 0; k < sides; k++) {
-      post_median(g, 1, ws, cur[k], ws.Dtmp[k], e->dD[k], n, s);
-      cur[k] = e->dD[k];
+      post_median(g, 1, ws, cur[k], ws.Dtmp[k], e->r->dD[k], n, s);
+      cur[k] = e->r->dD[k];
     }
   if ((rc = d2h(o->D1, cur[0], n))) return rc;
   if ((rc = d2h(o->D2, cur[1], n))) return rc;
@@ -461,8 +698,8 @@ extern "C" int jn_debug_support_filter(jn_elas* e, const int16_t* dcan, const in
   if (!e || !dcan || !dims) return JN_ERR_ARG;
   int rc = ensure_workspace(e, dims, 1);
   if (rc) return rc;
-  const Geo& g = e->g;
-  Workspace& ws = e->ws;
+  const Geo& g = e->r->g;
+  Workspace& ws = e->r->ws;
   const size_t np = (size_t)g.Wc * g.Hc;
   JN_CUDA_CHECK(cudaMemcpy(ws.dcan, dcan, np * sizeof(int16_t), cudaMemcpyHostToDevice));
   rc = launch_support_filter(g, 1, ws, 0);
@@ -489,8 +726,8 @@ extern "C" int jn_debug_triangulate(jn_elas* e, const int32_t* xy, int n, const 
   if (!e || !xy || !dims || n < 0) return JN_ERR_ARG;
   int rc = ensure_workspace(e, dims, 1);
   if (rc) return rc;
-  const Geo& g = e->g;
-  Workspace& ws = e->ws;
+  const Geo& g = e->r->g;
+  Workspace& ws = e->r->ws;
   if (n > g.cap_s) return JN_ERR_ARG;
   std::vector<int32_t> x(n), y(n);
   for (int i = 0; i < n; i++) { x[i] = xy[2 * i]; y[i] = xy[2 * i + 1]; }
@@ -520,8 +757,8 @@ extern "C" int jn_debug_postprocess(jn_elas* e, const float* D1raw, const float*
   if (rc) return rc;
   rc = ensure_staging(e, dims);
   if (rc) return rc;
-  const Geo& g = e->g;
-  Workspace& ws = e->ws;
+  const Geo& g = e->r->g;
+  Workspace& ws = e->r->ws;
   const size_t n = (size_t)g.Wd * g.Hd;
   JN_CUDA_CHECK(cudaMemcpy(ws.Draw[0], D1raw, n * sizeof(float), cudaMemcpyHostToDevice));
   JN_CUDA_CHECK(cudaMemcpy(ws.Draw[1], D2raw, n * sizeof(float), cudaMemcpyHostToDevice));
@@ -539,13 +776,13 @@ extern "C" int jn_elas_stages(jn_elas* e, const uint8_t* I1, const uint8_t* I2, 
   if (rc) return rc;
   rc = ensure_staging(e, dims);
   if (rc) return rc;
-  const Geo& g = e->g;
-  Workspace& ws = e->ws;
+  const Geo& g = e->r->g;
+  Workspace& ws = e->r->ws;
   const size_t n = (size_t)g.W * g.H, np = (size_t)g.Wc * g.Hc, nbytes = (size_t)dims[2] * dims[1];
-  JN_CUDA_CHECK(cudaMemcpy(e->dI[0], I1, nbytes, cudaMemcpyHostToDevice));
-  JN_CUDA_CHECK(cudaMemcpy(e->dI[1], I2, nbytes, cudaMemcpyHostToDevice));
+  JN_CUDA_CHECK(cudaMemcpy(e->r->dI[0], I1, nbytes, cudaMemcpyHostToDevice));
+  JN_CUDA_CHECK(cudaMemcpy(e->r->dI[1], I2, nbytes, cudaMemcpyHostToDevice));
   cudaStream_t s = 0;
-  launch_descriptor(g, 1, e->dI[0], e->dI[1], ws, s);
+  launch_descriptor(g, 1, e->r->dI[0], e->r->dI[1], ws, s);
   rc = launch_support(g, 1, ws, s);
   if (rc) return rc;
   JN_CUDA_CHECK(cudaDeviceSynchronize());

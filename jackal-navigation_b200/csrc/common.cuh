@@ -29,7 +29,8 @@
   } while (0)
 
 void jn_set_error(const char* fmt, ...);
-extern long long g_jn_launches;   // kernels launched by this library (bench.py gpu_launches)
+#include <atomic>
+extern std::atomic<long long> g_jn_launches;   // kernels launched by this library (bench.py gpu_launches)
 
 // Right-image x coordinates (u - d) are stored with this bias so that they stay non-negative
 // (corner support points reach u - d = -d); the Delaunay predicates are translation invariant.

@@ -1,0 +1,113 @@
+"""The reference-shaped calls of the C ABI on the GPU: a fresh Elas per frame (point_cloud.cpp:416-419)
+without allocations, D2 = NULL, and the host-buffer batch entry point (image pairs in, scans out)."""
+import ctypes as C
+import numpy as np
+import pytest
+import oracle_lib as ol
+import scan_lib
+
+pytestmark = pytest.mark.gpu
+
+
+def test_fresh_elas_per_frame_reuses_device_resources(jn, oracle, synth):
+    """point_cloud.cpp:416-419 constructs an Elas for every frame; the handles hand their device
+    resources to each other through the library's cache (no cudaMalloc per frame), results unchanged."""
+    import torch
+    W, H, dm = 320, 240, 64
+    frames = [synth.synth_pair(W, H, dm, s)[:2] for s in (41, 42, 43)]
+    refs = [oracle.process(ol.robotics(dm), a, b) for a, b in frames]
+    jn.lib().jn_cache_clear()
+    e = jn.Elas(jn.parameters(jn.ROBOTICS, disp_max=dm)); D1 = np.zeros((H, W), np.float32); D2 = D1.copy()
+    e.process(frames[0][0], frames[0][1], D1, D2, (W, H, W)); e.close()          # warm: allocates
+    torch.cuda.synchronize()
+    free0 = torch.cuda.mem_get_info()[0]
+    for rep in range(3):
+        for (a, b), (R1, R2) in zip(frames, refs):
+            e = jn.Elas(jn.parameters(jn.ROBOTICS, disp_max=dm))
+            D1 = np.zeros((H, W), np.float32); D2 = np.zeros((H, W), np.float32)
+            assert e.process(a, b, D1, D2, (W, H, W)) == 0
+            assert np.array_equal(D1, R1) and np.array_equal(D2, R2)
+            e.close()
+    assert torch.cuda.mem_get_info()[0] == free0          # nothing allocated or freed in between
+    jn.lib().jn_cache_clear()
+    assert torch.cuda.mem_get_info()[0] > free0
+
+
+def test_process_without_right_map(jn, oracle, synth):
+    W, H, dm = 333, 251, 100
+    I1, I2, _ = synth.textured_pair(W, H, dm, 5)
+    R1, _ = oracle.process(ol.robotics(dm), I1, I2)
+    e = jn.Elas(jn.parameters(jn.ROBOTICS, disp_max=dm))
+    D1 = np.zeros((H, W), np.float32)
+    assert e.process(I1, I2, D1, None, (W, H, W)) == 0
+    assert np.array_equal(D1, R1)
+    with pytest.raises(ValueError):
+        e.process(I1[:100], I2, D1, None, (W, H, W))      # image smaller than dims says
+    e.close()
+
+
+@pytest.mark.parametrize("pinned", [True, False])
+def test_host_batch_equals_per_frame_calls(jn, oracle, synth, pinned):
+    """jn_stereo_scan_submit / _wait: three overlapping submissions of host buffers (one textureless
+    frame among them) give per-frame exactly what Elas::process + the scan give."""
+    import torch
+    W, H, dm, n = 320, 240, 64, 4
+    cal = jn.Calibration(scan_lib.CALIB_YML)
+    cal.set_q_matrix(scan_lib.fixtures()["Q"]["320x180"])
+    sc = jn.ObstacleScan(cal, W, H)
+    e = jn.Elas(jn.parameters(jn.ROBOTICS, disp_max=dm))
+    mk = (lambda t: t.pin_memory()) if pinned else (lambda t: t)
+    sets = []
+    for call in range(3):
+        L, R = synth.scene_batch("textured" if call == 1 else "random_dot", W, H, dm, [60 + 10 * call + i for i in range(n)])
+        if call == 2:
+            L[1] = 7; R[1] = 7
+        sets.append(dict(L=mk(torch.from_numpy(L)), R=mk(torch.from_numpy(R)),
+                         D1=mk(torch.full((n, H, W), 5.0)), st=mk(torch.full((n,), -9, dtype=torch.int32)),
+                         ranges=mk(torch.zeros((n, 90), dtype=torch.float64)), meta=mk(torch.zeros((n, 5), dtype=torch.float64)),
+                         u8=mk(torch.zeros((n, H, W), dtype=torch.uint8))))
+    for s in sets:
+        e.stereo_scan_submit(sc, n, s["L"].data_ptr(), s["R"].data_ptr(), (W, H, W), s["ranges"].data_ptr(),
+                             s["meta"].data_ptr(), s["st"].data_ptr(), s["u8"].data_ptr(), s["D1"].data_ptr())
+    e.stereo_scan_wait()
+    sp = scan_lib.ScanPort()
+    A = cal.arrays()
+    gate = sp.gate(A["Q"], A["XR"], A["XT"], W, H)
+    for call, s in enumerate(sets):
+        st = s["st"].numpy()
+        for f in range(n):
+            I1, I2 = s["L"].numpy()[f], s["R"].numpy()[f]
+            if call == 2 and f == 1:
+                assert st[f] == 1 and (s["D1"].numpy()[f] == 0.0).all()       # zero map, as the reference's caller sees it
+                continue
+            R1, _ = oracle.process(ol.robotics(dm), I1, I2)
+            assert st[f] == 0 and np.array_equal(s["D1"].numpy()[f], R1), (call, f)
+            u8_ref = sp.convert_u8(R1)
+            assert np.array_equal(s["u8"].numpy()[f], u8_ref)
+            r_ref, m_ref = sp.scan(A["Q"], A["XR"], A["XT"], gate, u8_ref)
+            r = s["ranges"].numpy()[f]
+            assert np.array_equal(r < 1e9 - 1, r_ref < 1e9 - 1) and np.allclose(r, r_ref, rtol=0, atol=1e-9)
+    e.close(); sc.close()
+
+
+def test_c4_seeds_full_size(jn, oracle, synth):
+    """BASELINE config C4: 1920x1200 pairs with seeds 1000.. -- 32 of them (spread over the 1024),
+    final maps bit-exact against the oracle, in one batch through the device-resident entry point."""
+    import torch
+    W, H, dm = 1920, 1200, 255
+    seeds = [1000 + 33 * i for i in range(32)]
+    L, R = synth.synth_batch(W, H, dm, seeds)
+    dev = torch.device("cuda", 0)
+    dL = torch.from_numpy(L).to(dev); dR = torch.from_numpy(R).to(dev)
+    dD1 = torch.zeros((len(seeds), H, W), dtype=torch.float32, device=dev)
+    st = torch.zeros(len(seeds), dtype=torch.int32, device=dev)
+    e = jn.Elas(jn.parameters(jn.ROBOTICS, disp_max=dm))
+    e.process_batch(dL.data_ptr(), dR.data_ptr(), dD1.data_ptr(), 0, st.data_ptr(), (W, H, W), len(seeds), 0)
+    torch.cuda.synchronize()
+    D1 = dD1.cpu().numpy()
+    assert (st.cpu().numpy() == 0).all()
+    p = ol.robotics(dm)
+    for i in range(len(seeds)):
+        R1, _ = oracle.process(p, L[i], R[i])
+        assert np.array_equal(D1[i], R1), seeds[i]
+    e.close()
