@@ -236,6 +236,27 @@ void jn_rectify_destroy(jn_rectify* r);
 int jn_rectify_batch(jn_rectify* r, int32_t n, const uint8_t* src, int32_t src_w, int32_t src_h, int32_t src_stride,
                      const int32_t roi[4], uint8_t* dst, int32_t dst_stride, void* stream);
 
+/* ---- the scan's consumer without ROS --------------------------------
+ * laserScanCallback / checkObstacle / chooseDirection of the `navigate` node
+ * (src/obstacle_avoidance/navigate.cpp:344-363, 101-153, 155-197): host code, O(90) per frame.
+ *   jn_navigate_set_scan        LaserScan.ranges (compacted float32, as jn_scan_compact emits) + angle_min/max
+ *   jn_navigate_set_scan_bins   the 90-bin output of jn_scan_from_disparity directly
+ *   jn_navigate_check_obstacle  returns isObstacle after the spatial filter, the 50 cm rule and the 20-frame
+ *                               vote; report[4] = {points in the safe box, laser points, closest, confidence}
+ *   jn_navigate_choose_direction  0 keep / 1 left / 2 right, with the reference's hysteresis on last_dir
+ *                               (the caller stores its choice with jn_navigate_set_last_dir, as
+ *                               obstacleAvoidMode does) */
+typedef struct jn_navigate jn_navigate;
+jn_navigate* jn_navigate_create(void);
+void jn_navigate_destroy(jn_navigate* n);
+void jn_navigate_set_clearance(jn_navigate* n, double clear_front, double clear_side, int laser_pt_thresh);
+void jn_navigate_set_last_dir(jn_navigate* n, int dir);
+int  jn_navigate_last_dir(const jn_navigate* n);
+int  jn_navigate_set_scan(jn_navigate* n, const float* ranges, int count, double angle_min, double angle_max);
+int  jn_navigate_set_scan_bins(jn_navigate* n, const double ranges[JN_SCAN_BINS], const jn_scan_meta* meta);
+int  jn_navigate_check_obstacle(jn_navigate* n, double report[4]);
+int  jn_navigate_choose_direction(const jn_navigate* n);
+
 #ifdef __cplusplus
 }
 #endif

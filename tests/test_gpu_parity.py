@@ -318,6 +318,39 @@ def test_obstacle_scan_matches_port(jn, oracle, synth, qname, W, H, dm, seed):
     sc.close()
 
 
+def test_obstacle_scan_matches_statement_by_statement_execution(jn):
+    """The device scan path against point_cloud.cpp's own statements executed with cv2 (see
+    tests/golden/make_scan_statement_golden.py): gate cache incl. the 256 -> 0 wrap, u8 map, bins, point count
+    exact; ranges / angles within 1e-9 (device atan2 / sqrt vs libm), -g points within 1e-9 m."""
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "scan_statements.npz"))
+    for name in z["names"]:
+        g = lambda k: z["%s_%s" % (name, k)]
+        W, H, ox, oy = [int(x) for x in g("dims")]
+        cal = jn.Calibration(scan_lib.CALIB_YML)
+        cal.set_q_matrix(g("Q"))
+        sc = jn.ObstacleScan(cal, W, H, ox, oy)
+        assert np.array_equal(sc.gate_cache(), g("gate")), name
+        r, m, u8 = sc.from_disparity(g("D"), want_u8=True)
+        assert np.array_equal(u8, g("u8")), name
+        ref = g("scan")
+        assert np.array_equal(r < 1e9 - 1, ref < 1e9 - 1), name
+        assert np.allclose(r, ref, rtol=0, atol=1e-9), name
+        meta = g("meta")
+        assert m.n_points == int(meta[4]), name
+        if m.n_points:
+            for v, k in zip(meta[:4], ("angle_min", "angle_max", "range_min", "range_max")):
+                assert abs(getattr(m, k) - v) <= 1e-9, (name, k)
+        assert np.array_equal(jn.scan_compact(r), jn.scan_compact(ref)), name
+        pts, r2, m2 = sc.points(g("D"))
+        gp = g("pts")
+        assert pts.shape == gp.shape, name
+        fin = np.isfinite(gp).all(axis=1)
+        assert np.abs(pts[fin] - gp[fin]).max() <= 1e-9, name
+        rp = g("scan_p")
+        assert np.array_equal(r2 < 1e9 - 1, rp < 1e9 - 1) and np.allclose(r2, rp, rtol=0, atol=1e-9), name
+        sc.close()
+
+
 def test_obstacle_scan_general_q_matrix(jn):
     """A Q without stereoRectify's sparsity (CALIB_ZERO_DISPARITY off: Q33 != 0, plus a skew term) takes
     the general 4x4 product; same checks against the port as the sparse one."""

@@ -161,6 +161,40 @@ def test_scan_port_matches_opencv_arithmetic():
     assert np.array_equal(sp.convert_u8(z["D"]), z["u8"])
 
 
+def test_scan_port_matches_statement_by_statement_execution():
+    """oracle/scan_port.c against point_cloud.cpp:104-147, 149-211, 213-296, 321-349 executed statement by
+    statement in Python with cv2.gemm doing the cv::Mat products (tests/golden/make_scan_statement_golden.py):
+    gate cache (incl. the 256 -> 0 wrap of H8), u8 conversion, 90-bin scan, extrema, compaction, the -g point
+    list and the scan from the points -- all bit-exact (same libm)."""
+    import scan_lib
+    z = np.load(gu.GOLD + "/scan_statements.npz")
+    sp = scan_lib.ScanPort()
+    XR, XT = z["XR"], z["XT"]
+    wrapped = 0
+    for name in z["names"]:
+        g = lambda k: z["%s_%s" % (name, k)]
+        W, H, ox, oy = [int(x) for x in g("dims")]
+        Q = g("Q")
+        gate = sp.gate(Q, XR, XT, W, H, ox, oy)
+        assert np.array_equal(gate, g("gate")), name
+        wrapped += int((gate[..., 0] == 0).sum())
+        u8 = sp.convert_u8(g("D"))
+        assert np.array_equal(u8, g("u8")), name
+        r, m = sp.scan(Q, XR, XT, gate, u8, ox, oy)
+        assert np.array_equal(r, g("scan")), name
+        meta = g("meta")
+        assert (m.angle_min, m.angle_max, m.range_min, m.range_max, m.n_points) == tuple(meta[:4]) + (int(meta[4]),), name
+        assert np.array_equal(sp.compact(r), g("compact")), name
+        pts = sp.points(Q, XR, XT, u8, ox, oy)
+        gp = g("pts")
+        assert pts.shape == gp.shape and np.array_equal(pts, gp, equal_nan=True), name
+        r2, m2 = sp.scan_points(pts)
+        assert np.array_equal(r2, g("scan_p")), name
+        mp_ = g("meta_p")
+        assert (m2.angle_min, m2.angle_max, m2.range_min, m2.range_max) == tuple(mp_[:4]), name
+    assert wrapped > 0          # the wrap case is in the fixture
+
+
 def test_raster_overlaps_stay_on_span_borders(port, synth):
     """Design invariant behind raster_kernel's plain stores: where two scan-converted triangles of
     computeDisparity (elas.cpp:843-903) cover the same pixel, the pixel is in the first or last row of
