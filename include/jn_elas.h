@@ -143,6 +143,18 @@ int jn_calib_load_yaml(const char* path, jn_calib* c);
 /* Q = [[1,0,0,-cx],[0,1,0,-cy],[0,0,0,f],[0,0,-1/Tx,0]] (CALIB_ZERO_DISPARITY). */
 void jn_calib_set_q(jn_calib* c, double cx, double cy, double f, double tx);
 
+/* cv::stereoRectify as the reference calls it (point_cloud.cpp:543-544: flags = CALIB_ZERO_DISPARITY,
+ * alpha = 0, newImageSize = rawimsize) without OpenCV: fills c->Q and returns R1, R2 (3x3), P1, P2 (3x4),
+ * row-major (any output pointer may be NULL).  calib_w x calib_h = size of the calibration images
+ * (640x360 in the reference), new_w x new_h = size of the rectified images (0 = same).
+ * Agrees with cv2 4.13 to 1e-9 relative. */
+int jn_calib_stereo_rectify(jn_calib* c, int calib_w, int calib_h, int new_w, int new_h, int zero_disparity,
+                            double alpha, double R1[9], double R2[9], double P1[12], double P2[12]);
+/* cv::initUndistortRectifyMap(K, D, R, P, Size(w, h), CV_32F, mapx, mapy) (point_cloud.cpp:553-554):
+ * host arrays of w*h floats, the input of jn_rectify_create.  Within 1e-3 px of cv2 4.13. */
+int jn_calib_init_undistort_rectify_map(const double K[9], const double D[5], const double R[9],
+                                        const double P[12], int w, int h, float* mapx, float* mapy);
+
 #define JN_SCAN_BINS 90
 
 typedef struct jn_scan_meta {

@@ -320,6 +320,27 @@ class Calibration:
     def set_q(self, cx, cy, f, tx):
         lib().jn_calib_set_q(C.byref(self.c), cx, cy, f, tx)
 
+    def stereo_rectify(self, calib_w, calib_h, new_w=0, new_h=0, zero_disparity=True, alpha=0.0):
+        """cv::stereoRectify as point_cloud.cpp:543-544 calls it, without OpenCV: sets Q, returns
+        (R1, R2, P1, P2)."""
+        R1 = np.zeros(9); R2 = np.zeros(9); P1 = np.zeros(12); P2 = np.zeros(12)
+        f = lib().jn_calib_stereo_rectify
+        f.argtypes = [C.POINTER(Calib), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, _P, _P, _P, _P]
+        _check(f(C.byref(self.c), int(calib_w), int(calib_h), int(new_w), int(new_h), int(bool(zero_disparity)),
+                 float(alpha), _ptr(R1), _ptr(R2), _ptr(P1), _ptr(P2)), "jn_calib_stereo_rectify")
+        return R1.reshape(3, 3), R2.reshape(3, 3), P1.reshape(3, 4), P2.reshape(3, 4)
+
+    def undistort_rectify_map(self, camera, R, P, w, h):
+        """cv::initUndistortRectifyMap(K, D, R, P, (w, h), CV_32F) for camera 1 or 2 (point_cloud.cpp:553-554)."""
+        K = np.ascontiguousarray(list(self.c.K1 if camera == 1 else self.c.K2), np.float64)
+        D = np.ascontiguousarray(list(self.c.D1 if camera == 1 else self.c.D2), np.float64)
+        R = np.ascontiguousarray(R, np.float64).reshape(9); P = np.ascontiguousarray(P, np.float64).reshape(12)
+        mx = np.zeros((h, w), np.float32); my = np.zeros((h, w), np.float32)
+        f = lib().jn_calib_init_undistort_rectify_map
+        f.argtypes = [_P, _P, _P, _P, C.c_int, C.c_int, _P, _P]
+        _check(f(_ptr(K), _ptr(D), _ptr(R), _ptr(P), int(w), int(h), _ptr(mx), _ptr(my)), "jn_calib_init_undistort_rectify_map")
+        return mx, my
+
     def set_q_matrix(self, Q):
         Q = np.asarray(Q, np.float64).reshape(16)
         for i in range(16):

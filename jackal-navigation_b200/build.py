@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_obj")
 LIB = os.path.join(HERE, "libjn_elas.so")
-SOURCES = ["api.cu", "descriptor.cu", "support.cu", "delaunay.cu", "planes_grid.cu", "dense.cu", "post.cu", "scan.cu", "rectify.cu", "navigate.cu"]
+SOURCES = ["api.cu", "descriptor.cu", "support.cu", "delaunay.cu", "planes_grid.cu", "dense.cu", "post.cu", "scan.cu", "rectify.cu", "navigate.cu", "calib.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-fmad=false",
          "-Xcompiler", "-fPIC", "-Xptxas", "-v"]

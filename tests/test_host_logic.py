@@ -132,3 +132,50 @@ def test_synth_ground_truth(synth):
     assert d == int(0.10 * 64 + 0.50 * 64 * v / 240)
     assert I2[v, u - d] == I1[v, u]
     assert gt[120, 160] == int(0.6 * 64)
+
+
+def test_stereo_rectify_and_maps_match_opencv(jn):
+    """csrc/calib.cu (OpenCV-free stereoRectify / initUndistortRectifyMap, point_cloud.cpp:543-554) against
+    cv2 4.13 outputs (tests/golden/make_rectify_golden.py): the reference's own call on the shipped
+    calibration at three image sizes, and perturbed calibrations incl. vertical stereo, no
+    ZERO_DISPARITY and other alpha.  R1/R2/P1/P2/Q within 1e-9 relative, maps within 1e-3 px."""
+    lib = jn.lib()
+    P = C.c_void_p
+    lib.jn_calib_stereo_rectify.argtypes = [C.POINTER(jn.Calib), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
+                                            P, P, P, P]
+    lib.jn_calib_init_undistort_rectify_map.argtypes = [P, P, P, P, C.c_int, C.c_int, P, P]
+    z = np.load(os.path.join(ROOT, "tests", "golden", "stereo_rectify_cv2.npz"))
+    n = int(z["n"])
+    assert n >= 10
+    for i in range(n):
+        g = lambda k: z["c%d_%s" % (i, k)]
+        c = jn.Calib()
+        for name, size in (("K1", 9), ("K2", 9), ("D1", 5), ("D2", 5), ("R", 9), ("T", 3)):
+            v = np.asarray(g(name), np.float64).reshape(-1)
+            assert v.size == size
+            for j in range(size):
+                getattr(c, name)[j] = float(v[j])
+        cw, ch, nw, nh, zero = [int(x) for x in g("cfg")]
+        R1 = np.zeros(9); R2 = np.zeros(9); P1 = np.zeros(12); P2 = np.zeros(12)
+        ptr = lambda a: a.ctypes.data_as(P)
+        rc = lib.jn_calib_stereo_rectify(C.byref(c), cw, ch, nw, nh, zero, float(g("alpha")), ptr(R1), ptr(R2), ptr(P1), ptr(P2))
+        assert rc == 0 and c.has_q == 1
+        for got, name in ((R1, "R1"), (R2, "R2"), (P1, "P1"), (P2, "P2"), (np.array(list(c.Q)), "Q")):
+            ref = np.asarray(g(name), np.float64).reshape(-1)
+            assert np.allclose(got, ref, rtol=1e-9, atol=1e-10), (i, name, np.abs(got - ref).max())
+        w, h = (nw, nh) if nw else (cw, ch)
+        for K, D, Rr, Pp, kx, ky in ((g("K1"), g("D1"), R1, P1, "mx", "my"), (g("K2"), g("D2"), R2, P2, "mx2", "my2")):
+            mx = np.zeros((h, w), np.float32); my = np.zeros((h, w), np.float32)
+            K = np.ascontiguousarray(K, np.float64); D = np.ascontiguousarray(np.asarray(D, np.float64).reshape(-1))
+            assert lib.jn_calib_init_undistort_rectify_map(ptr(K), ptr(D), ptr(Rr), ptr(Pp), w, h, ptr(mx), ptr(my)) == 0
+            assert np.abs(mx[::23, ::29] - g(kx)).max() <= 1e-3 and np.abs(my[::23, ::29] - g(ky)).max() <= 1e-3, (i, kx)
+
+
+def test_calibration_to_q_without_opencv(jn):
+    """The whole init path of point_cloud.cpp:530-544 without OpenCV: YAML -> stereoRectify -> Q equals the
+    cv2-generated fixture Q used everywhere else in the tests."""
+    cal = jn.Calibration(scan_lib.CALIB_YML)
+    fx = scan_lib.fixtures()["Q"]
+    for name, (cw, ch, nw, nh, scale) in {"640x480": (640, 360, 640, 480, 1), "320x180": (640, 360, 320, 180, 1)}.items():
+        cal.stereo_rectify(cw, ch, nw, nh)
+        assert np.allclose(cal.arrays()["Q"], np.array(fx[name]), rtol=1e-9, atol=1e-10), name
