@@ -224,6 +224,15 @@ int jn_pointcloud_from_disparity(jn_scan* s, const float* D, const uint8_t* imag
                                  int32_t channels, float* xyz, float* rgb, int32_t* n_points,
                                  double ranges[JN_SCAN_BINS], jn_scan_meta* meta);
 
+/* The -g path for n frames with everything in DEVICE memory (no host synchronisation, no allocation
+ * after the first call): D n*W*H floats; image optional (n frames, H rows of image_stride bytes, 1 or 3
+ * channels); xyz n*W*H*3 floats (frame f at f*W*H*3, its first counts[f] points valid, reference order);
+ * rgb optional n*W*H floats; counts n int32; ranges n*90 doubles and meta n: the scan from those points
+ * (publishObstacleScan(vector<Point3d>), point_cloud.cpp:149-211).  Asynchronous on `stream`. */
+int jn_pointcloud_batch(jn_scan* s, int n, const float* D, const uint8_t* image, int32_t image_stride,
+                        int32_t channels, float* xyz, float* rgb, int32_t* counts, double* ranges,
+                        jn_scan_meta* meta, void* stream);
+
 /* Compacted LaserScan.ranges as the reference publishes them: finite bins,
  * k = 89..0 (point_cloud.cpp:278-282).  Returns the count. */
 int jn_scan_compact(const double ranges[JN_SCAN_BINS], float* out);
@@ -247,6 +256,18 @@ void jn_rectify_destroy(jn_rectify* r);
  * dst: n frames of roi h rows, dst_stride bytes per row -- rows laid out as Elas::process takes them. */
 int jn_rectify_batch(jn_rectify* r, int32_t n, const uint8_t* src, int32_t src_w, int32_t src_h, int32_t src_stride,
                      const int32_t roi[4], uint8_t* dst, int32_t dst_stride, void* stream);
+
+/* ---- compressed frames in ---------------------------------------------
+ * cv::imdecode(Mat(msg->data), CV_LOAD_IMAGE_GRAYSCALE) (point_cloud.cpp:436, 478) for a batch of JPEG
+ * bitstreams, decoded by nvJPEG into DEVICE buffers (frame i at dst + i*frame_stride, rows dst_stride
+ * bytes apart) that jn_rectify_batch / jn_elas_process_batch read.  Luma plane = grayscale; within +-2
+ * grey levels of OpenCV's decoder (IDCT rounding), not bit-exact.  Asynchronous on `stream`. */
+typedef struct jn_jpeg jn_jpeg;
+jn_jpeg* jn_jpeg_create(int device);
+void jn_jpeg_destroy(jn_jpeg* j);
+int jn_jpeg_info(jn_jpeg* j, const uint8_t* data, size_t length, int32_t* width, int32_t* height);
+int jn_jpeg_decode_gray_batch(jn_jpeg* j, int n, const uint8_t* const* data, const size_t* lengths, uint8_t* dst,
+                              int32_t width, int32_t height, int32_t dst_stride, size_t frame_stride, void* stream);
 
 /* ---- the scan's consumer without ROS --------------------------------
  * laserScanCallback / checkObstacle / chooseDirection of the `navigate` node

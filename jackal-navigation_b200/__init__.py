@@ -354,6 +354,50 @@ class Calibration:
                 "XR": g(self.c.XR, (3, 3)), "XT": g(self.c.XT, (3, 1)), "Q": g(self.c.Q, (4, 4))}
 
 
+class JpegDecoder:
+    """cv::imdecode(..., CV_LOAD_IMAGE_GRAYSCALE) of point_cloud.cpp:436/478 for a batch of JPEG bitstreams,
+    decoded by nvJPEG into device memory (jn_jpeg_decode_gray_batch)."""
+
+    def __init__(self, device=0):
+        l = lib()
+        l.jn_jpeg_create.restype = _P
+        l.jn_jpeg_create.argtypes = [C.c_int]
+        l.jn_jpeg_destroy.argtypes = [_P]
+        l.jn_jpeg_info.argtypes = [_P, _P, C.c_size_t, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        l.jn_jpeg_decode_gray_batch.argtypes = [_P, C.c_int, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_size_t, _P]
+        self._h = l.jn_jpeg_create(int(device))
+        if not self._h:
+            raise JnError("jn_jpeg_create: " + last_error())
+
+    def info(self, data):
+        w = C.c_int32(0); h = C.c_int32(0)
+        buf = np.frombuffer(bytes(data), np.uint8)
+        _check(lib().jn_jpeg_info(self._h, _ptr(buf), buf.size, C.byref(w), C.byref(h)), "jn_jpeg_info")
+        return w.value, h.value
+
+    def decode_gray_batch(self, bitstreams, dst_ptr, width, height, dst_stride=None, frame_stride=None, stream=0):
+        """bitstreams: list of bytes-like; dst_ptr: device address of len(bitstreams) frames."""
+        bufs = [np.frombuffer(bytes(b), np.uint8) for b in bitstreams]
+        n = len(bufs)
+        ptrs = (C.c_void_p * n)(*[b.ctypes.data for b in bufs])
+        lens = (C.c_size_t * n)(*[b.size for b in bufs])
+        dst_stride = dst_stride or width
+        frame_stride = frame_stride or dst_stride * height
+        return _check(lib().jn_jpeg_decode_gray_batch(self._h, n, ptrs, lens, _P(int(dst_ptr)), width, height, dst_stride,
+                                                      frame_stride, _P(stream) if stream else None), "jn_jpeg_decode_gray_batch")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().jn_jpeg_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class ObstacleScan:
     """cacheDisparityValues + publishObstacleScan without ROS (point_cloud.cpp:104-147, 213-296)."""
 
@@ -420,6 +464,15 @@ class ObstacleScan:
                                                   _ptr(rgb), C.byref(n), _ptr(ranges), C.byref(meta)),
                "jn_pointcloud_from_disparity")
         return xyz[:n.value], rgb[:n.value], ranges, meta
+
+
+    def pointcloud_batch(self, n, D, xyz, counts, ranges, meta, rgb=0, image=0, image_stride=0, channels=1, stream=0):
+        """The -g path for n frames, all arguments DEVICE addresses (ints); asynchronous on `stream`."""
+        f = lib().jn_pointcloud_batch
+        f.argtypes = [_P, C.c_int, _P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P]
+        P = lambda x: _P(int(x)) if x else None
+        return _check(f(self._h, int(n), P(D), P(image), int(image_stride), int(channels), P(xyz), P(rgb), P(counts),
+                        P(ranges), P(meta), P(stream)), "jn_pointcloud_batch")
 
 
 def scan_compact(ranges):

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_obj")
 LIB = os.path.join(HERE, "libjn_elas.so")
-SOURCES = ["api.cu", "descriptor.cu", "support.cu", "delaunay.cu", "planes_grid.cu", "dense.cu", "post.cu", "scan.cu", "rectify.cu", "navigate.cu", "calib.cu"]
+SOURCES = ["api.cu", "descriptor.cu", "support.cu", "delaunay.cu", "planes_grid.cu", "dense.cu", "post.cu", "scan.cu", "rectify.cu", "navigate.cu", "calib.cu", "jpeg.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-fmad=false",
          "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
@@ -57,7 +57,9 @@ def build(force=False, verbose=False):
                 print(out)
     objs = [os.path.join(OBJ, s.replace(".cu", ".o")) for s in SOURCES]
     if force or _newer(LIB, objs):
-        r = subprocess.run([NVCC, "-shared", "-o", LIB] + objs + ["-cudart", "static"], capture_output=True, text=True)
+        # nvJPEG (the decode library behind jn_jpeg_*) is linked statically: nothing to find at run time
+        r = subprocess.run([NVCC, "-shared", "-o", LIB] + objs + ["-cudart", "static", "-lnvjpeg_static", "-lculibos"],
+                           capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
     with open(os.path.join(OBJ, "ptxas.log"), "w") as f:

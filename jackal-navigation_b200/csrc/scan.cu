@@ -16,6 +16,7 @@
 // keys; a bin index outside [0,89] is skipped.
 // Roofline: HBM, 4 N bytes read per frame (+1 N if the u8 map is written).
 #include "common.cuh"
+#include "blockutil.cuh"
 #include <math.h>
 
 struct ScanConst {
@@ -305,6 +306,70 @@ scan_points_kernel(ScanConst c, const double* __restrict__ pts, const int* __res
   acc_flush(s, acc, tid, SCAN_THREADS);
 }
 
+// ---- -g path, batched and device resident: grid.y = frame -------------------------------------
+// 1. points per column (d >= 2), 2. exclusive scan over the columns of each frame, 3. one thread per
+// column writes its points (Point32 + packed rgb, point_cloud.cpp:351-383) at its offset -- the
+// reference's order, columns outer -- and feeds the same double-precision points to the scan
+// accumulators with the ground gate of publishObstacleScan(vector<Point3d>) (point_cloud.cpp:166-172).
+__global__ void pc_count_kernel(ScanConst c, const float* __restrict__ D, int* __restrict__ colcount) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, frame = blockIdx.y;
+  if (i >= c.W) return;
+  const float* Df = D + (size_t)frame * c.W * c.H;
+  int n = 0;
+  for (int j = 0; j < c.H; j++) n += to_u8(Df[(size_t)j * c.W + i]) >= 2;
+  colcount[(size_t)frame * c.W + i] = n;
+}
+__global__ void __launch_bounds__(256) pc_scan_kernel(int* __restrict__ colcount, int W, int32_t* __restrict__ totals) {
+  __shared__ int part[256 + 1];
+  int* col = colcount + (size_t)blockIdx.x * W;
+  const int total = block_exclusive_scan(col, W, part);
+  if (threadIdx.x == 0) totals[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(SCAN_THREADS)
+pc_write_kernel(ScanConst c, const float* __restrict__ D, const int* __restrict__ coloff, const uint8_t* __restrict__ img,
+                int stride, int channels, size_t img_frame_bytes, float* __restrict__ xyz, float* __restrict__ rgb,
+                unsigned long long* __restrict__ acc) {
+  __shared__ BlockAcc s;
+  const int tid = threadIdx.x, frame = blockIdx.y;
+  acc_init(s, tid, SCAN_THREADS);
+  __syncthreads();
+  const int i = blockIdx.x * SCAN_THREADS + tid;
+  const size_t n = (size_t)c.W * c.H;
+  LocalAcc l;
+  lacc_init(l);
+  if (i < c.W) {
+    const float* Df = D + (size_t)frame * n;
+    float* xf = xyz + (size_t)frame * n * 3;
+    float* cf = rgb ? rgb + (size_t)frame * n : nullptr;
+    const uint8_t* im = img ? img + (size_t)frame * img_frame_bytes : nullptr;
+    const size_t img_bytes = (size_t)stride * c.H;
+    size_t k = coloff[(size_t)frame * c.W + i];
+    for (int j = 0; j < c.H; j++) {
+      const int d = to_u8(Df[(size_t)j * c.W + i]);
+      if (d < 2) continue;
+      double r[3];
+      reproject(c, (double)(i + c.ox), (double)(j + c.oy), (double)d, r);
+      xf[3 * k] = (float)r[0]; xf[3 * k + 1] = (float)r[1]; xf[3 * k + 2] = (float)r[2];
+      if (cf) {
+        int ch[3] = {0, 0, 0};
+        if (im) {
+#pragma unroll
+          for (int b = 0; b < 3; b++) {
+            const size_t a = (size_t)j * stride + 3 * (size_t)i + b;
+            ch[b] = (channels == 3 || a < img_bytes) ? im[a] : 0;
+          }
+        }
+        cf[k] = __int_as_float((ch[2] << 16) | (ch[1] << 8) | ch[0]);
+      }
+      k++;
+      if (above_ground(c, r[0], r[2])) lacc_add(l, s, r[0], r[1]);
+    }
+  }
+  lacc_finish(l, s);
+  __syncthreads();
+  acc_flush(s, acc + (size_t)frame * ACC_WORDS, tid, SCAN_THREADS);
+}
+
 }  // namespace
 
 // ---- host-side object ---------------------------------------------------------------------
@@ -319,6 +384,7 @@ struct jn_scan {
   int* dCol; int* dTotal; double* dPts;
   // -g path scratch, allocated on first use and kept (no cudaMalloc per frame)
   uint8_t* dImg; size_t img_bytes; float* dXyz;
+  int* dColBatch; int col_frames;   // batched -g path: per-column counts / offsets of n frames
 };
 
 static int ensure_acc(jn_scan* s, int n) {
@@ -369,7 +435,7 @@ extern "C" jn_scan* jn_scan_create(const jn_calib* cal, int width, int height, i
 extern "C" void jn_scan_destroy(jn_scan* s) {
   if (!s) return;
   cudaSetDevice(s->device);
-  cudaFree(s->dImg); cudaFree(s->dXyz);
+  cudaFree(s->dImg); cudaFree(s->dXyz); cudaFree(s->dColBatch);
   cudaFree(s->gate); cudaFree(s->acc); cudaFree(s->dD); cudaFree(s->dRanges); cudaFree(s->dMeta);
   cudaFree(s->dU8); cudaFree(s->dCol); cudaFree(s->dTotal); cudaFree(s->dPts);
   delete s;
@@ -477,6 +543,40 @@ extern "C" int jn_pointcloud_from_disparity(jn_scan* s, const float* D, const ui
   if (e == cudaSuccess) e = cudaMemcpy(meta, s->dMeta, sizeof(jn_scan_meta), cudaMemcpyDeviceToHost);
   if (e != cudaSuccess) { jn_set_error("jn_pointcloud_from_disparity: %s", cudaGetErrorString(e)); return JN_ERR_CUDA; }
   *n_points = total;
+  return JN_OK;
+}
+
+// -g path for n frames, everything in DEVICE memory, asynchronous on `stream`, no allocation after
+// the first call of a given n: D n*W*H floats; image (optional) n frames of H rows, image_stride bytes
+// each, 1 or 3 channels; xyz n*W*H*3 floats capacity (frame f starts at f*W*H*3); rgb (optional)
+// n*W*H floats; counts n int32 (points of each frame); ranges n*90 doubles; meta n.
+extern "C" int jn_pointcloud_batch(jn_scan* s, int n, const float* D, const uint8_t* image, int32_t image_stride,
+                                   int32_t channels, float* xyz, float* rgb, int32_t* counts, double* ranges,
+                                   jn_scan_meta* meta, void* stream) {
+  if (!s || n <= 0 || !D || !xyz || !counts || !ranges || !meta || (image && channels != 1 && channels != 3) ||
+      (image && image_stride < s->c.W * channels)) {
+    jn_set_error("jn_pointcloud_batch: bad arguments");
+    return JN_ERR_ARG;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  JN_CUDA_CHECK(cudaSetDevice(s->device));
+  int rc = ensure_acc(s, n);
+  if (rc) return rc;
+  if (s->col_frames < n) {
+    cudaFree(s->dColBatch);
+    s->dColBatch = nullptr; s->col_frames = 0;
+    JN_CUDA_CHECK(cudaMalloc(&s->dColBatch, (size_t)n * s->c.W * sizeof(int)));
+    s->col_frames = n;
+  }
+  const int W = s->c.W;
+  pc_count_kernel<<<dim3((W + 127) / 128, n), 128, 0, st>>>(s->c, D, s->dColBatch);
+  pc_scan_kernel<<<n, 256, 0, st>>>(s->dColBatch, W, counts);
+  acc_reset_kernel<<<(n * ACC_WORDS + 255) / 256, 256, 0, st>>>(s->acc, n);
+  pc_write_kernel<<<dim3((W + SCAN_THREADS - 1) / SCAN_THREADS, n), SCAN_THREADS, 0, st>>>(
+      s->c, D, s->dColBatch, image, image_stride, channels, (size_t)image_stride * s->c.H, xyz, rgb, s->acc);
+  scan_finalize_kernel<<<n, 96, 0, st>>>(s->acc, ranges, meta);
+  g_jn_launches += 5;
+  JN_CUDA_CHECK(cudaGetLastError());
   return JN_OK;
 }
 

@@ -111,3 +111,69 @@ def test_c4_seeds_full_size(jn, oracle, synth):
         R1, _ = oracle.process(p, L[i], R[i])
         assert np.array_equal(D1[i], R1), seeds[i]
     e.close()
+
+
+def test_jpeg_decode_matches_imdecode(jn):
+    """nvJPEG luma plane against cv2.imdecode(IMREAD_GRAYSCALE) of the same bitstreams (grayscale and colour
+    JPEGs, two qualities): decoders round the IDCT differently, so within 2 grey levels, mean below 0.3."""
+    import os
+    import torch
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "jpeg_cv2.npz"))
+    n = int(z["n"])
+    dec = jn.JpegDecoder()
+    streams = [z["jpg%d" % i].tobytes() for i in range(n)]
+    assert dec.info(streams[0]) == (320, 240)
+    dst = torch.zeros((n, 240, 320), dtype=torch.uint8, device="cuda")
+    dec.decode_gray_batch(streams, dst.data_ptr(), 320, 240)
+    torch.cuda.synchronize()
+    got = dst.cpu().numpy().astype(np.int32)
+    for i in range(n):
+        d = np.abs(got[i] - z["gray%d" % i].astype(np.int32))
+        assert d.max() <= 2 and d.mean() < 0.3, (i, d.max(), d.mean())
+    # second batch of another size through the same decoder, into a strided destination
+    dst2 = torch.zeros((2, 240, 384), dtype=torch.uint8, device="cuda")
+    dec.decode_gray_batch(streams[:2], dst2.data_ptr(), 320, 240, dst_stride=384)
+    torch.cuda.synchronize()
+    assert np.array_equal(dst2.cpu().numpy()[:, :, :320], got[:2].astype(np.uint8))
+    with pytest.raises(jn.JnError):
+        dec.decode_gray_batch([b"not a jpeg"], dst.data_ptr(), 320, 240)
+    dec.close()
+
+
+def test_pointcloud_batch_equals_single_frame_path(jn, oracle, synth):
+    """jn_pointcloud_batch (device resident, batched -g path) against the single-frame host entry point,
+    which is checked against the restatement of point_cloud.cpp:298-404 / 149-211 elsewhere: same points in
+    the same order (Point32 bits), same packed rgb, same scan."""
+    import torch
+    W, H, dm, n = 320, 240, 64, 3
+    cal = jn.Calibration(scan_lib.CALIB_YML)
+    cal.set_q_matrix(scan_lib.fixtures()["Q"]["320x180"])
+    sc = jn.ObstacleScan(cal, W, H)
+    rng = np.random.default_rng(8)
+    Ds, imgs = [], []
+    for f in range(n):
+        I1, I2, _ = synth.synth_pair(W, H, dm, 90 + f)
+        D1, _ = oracle.process(ol.robotics(dm), I1, I2)
+        Ds.append(D1); imgs.append(rng.integers(0, 256, (H, W, 3), dtype=np.uint8))
+    Ds[1][:] = -10.0                                            # an empty frame in the middle
+    dD = torch.from_numpy(np.stack(Ds)).cuda()
+    dI = torch.from_numpy(np.stack(imgs)).cuda()
+    xyz = torch.zeros((n, W * H, 3), dtype=torch.float32, device="cuda")
+    rgb = torch.zeros((n, W * H), dtype=torch.float32, device="cuda")
+    cnt = torch.zeros(n, dtype=torch.int32, device="cuda")
+    rg = torch.zeros((n, 90), dtype=torch.float64, device="cuda")
+    mt = torch.zeros((n, 5), dtype=torch.float64, device="cuda")
+    st = torch.cuda.Stream()
+    for rep in range(2):                                        # second call: nothing left to allocate
+        sc.pointcloud_batch(n, dD.data_ptr(), xyz.data_ptr(), cnt.data_ptr(), rg.data_ptr(), mt.data_ptr(), rgb.data_ptr(),
+                            dI.data_ptr(), 3 * W, 3, st.cuda_stream)
+    torch.cuda.synchronize()
+    counts = cnt.cpu().numpy()
+    assert counts[1] == 0
+    for f in range(n):
+        x_ref, c_ref, r_ref, m_ref = sc.pointcloud(Ds[f], imgs[f])
+        assert counts[f] == len(x_ref)
+        assert np.array_equal(xyz[f, :counts[f]].cpu().numpy().view(np.int32), x_ref.view(np.int32))
+        assert np.array_equal(rgb[f, :counts[f]].cpu().numpy().view(np.int32), c_ref.view(np.int32))
+        assert np.array_equal(rg[f].cpu().numpy(), r_ref)
+    sc.close()
