@@ -236,6 +236,31 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def pin_rank_to_cores(local, world):
+    """One rank per GPU: give every rank its own cores on the NUMA node of its GPU (pinned buffers are then
+    allocated node-locally by first touch and the copy threads of the ranks do not migrate over each other)."""
+    try:
+        bus = subprocess.run(["nvidia-smi", "-i", str(local), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        bus = bus[-12:] if len(bus) > 12 else bus                      # 00000000:1B:00.0 -> 0000:1b:00.0
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+        avail = sorted(os.sched_getaffinity(0))
+        cpus = avail
+        if node >= 0:
+            lst = open("/sys/devices/system/node/node%d/cpulist" % node).read().strip()
+            on_node = set()
+            for part in lst.split(","):
+                a, _, b = part.partition("-")
+                on_node.update(range(int(a), int(b or a) + 1))
+            cpus = [c for c in avail if c in on_node] or avail
+        per = max(1, len(cpus) // max(1, world))
+        mine = cpus[(local * per) % len(cpus):][:per] or cpus
+        os.sched_setaffinity(0, mine)
+        return {"numa_node": node, "cpus": "%d-%d (%d)" % (mine[0], mine[-1], len(mine))}
+    except Exception as ex:      # best effort: containers without sysfs / nvidia-smi
+        return {"numa_node": None, "cpus": None, "note": repr(ex)[:80]}
+
+
 STAGES = ["descriptor", "support", "delaunay", "planes_grid", "raster", "dense_match", "post"]
 
 
@@ -282,6 +307,15 @@ class Runner:
                                 self.dStatus.data_ptr(), self.dims, B, self.stream.cuda_stream)
         self.scan.from_disparity_batch(B, self.dD1.data_ptr(), self.dRanges.data_ptr(), self.dMeta.data_ptr(),
                                        self.dU8.data_ptr(), self.stream.cuda_stream)
+
+    def step_e2e_scans(self, k=0):
+        """Same call, the optional u8 disparity maps not requested: scans, meta and status come back."""
+        B, n = self.B, self.W * self.H
+        j = self.it & 1
+        self.it += 1
+        self.elas.stereo_scan_submit(self.scan, B, self.hL.data_ptr() + k * B * n, self.hR.data_ptr() + k * B * n,
+                                     self.dims, self.hRanges[j].data_ptr(), self.hMeta[j].data_ptr(),
+                                     self.hStatus[j].data_ptr())
 
     def step_e2e(self, k=0):
         """The call a user of the C ABI makes: host image pairs in, scans + u8 maps out (asynchronous;
@@ -331,6 +365,7 @@ class Runner:
             self.step_e2e(s % self.nb)
         self.elas.stereo_scan_wait()
         ms_e2e = self.timed(self.step_e2e, steps, self.elas.stereo_scan_wait)
+        self.ms_e2e_scans = self.timed(self.step_e2e_scans, steps, self.elas.stereo_scan_wait)
         return ms, ms_e2e, launches
 
     def stage_times(self, reps=3):
@@ -437,6 +472,7 @@ def run_ours(a):
         l2, r2 = make_frames(other_scene, W, H, dm, [SEED0 + rank * B + i for i in range(nd2)], procs)
         L2o = np.concatenate([l2] * (B // nd2)); R2o = np.concatenate([r2] * (B // nd2))
 
+    pin = pin_rank_to_cores(local, world) if world > 1 else None
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -529,6 +565,10 @@ def run_ours(a):
         "frames_ok": int((status == 0).sum()), "frames_few_support": int((status == 1).sum()),
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": run.h2d, "d2h_bytes_per_step": run.d2h,
                 "ms_per_step": ms_e2e / steps,
+                "scans_only": {"value": world * frames_done / (run.ms_e2e_scans / 1000.0), "unit": UNIT,
+                               "d2h_bytes_per_step": B * (90 * 8 + 40 + 4),
+                               "what": "same call without the optional u8 disparity maps in the output"},
+                "rank_pinning": pin,
                 "what": "C ABI jn_stereo_scan_submit/_wait: pinned host image pairs -> H2D -> ELAS + scan kernels -> "
                         "D2H of 90-bin scans, scan meta, status and the u8 disparity maps into pinned host buffers; "
                         "copies on the library's own streams, double-buffered, all inside the timed region"},
