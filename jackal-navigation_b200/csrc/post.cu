@@ -507,6 +507,16 @@ __global__ void gap_cols_kernel(Geo g, Workspace ws, int side) {
 // ------------------------------------------------------------ adaptive mean
 __device__ __forceinline__ float buggy_abs(float x) { return __uint_as_float(__float_as_uint(x) & 0x4F000000u); }
 
+// fs / ws, bit for bit.  The weights are 0, 2 or 4 (H2), so ws is an even number up to 32 and a power of
+// two wherever the window has no outlier (32 on a smooth surface): the quotient is then an exact
+// scaling, done with one multiply by the exactly representable reciprocal (exponent flipped) instead
+// of the ~25-instruction IEEE division; other sums take the division.
+__device__ __forceinline__ float div_weight_sum(float fs, float ws) {
+  const unsigned wb = __float_as_uint(ws);
+  if ((wb & 0x007FFFFFu) == 0u) return fs * __uint_as_float(0x7F000000u - wb);
+  return fs / ws;
+}
+
 // One output of the 8-tap filter.  x[k] = sample at coordinate c-4+k; the reference keeps
 // samples in a ring indexed by coordinate mod 8 and adds lanes (s, s+4) first, then
 // ((l0+l1)+l2)+l3 (elas.cpp:1425-1432); `rot` = (c-4) & 3 restores that order.
@@ -550,7 +560,7 @@ __device__ __forceinline__ bool mean8(const float x[8], float centre, int rot, f
     fs = ((d[0] + d[1]) + d[2]) + d[3];
   }
   if (ws > 0) {
-    float d = fs / ws;
+    const float d = div_weight_sum(fs, ws);
     if (d >= 0) { out = d; return true; }
   }
   return false;
@@ -642,7 +652,7 @@ __device__ __forceinline__ bool mean4(const float x[4], float centre, int rot, f
     default: ws = ((w[1] + w[2]) + w[3]) + w[0]; fs = ((f[1] + f[2]) + f[3]) + f[0]; break;
   }
   if (ws > 0) {
-    float d = fs / ws;
+    const float d = div_weight_sum(fs, ws);
     if (d >= 0) { out = d; return true; }
   }
   return false;
