@@ -29,7 +29,7 @@ for name, r in seen.items():
     st = sorted(((col(r, h), h[len("smsp__average_warps_issue_stalled_"):-len("_per_issue_active.ratio")]) for h in stalls if h.find("selected") < 0), reverse=True)[:2]
     print("%-34s %9.1f %9.1f %6.1f %6.1f %5.1f %5.1f %5.1f %5.1f %6.1f %4d  %s" % (
         name[:34], col(r, "gpu__time_duration.sum"), (col(r, "dram__bytes_read.sum") + col(r, "dram__bytes_write.sum")) / 1e6,
-        col(r, "dram__throughput.avg.pct_of_peak_sustained_elapsed"), col(r, "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+        col(r, "dram__bytes_read.sum.pct_of_peak_sustained_elapsed") + col(r, "dram__bytes_write.sum.pct_of_peak_sustained_elapsed"), col(r, "smsp__issue_active.avg.pct_of_peak_sustained_active"),
         col(r, "sm__inst_executed_pipe_alu.sum.pct_of_peak_sustained_active"), col(r, "sm__inst_executed_pipe_fma.sum.pct_of_peak_sustained_active"),
         col(r, "sm__inst_executed_pipe_lsu.sum.pct_of_peak_sustained_active"), col(r, "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"),
         col(r, "sm__warps_active.avg.pct_of_peak_sustained_active"), int(col(r, "launch__registers_per_thread")),

@@ -12,7 +12,7 @@ for ln in out.splitlines():
     m = re.search(r"Function : (\S+)", ln)
     if m:
         name = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip()
-        name = re.sub(r"\(.*", "", name).replace("(anonymous namespace)::", "")
+        name = re.sub(r"\((?!anonymous).*", "", name.replace("(anonymous namespace)::", "")).replace("void ", "")
         cur = per.setdefault(name, collections.Counter()); continue
     m = re.match(r"\s+/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d\s+)?([A-Z0-9_.]+)", ln)
     if m and cur is not None:
