@@ -33,7 +33,11 @@ void post_mean(const Geo& g, int B, Workspace& ws, const float* in, float* tmp, 
 void post_median(const Geo& g, int B, Workspace& ws, const float* in, float* tmp, float* out, size_t ostride, cudaStream_t s);
 void post_copy(const Geo& g, int B, Workspace& ws, const float* in, float* out, int32_t* status, cudaStream_t s);
 
+int launch_support_match(const Geo& g, int B, Workspace& ws, cudaStream_t s);
 constexpr int JN_MAX_PARTS = 4;
+#ifndef JN_DEFAULT_STAGGER
+#define JN_DEFAULT_STAGGER 1
+#endif
 
 // Device-side resources of one handle: workspace arenas, streams, events, single-frame staging.
 // They outlive the handle: jn_elas_destroy parks them in a small per-process cache and the next
@@ -49,7 +53,9 @@ struct DevRes {
   void* arenax[JN_MAX_PARTS - 1];
   size_t arenax_bytes[JN_MAX_PARTS - 1];
   cudaStream_t aux[JN_MAX_PARTS - 1];
-  cudaEvent_t ev_fork, ev_join[JN_MAX_PARTS - 1];
+  cudaEvent_t ev_fork, ev_join[JN_MAX_PARTS - 1], ev_stag[JN_MAX_PARTS - 1];
+  cudaStream_t hi[JN_MAX_PARTS];                 // high-priority streams for the latency-bound stages
+  cudaEvent_t ev_hi_in[JN_MAX_PARTS], ev_hi_out[JN_MAX_PARTS];
   // single-frame staging for the host-pointer entry point + its stream
   uint8_t* dI[2];
   float* dD[2];
@@ -78,6 +84,9 @@ struct jn_elas {
                     // latency-bound kernels (Delaunay, support filter: a CTA or two per frame) of
                     // one part overlap the bandwidth-bound kernels of the others
   int profile;
+  int stagger;      // >= 0: sub-batch k+1 starts when sub-batch k has finished this stage, so the parts
+                    // are always in DIFFERENT stages and a latency-bound stage of one (Delaunay, support
+                    // filter: one or two CTAs per frame) runs next to a throughput-bound stage of the other
   DevRes* r;
 };
 
@@ -135,7 +144,7 @@ static void devres_free(DevRes* r) {
   if (r->arena) cudaFree(r->arena);
   for (int k = 0; k < JN_MAX_PARTS - 1; k++) {
     if (r->arenax[k]) cudaFree(r->arenax[k]);
-    if (r->aux[k]) { cudaStreamDestroy(r->aux[k]); cudaEventDestroy(r->ev_join[k]); }
+    if (r->aux[k]) { cudaStreamDestroy(r->aux[k]); cudaEventDestroy(r->ev_join[k]); cudaEventDestroy(r->ev_stag[k]); }
   }
   for (int k = 0; k < 2; k++) {
     cudaFree(r->dI[k]); cudaFree(r->dD[k]);
@@ -148,6 +157,8 @@ static void devres_free(DevRes* r) {
   if (r->ev[0])
     for (int i = 0; i <= JN_PROFILE_STAGES; i++) cudaEventDestroy(r->ev[i]);
   if (r->ev_fork) cudaEventDestroy(r->ev_fork);
+  for (int k = 0; k < JN_MAX_PARTS; k++)
+    if (r->hi[k]) { cudaStreamDestroy(r->hi[k]); cudaEventDestroy(r->ev_hi_in[k]); cudaEventDestroy(r->ev_hi_out[k]); }
   if (r->own) cudaStreamDestroy(r->own);
   if (r->s_in) cudaStreamDestroy(r->s_in);
   if (r->s_out) cudaStreamDestroy(r->s_out);
@@ -205,6 +216,9 @@ extern "C" jn_elas* jn_elas_create(const jn_elas_params* p, int device) {
   e->parts = sp ? atoi(sp) : 2;
   if (e->parts < 1) e->parts = 1;
   if (e->parts > JN_MAX_PARTS) e->parts = JN_MAX_PARTS;
+  const char* sg = getenv("JN_ELAS_STAGGER");   // stage index (0 descriptor .. 5 dense), -1 = parts in lockstep
+  e->stagger = sg ? atoi(sg) : JN_DEFAULT_STAGGER;
+  if (e->stagger >= JN_PROFILE_STAGES - 1) e->stagger = JN_PROFILE_STAGES - 2;
   e->r = devres_acquire(device);
   return e;
 }
@@ -357,6 +371,7 @@ static int ensure_workspace(jn_elas* e, const int32_t dims[3], int B) {
     if (!r->aux[k]) {
       JN_CUDA_CHECK(cudaStreamCreateWithFlags(&r->aux[k], cudaStreamNonBlocking));
       JN_CUDA_CHECK(cudaEventCreateWithFlags(&r->ev_join[k], cudaEventDisableTiming));
+      JN_CUDA_CHECK(cudaEventCreateWithFlags(&r->ev_stag[k], cudaEventDisableTiming));
     }
   }
   if (K > 1 && !r->ev_fork) JN_CUDA_CHECK(cudaEventCreateWithFlags(&r->ev_fork, cudaEventDisableTiming));
@@ -397,6 +412,47 @@ static int run_pipeline(jn_elas* e, int B, const uint8_t* I1, const uint8_t* I2,
     for (int k = 0; k + 1 < K; k++) JN_CUDA_CHECK(cudaStreamWaitEvent(e->r->aux[k], e->r->ev_fork, 0));
   }
   int rc = JN_OK;
+  if (K > 1 && e->stagger >= 0) {
+    // staggered: part by part; part k+1 is released when part k is past stage `stagger`.  The
+    // latency-bound stages (support filter, Delaunay, planes + grid: one or two CTAs per frame) go to a
+    // high-priority stream of the part, so that their few CTAs are placed as soon as an SM frees up
+    // instead of queueing behind the other part's large grids.
+    int lo_p = 0, hi_p = 0;
+    cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p);
+    for (int k = 0; k < K; k++)
+      if (!e->r->hi[k]) {
+        JN_CUDA_CHECK(cudaStreamCreateWithPriority(&e->r->hi[k], cudaStreamNonBlocking, hi_p));
+        JN_CUDA_CHECK(cudaEventCreateWithFlags(&e->r->ev_hi_in[k], cudaEventDisableTiming));
+        JN_CUDA_CHECK(cudaEventCreateWithFlags(&e->r->ev_hi_out[k], cudaEventDisableTiming));
+      }
+    for (int k = 0; k < K && rc == JN_OK; k++) {
+      cudaStream_t sk = k ? e->r->aux[k - 1] : s, hk = e->r->hi[k];
+      Workspace& wk = k ? e->r->wsx[k - 1] : e->r->ws;
+      const int Bk = k ? Bx : B0;
+      const size_t f0 = k ? (size_t)B0 + (size_t)(k - 1) * Bx : 0;
+      if (k > 0) JN_CUDA_CHECK(cudaStreamWaitEvent(sk, e->r->ev_stag[k - 1], 0));
+      launch_descriptor(g, Bk, I1 + f0 * ibytes, I2 + f0 * ibytes, wk, sk);
+      if (e->stagger == 0 && k + 1 < K) JN_CUDA_CHECK(cudaEventRecord(e->r->ev_stag[k], sk));
+      rc = launch_support_match(g, Bk, wk, sk);
+      if (rc) break;
+      if (e->stagger == 1 && k + 1 < K) JN_CUDA_CHECK(cudaEventRecord(e->r->ev_stag[k], sk));
+      JN_CUDA_CHECK(cudaEventRecord(e->r->ev_hi_in[k], sk));
+      JN_CUDA_CHECK(cudaStreamWaitEvent(hk, e->r->ev_hi_in[k], 0));
+      rc = launch_support_filter(g, Bk, wk, hk);
+      if (rc) break;
+      rc = launch_delaunay(g, Bk, wk, hk);
+      if (rc) break;
+      launch_planes_grid(g, Bk, wk, hk);
+      JN_CUDA_CHECK(cudaEventRecord(e->r->ev_hi_out[k], hk));
+      JN_CUDA_CHECK(cudaStreamWaitEvent(sk, e->r->ev_hi_out[k], 0));
+      if (e->stagger >= 2 && e->stagger <= 3 && k + 1 < K) JN_CUDA_CHECK(cudaEventRecord(e->r->ev_stag[k], sk));
+      launch_raster(g, Bk, wk, sk);
+      if (e->stagger == 4 && k + 1 < K) JN_CUDA_CHECK(cudaEventRecord(e->r->ev_stag[k], sk));
+      launch_dense_match(g, Bk, wk, sk);
+      if (e->stagger >= 5 && k + 1 < K) JN_CUDA_CHECK(cudaEventRecord(e->r->ev_stag[k], sk));
+      launch_post(g, Bk, wk, D1 + f0 * n, D2 ? D2 + f0 * n : nullptr, status ? status + f0 : nullptr, sk);
+    }
+  } else
   for (int stage = 0; stage < JN_PROFILE_STAGES && rc == JN_OK; stage++) {
     if (prof) cudaEventRecord(e->r->ev[stage], s);
     rc = run_stage(stage, g, B0, e->r->ws, I1, I2, D1, D2, status, s);

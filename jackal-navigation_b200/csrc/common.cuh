@@ -133,6 +133,7 @@ __device__ __forceinline__ unsigned texture16(const uint4& a) {
 // stage kernels (one translation unit each)
 void launch_descriptor(const Geo& g, int B, const uint8_t* I1, const uint8_t* I2, Workspace& ws, cudaStream_t s);
 int  launch_support(const Geo& g, int B, Workspace& ws, cudaStream_t s);
+int  launch_support_match(const Geo& g, int B, Workspace& ws, cudaStream_t s);
 int  launch_support_filter(const Geo& g, int B, Workspace& ws, cudaStream_t s);
 int  launch_delaunay(const Geo& g, int B, Workspace& ws, cudaStream_t s);
 void launch_planes_grid(const Geo& g, int B, Workspace& ws, cudaStream_t s);

@@ -518,6 +518,12 @@ support_filter_kernel(Geo g, const int16_t* __restrict__ dcan_all, int32_t* __re
 }  // namespace
 
 int launch_support(const Geo& g, int B, Workspace& ws, cudaStream_t s) {
+  int rc = launch_support_match(g, B, ws, s);
+  if (rc) return rc;
+  return launch_support_filter(g, B, ws, s);
+}
+
+int launch_support_match(const Geo& g, int B, Workspace& ws, cudaStream_t s) {
   size_t smem = (size_t)4 * g.W * 16 + 3 * (size_t)((g.Wc * 4 + 15) & ~15) + 16;
   if (smem > 226 * 1024 || g.Wc > 2048) {   // 227 KB per CTA minus the static shared memory
     jn_set_error("image width %d too large for the shared-memory support matcher", g.W);
@@ -528,7 +534,7 @@ int launch_support(const Geo& g, int B, Workspace& ws, cudaStream_t s) {
                                      226 * 1024));
   support_match_kernel<<<dim3(g.Hc, B), MATCH_THREADS, smem, s>>>(g, ws.desc[0], ws.desc[1], ws.dcan);
   g_jn_launches += 1;
-  return launch_support_filter(g, B, ws, s);
+  return JN_OK;
 }
 
 // Filtering + compaction of the candidate images in ws.dcan (also driven directly by the tests).
