@@ -82,6 +82,15 @@ void jn_debug_delaunay_limits(int sort_max, int smem_max);
  * dense matcher instead of the compact list (-1 = default 16; 0 = always the bit set). */
 void jn_debug_grid_list_limit(int limit);
 
+/* 1 if this scan object uses the table-division / float-filtered fast path of scan_kernel (Q has
+ * stereoRectify's sparsity and the table division was verified against the IEEE division for this
+ * image size when the object was created), 0 if it evaluates the general expressions. */
+int jn_scan_fast_path(const jn_scan* s);
+
+/* Test hook: 0 = objects created from now on never take the fast path, 1 = they may, -1 = default
+ * (environment variable JN_SCAN_FAST=0 disables it). */
+void jn_debug_scan_fast(int enable);
+
 /* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
 long long jn_launch_count(void);
 

@@ -418,6 +418,13 @@ class ObstacleScan:
         except Exception:
             pass
 
+    def fast_path(self):
+        """include/jn_elas_debug.h: jn_scan_fast_path."""
+        f = lib().jn_scan_fast_path
+        f.restype = C.c_int
+        f.argtypes = [C.c_void_p]
+        return int(f(self._h))
+
     def gate_cache(self):
         out = np.zeros((self.H, self.W, 2), np.uint8)
         _check(lib().jn_scan_gate_cache(self._h, _ptr(out)), "jn_scan_gate_cache")

@@ -5,7 +5,7 @@
 // covered pixel; a pixel covered by two triangles keeps the result of the later
 // one.  Here that is two passes, both in image order:
 //
-//   raster_kernel  one warp per triangle replays the reference scan converter
+//   raster_kernel  sixteen lanes per triangle replay the reference scan converter
 //                  (same float operations, same truncations).  Everything
 //                  that is per triangle is finished here: each covered pixel gets one
 //                  32-bit "plane map" entry
@@ -76,6 +76,11 @@ __device__ __forceinline__ void write_span(unsigned* __restrict__ map, int W, in
   for (int v = vlo + 1; v < vhi - 1; v++) map[v * W + u] = span_entry(p, v);
 }
 
+#ifndef JN_RASTER_LANES
+#define JN_RASTER_LANES 16
+#endif
+constexpr int RASTER_LANES = JN_RASTER_LANES;
+
 __global__ void raster_kernel(Geo g, Workspace ws) {
   const int side = blockIdx.y, frame = blockIdx.z;
   FrameInfo* info = ws.info + frame;
@@ -88,11 +93,14 @@ __global__ void raster_kernel(Geo g, Workspace ws) {
   const int* tri = ws.tri[side] + (size_t)frame * g.cap_t * 3;
   const float* planes = ws.planes[side] + (size_t)frame * g.cap_t * 6;
   unsigned* map = reinterpret_cast<unsigned*>(ws.trimap[side]) + (size_t)frame * W * H;
-  const int lane = threadIdx.x & 31;
+  // RASTER_LANES lanes per triangle: support points sit on a 5-px lattice, so most triangles are 5 to
+  // 10 columns wide and a full warp per triangle would leave three quarters of its lanes idle
+  const int lane = threadIdx.x & (RASTER_LANES - 1);
   const bool exact = W <= 2048 && H <= 2048;
   const int po = side ? 3 : 0;              // this image's plane, the other image's slope
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (int i = warp; i < nt; i += nwarps) {
+  const int grp = (blockIdx.x * blockDim.x + threadIdx.x) / RASTER_LANES;
+  const int ngrps = (gridDim.x * blockDim.x) / RASTER_LANES;
+  for (int i = grp; i < nt; i += ngrps) {
     float tu[3], tv[3];
 #pragma unroll
     for (int k = 0; k < 3; k++) {
@@ -127,14 +135,14 @@ __global__ void raster_kernel(Geo g, Workspace ws) {
     if ((int)Bu != (int)Cu) BCa = (Bv - Cv) / (Bu - Cu);
     const float ABb = Av - ABa * Au, ACb = Av - ACa * Au, BCb = Bv - BCa * Bu;
     if ((int)Au != (int)Bu)
-      for (int u = max((int)Au, 0) + lane; u < min((int)Bu, W); u += 32) {
+      for (int u = max((int)Au, 0) + lane; u < min((int)Bu, W); u += RASTER_LANES) {
         int v1 = f2u_lo32(ACa * (float)u + ACb), v2 = f2u_lo32(ABa * (float)u + ABb);
         int vlo = max(min(v1, v2), 0), vhi = min(max(v1, v2), H);
         sp.au = pa * (float)u;
         write_span(map, W, u, vlo, vhi, sp, exact);
       }
     if ((int)Bu != (int)Cu)
-      for (int u = max((int)Bu, 0) + lane; u < min((int)Cu, W); u += 32) {
+      for (int u = max((int)Bu, 0) + lane; u < min((int)Cu, W); u += RASTER_LANES) {
         int v1 = f2u_lo32(ACa * (float)u + ACb), v2 = f2u_lo32(BCa * (float)u + BCb);
         int vlo = max(min(v1, v2), 0), vhi = min(max(v1, v2), H);
         sp.au = pa * (float)u;

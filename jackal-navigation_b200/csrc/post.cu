@@ -339,6 +339,203 @@ __global__ void __launch_bounds__(Q_THREADS) seg_apply4_kernel(Geo g, Workspace 
     if (kill[j]) D[j] = -10.f;
 }
 
+// ---- tiled components: the union-find of a 256 x 16 tile runs in shared memory ----------------------
+// seg_tile_kernel labels the 4-connected components of ONE tile: horizontal runs from ballots (as
+// seg_rows_kernel), vertical links by a union-find on the run starts with shared-memory atomics (tens
+// of cycles per hop instead of an L2 round trip), then every pixel's label is its tile component's
+// root (the smallest pixel index of the component, as a global index) and segsize is the tile
+// component's size at the root and 0 everywhere else.  seg_border_kernel then links tile components
+// across tile borders (1/16 of the row pairs, 1/256 of the column pairs) with the global union-find,
+// seg_roots_kernel adds the size of every tile root that is not a global root to its global root, and
+// seg_apply*_kernel reads label -> tile root -> global root -> size as before.
+// A vertical link is skipped when the left neighbours make the same link (see seg_merge_kernel); the
+// links that argument relies on are in-tile run links or vertical links further left in the same tile,
+// never links that could be skipped for the mirrored reason: at a tile's left column and on vertical
+// tile borders every link is made.
+constexpr int CT_W = 256, CT_H = 16, CT_THREADS = 256;
+
+__device__ __forceinline__ int sm_find(volatile int* lab, int x) {
+  int p = lab[x];
+  while (p != x) {
+    const int gp = lab[p];
+    if (gp != p) lab[x] = gp;   // path halving; labels only ever decrease toward an ancestor
+    x = p;
+    p = gp;
+  }
+  return x;
+}
+__device__ __forceinline__ void sm_union(int* lab, int a, int b) {
+  while (true) {
+    a = sm_find(lab, a);
+    b = sm_find(lab, b);
+    if (a == b) return;
+    if (a < b) { const int t = a; a = b; b = t; }
+    const int old = atomicMin(&lab[a], b);
+    if (old == a) return;
+    a = old;
+  }
+}
+
+__global__ void __launch_bounds__(CT_THREADS) seg_tile_kernel(Geo g, Workspace ws, int side) {
+  __shared__ float sD[CT_H * CT_W];   // the tile; reused for the component sizes
+  __shared__ int lab[CT_H * CT_W];
+  const int frame = blockIdx.z;
+  if (ws.info[frame].status != JN_OK) return;
+  const int W = g.Wd, H = g.Hd;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int x0 = blockIdx.x * CT_W, y0 = blockIdx.y * CT_H;
+  const size_t fp = (size_t)frame * W * H;
+  const float* __restrict__ D = ws.Dlr[side] + fp;
+  const float thr = g.p.speckle_sim_threshold;
+  const unsigned le_mask = 0xFFFFFFFFu >> (31 - lane);   // lanes 0..lane
+  // rows of the tile: a warp per row, 32 pixels per step; pixels outside the map are invalid
+  for (int r = warp; r < CT_H; r += CT_THREADS / 32) {
+    const int y = y0 + r;
+    int cur = -1;
+    float prev = -10.f;
+    for (int u0 = 0; u0 < CT_W; u0 += 32) {
+      const int c = u0 + lane, x = x0 + c;
+      const float d = (y < H && x < W) ? D[(size_t)y * W + x] : -10.f;
+      sD[r * CT_W + c] = d;
+      float dl = __shfl_up_sync(0xffffffffu, d, 1);
+      if (lane == 0) dl = prev;
+      prev = __shfl_sync(0xffffffffu, d, 31);
+      const bool valid = d >= 0;
+      const bool start = valid && (c == 0 || !(dl >= 0) || fabsf(d - dl) > thr);
+      const unsigned below = __ballot_sync(0xffffffffu, start) & le_mask;
+      // a valid pixel without a start at or before it in this chunk continues the carried run
+      const int st = valid ? (below ? u0 + 31 - __clz(below) : cur) : -1;
+      lab[r * CT_W + c] = valid ? r * CT_W + st : -1;
+      cur = __shfl_sync(0xffffffffu, st, 31);
+    }
+  }
+  __syncthreads();
+  // vertical links inside the tile (thread = column, rows top to bottom)
+  for (int r = 0; r < CT_H - 1; r++) {
+    const int idx = r * CT_W + tid;
+    const float d = sD[idx], e = sD[idx + CT_W];
+    if (d >= 0 && e >= 0 && fabsf(d - e) <= thr) {
+      bool dup = false;
+      if (tid > 0) {
+        const float dl = sD[idx - 1], el = sD[idx + CT_W - 1];
+        dup = dl >= 0 && el >= 0 && fabsf(d - dl) <= thr && fabsf(e - el) <= thr && fabsf(dl - el) <= thr;
+      }
+      if (!dup) sm_union(lab, lab[idx], lab[idx + CT_W]);
+    }
+  }
+  __syncthreads();
+  int* ssz = reinterpret_cast<int*>(sD);
+  for (int i = tid; i < CT_H * CT_W; i += CT_THREADS) ssz[i] = 0;
+  __syncthreads();
+  // roots and sizes: one shared atomic per (run, 32-pixel chunk)
+  int root[CT_H];
+#pragma unroll
+  for (int r = 0; r < CT_H; r++) {
+    const int idx = r * CT_W + tid;
+    const int l = lab[idx];
+    int x = l;
+    if (l >= 0) {
+      int p = lab[x];
+      while (p != x) { x = p; p = lab[x]; }
+    }
+    root[r] = x;
+    const int lp = __shfl_up_sync(0xffffffffu, l, 1);
+    const bool head = l >= 0 && (lane == 0 || l != lp);
+    const unsigned hm = __ballot_sync(0xffffffffu, head), vm = __ballot_sync(0xffffffffu, l >= 0);
+    if (head) {
+      const unsigned end = (hm | ~vm) & ~le_mask;
+      atomicAdd(&ssz[x], end ? __ffs(end) - 1 - lane : 32 - lane);
+    }
+  }
+  __syncthreads();
+  int* __restrict__ label = ws.label + fp;
+  int* __restrict__ segsize = ws.segsize + fp;
+  const int x = x0 + tid;
+  if (x < W) {
+#pragma unroll
+    for (int r = 0; r < CT_H; r++) {
+      const int y = y0 + r;
+      if (y >= H) break;
+      const int rt = root[r];
+      const size_t a = (size_t)y * W + x;
+      label[a] = rt >= 0 ? (y0 + (rt >> 8)) * W + x0 + (rt & (CT_W - 1)) : -1;
+      segsize[a] = (rt == r * CT_W + tid) ? ssz[rt] : 0;
+    }
+  }
+}
+
+// links across tile borders: first the pixel pairs (v, v+1) with v + 1 a multiple of CT_H, then the
+// pairs (u, u+1) with u + 1 a multiple of CT_W
+__global__ void __launch_bounds__(256) seg_border_kernel(Geo g, Workspace ws, int side) {
+  const int frame = blockIdx.y;
+  if (ws.info[frame].status != JN_OK) return;
+  const int W = g.Wd, H = g.Hd;
+  const size_t fp = (size_t)frame * W * H;
+  const float* __restrict__ D = ws.Dlr[side] + fp;
+  int* label = ws.label + fp;
+  const float thr = g.p.speckle_sim_threshold;
+  const int nhb = (H - 1) / CT_H, nvb = (W - 1) / CT_W;
+  const int total = nhb * W + nvb * H;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    if (t < nhb * W) {
+      const int k = t / W, u = t - k * W, v = CT_H * (k + 1) - 1;
+      const int i = v * W + u;
+      const float d = D[i], e = D[i + W];
+      if (!(d >= 0 && e >= 0 && fabsf(d - e) <= thr)) continue;
+      if (u % CT_W != 0) {
+        const float dl = D[i - 1], el = D[i + W - 1];
+        if (dl >= 0 && el >= 0 && fabsf(d - dl) <= thr && fabsf(e - el) <= thr && fabsf(dl - el) <= thr) continue;
+      }
+      uf_union(label, i, i + W);
+    } else {
+      const int t2 = t - nhb * W;
+      const int k = t2 / H, v = t2 - k * H, u = CT_W * (k + 1) - 1;
+      const int i = v * W + u;
+      const float d = D[i], e = D[i + 1];
+      if (d >= 0 && e >= 0 && fabsf(d - e) <= thr) uf_union(label, i, i + 1);
+    }
+  }
+}
+
+// every tile root (segsize > 0) that is not a global root adds its size to its global root and is left
+// pointing straight at it
+template <bool QUAD>
+__global__ void __launch_bounds__(256) seg_roots_kernel(Geo g, Workspace ws) {
+  const int frame = blockIdx.y;
+  if (ws.info[frame].status != JN_OK) return;
+  const int n = g.Wd * g.Hd;
+  const size_t fp = (size_t)frame * n;
+  int* label = ws.label + fp;
+  int* segsize = ws.segsize + fp;
+  constexpr int PER = QUAD ? 4 : 1;
+  const int i0 = (blockIdx.x * 256 + threadIdx.x) * PER;
+  if (i0 >= n) return;
+  int sz[PER];
+  if constexpr (QUAD) {
+    const int4 q = *reinterpret_cast<const int4*>(segsize + i0);
+    sz[0] = q.x; sz[1] = q.y; sz[2] = q.z; sz[3] = q.w;
+  } else {
+    sz[0] = segsize[i0];
+  }
+#pragma unroll
+  for (int j = 0; j < PER; j++) {
+    if (sz[j] <= 0) continue;
+    const int i = i0 + j;
+    // a component's root is its smallest pixel index and labels only decrease towards it, so
+    // compressing with atomicMin can never replace a root by a larger ancestor
+    int x = i, p = __ldcg(label + x);
+    while (p != x) {
+      const int gp = __ldcg(label + p);
+      if (gp != p) atomicMin(label + x, gp);
+      x = p;
+      p = gp;
+    }
+    if (x == i) continue;               // a global root keeps its own size and collects the others'
+    atomicMin(label + i, x);
+    atomicAdd(segsize + x, sz[j]);      // i is not a global root, so nobody adds to segsize[i]: sz[j] is final
+  }
+}
+
 // ------------------------------------------------------------ gap interpolation
 __device__ __forceinline__ float ipol(float d1, float d2) {
   return (fabsf(d1 - d2) < 3.0f) ? (d1 + d2) / 2 : fminf(d1, d2);
@@ -575,8 +772,8 @@ constexpr int MT_W = 64, MT_H = 32, MT_IN_W = MT_W + 7, MT_ROWS = MT_H + 7;
 __global__ void __launch_bounds__(256)
 mean_fused_kernel(Geo g, Workspace ws, const float* __restrict__ in, float* __restrict__ out,
                   size_t out_frame_stride) {
-  __shared__ float s_in[MT_ROWS][MT_IN_W + 1];   // rows y0-4 .. y0+MT_H+2, columns x0-4 .. x0+MT_W+2
-  __shared__ float s_tmp[MT_ROWS][MT_W];         // horizontally filtered (the reference's D_tmp)
+  __shared__ __align__(16) float s_in[MT_ROWS][MT_IN_W + 1];   // rows y0-4 .. y0+MT_H+2, columns x0-4 .. x0+MT_W+2
+  __shared__ __align__(16) float s_tmp[MT_ROWS][MT_W];         // horizontally filtered (the reference's D_tmp)
   const int frame = blockIdx.z;
   if (ws.info[frame].status != JN_OK) return;
   const int W = g.Wd, H = g.Hd, tid = threadIdx.x;
@@ -594,38 +791,56 @@ mean_fused_kernel(Geo g, Workspace ws, const float* __restrict__ in, float* __re
     }
   }
   __syncthreads();
+  // Four neighbouring outputs per thread in both passes: their 8-tap windows overlap (11 samples instead
+  // of 32) and the ring rotation (c-4) & 3 of output s is s itself (tile origins are multiples of 4),
+  // a compile-time constant, so the summation order needs no selects.
   // D_tmp: filtered for rows 3..H-4 and centres 4..W-4, otherwise -10 (invalid input) or 0 (H1)
-  for (int i = tid; i < MT_ROWS * MT_W; i += 256) {
-    const int r = i / MT_W, c = i - r * MT_W;
-    const int y = y0 - 4 + r, x = x0 + c;
-    const float d = s_in[r][c + 4];
-    float o = (d < 0) ? -10.f : 0.f;
-    if (W >= 8 && y >= 3 && y <= H - 4 && x >= 4 && x <= W - 4) {
-      float w8[8];
-      // the reference first sets every negative sample to -10 (elas.cpp:1304-1309); after the L/R check
-      // (always run before, elas.cpp:108-118) -10 is the only negative value there is
+  for (int i = tid; i < MT_ROWS * (MT_W / 4); i += 256) {
+    const int r = i / (MT_W / 4), c = 4 * (i - r * (MT_W / 4));
+    const int y = y0 - 4 + r;
+    const bool yok = W >= 8 && y >= 3 && y <= H - 4;
+    // the reference first sets every negative sample to -10 (elas.cpp:1304-1309); after the L/R check
+    // (always run before, elas.cpp:108-118) -10 is the only negative value there is
+    float v[12];
+    const float4 q0 = *reinterpret_cast<const float4*>(&s_in[r][c]);
+    const float4 q1 = *reinterpret_cast<const float4*>(&s_in[r][c + 4]);
+    const float4 q2 = *reinterpret_cast<const float4*>(&s_in[r][c + 8]);
+    v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w; v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
+    v[8] = q2.x; v[9] = q2.y; v[10] = q2.z; v[11] = q2.w;
+    float o[4];
 #pragma unroll
-      for (int k = 0; k < 8; k++) w8[k] = s_in[r][c + k];
-      float m;
-      if (mean8<false>(w8, w8[4], (x - 4) & 3, m)) o = m;
+    for (int s4 = 0; s4 < 4; s4++) {
+      const int x = x0 + c + s4;
+      const float d = v[s4 + 4];
+      o[s4] = (d < 0) ? -10.f : 0.f;
+      if (yok && x >= 4 && x <= W - 4) {
+        float m;
+        if (mean8<true>(v + s4, d, s4, m)) o[s4] = m;
+      }
     }
-    s_tmp[r][c] = o;
+    *reinterpret_cast<float4*>(&s_tmp[r][c]) = make_float4(o[0], o[1], o[2], o[3]);
   }
   __syncthreads();
   float* dst = out + (size_t)frame * out_frame_stride;
-  for (int i = tid; i < MT_H * MT_W; i += 256) {
-    const int r = i / MT_W, c = i - r * MT_W;
-    const int y = y0 + r, x = x0 + c;
-    if (x >= W || y >= H) continue;
-    float o = s_in[r + 4][c + 4];
-    if (H >= 8 && x >= 3 && x <= W - 4 && y >= 4 && y <= H - 4) {
-      float w8[8];
+  for (int i = tid; i < (MT_H / 4) * MT_W; i += 256) {
+    const int rq = i / MT_W, c = i - rq * MT_W;
+    const int x = x0 + c;
+    if (x >= W) continue;
+    const bool xok = H >= 8 && x >= 3 && x <= W - 4;
+    float v[11];
 #pragma unroll
-      for (int k = 0; k < 8; k++) w8[k] = s_tmp[r + k][c];   // rows y-4 .. y+3
-      float m;
-      if (mean8<true>(w8, w8[4], (y - 4) & 3, m)) o = m;
+    for (int k = 0; k < 11; k++) v[k] = s_tmp[4 * rq + k][c];   // rows y-4 .. y+3 of the four outputs
+#pragma unroll
+    for (int s4 = 0; s4 < 4; s4++) {
+      const int r = 4 * rq + s4, y = y0 + r;
+      if (y >= H) continue;
+      float o = s_in[r + 4][c + 4];
+      if (xok && y >= 4 && y <= H - 4) {
+        float m;
+        if (mean8<true>(v + s4, v[s4 + 4], s4, m)) o = m;
+      }
+      dst[(size_t)y * W + x] = o;
     }
-    dst[(size_t)y * W + x] = o;
   }
 }
 
@@ -776,6 +991,23 @@ void post_lr(const Geo& g, int B, Workspace& ws, cudaStream_t s, bool need_right
 
 void post_segments(const Geo& g, int B, Workspace& ws, int side, cudaStream_t s) {
   dim3 pg((g.Wd + 255) / 256, g.Hd, B);
+  static const bool tiled = !(getenv("JN_SEG_TILED") && getenv("JN_SEG_TILED")[0] == '0');
+  if (tiled) {
+    const int n = g.Wd * g.Hd;
+    seg_tile_kernel<<<dim3((g.Wd + CT_W - 1) / CT_W, (g.Hd + CT_H - 1) / CT_H, B), CT_THREADS, 0, s>>>(g, ws, side);
+    const int nb = ((g.Hd - 1) / CT_H) * g.Wd + ((g.Wd - 1) / CT_W) * g.Hd;
+    if (nb > 0) seg_border_kernel<<<dim3((nb + 255) / 256, B), 256, 0, s>>>(g, ws, side);
+    if (n % 4 == 0) seg_roots_kernel<true><<<dim3((n / 4 + 255) / 256, B), 256, 0, s>>>(g, ws);
+    else seg_roots_kernel<false><<<dim3((n + 255) / 256, B), 256, 0, s>>>(g, ws);
+    if (g.Wd % 4 == 0) {
+      dim3 qg((g.Wd / 4 + Q_THREADS - 1) / Q_THREADS, g.Hd, B);
+      seg_apply4_kernel<<<qg, Q_THREADS, 0, s>>>(g, ws, side);
+    } else {
+      seg_apply_kernel<<<pg, 256, 0, s>>>(g, ws, side);
+    }
+    g_jn_launches += nb > 0 ? 4 : 3;
+    return;
+  }
   seg_rows_kernel<<<dim3((g.Hd + SEG_ROWS_PER_CTA - 1) / SEG_ROWS_PER_CTA, B), 32 * SEG_ROWS_PER_CTA, 0, s>>>(g, ws, side);
   if (g.Wd % 4 == 0) {
     dim3 qg((g.Wd / 4 + Q_THREADS - 1) / Q_THREADS, g.Hd, B);

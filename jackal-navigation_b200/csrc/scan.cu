@@ -24,6 +24,9 @@ struct ScanConst {
   double tan_gp;          // tan(4 * 3.1415 / 180)
   int W, H, ox, oy;
   int q_simple;           // Q has stereoRectify's sparsity: only Q03, Q13, Q23, Q32 and the two unit entries
+  int fast_ok;            // q_simple and the table division below verified against IEEE division at create time
+  const double* tab;      // device, 4 x 256 doubles indexed by the u8 disparity d: b = Q32*d + 0, RN(1/b),
+                          // XR[2]*(Q23/b), XR[5]*(Q23/b)
 };
 
 namespace {
@@ -132,9 +135,30 @@ __device__ __forceinline__ void lacc_add(LocalAcc& l, BlockAcc& a, double X, dou
     }
   }
 }
+// The running (bin, key) pairs of a warp: lanes are neighbouring columns, so they sit in the same one or
+// two bins.  A 64-bit shared-memory atomicMin is a compare-and-swap loop, and 32 lanes hitting one
+// address serialise it; instead the lanes of each distinct bin reduce their keys with two REDUX.MIN (high
+// word, then low word among the lanes that hold the smallest high word) and one lane issues the atomic.
+// Called by all 32 lanes (curbin < 0: nothing pending).
+__device__ __forceinline__ void warp_bin_flush(BlockAcc& a, int bin, unsigned long long key) {
+  const int lane = threadIdx.x & 31;
+  unsigned pending = __ballot_sync(0xffffffffu, bin >= 0);
+  while (pending) {
+    const int leader = __ffs(pending) - 1;
+    const int b = __shfl_sync(0xffffffffu, bin, leader);
+    const bool mine = bin == b;
+    const unsigned hi = mine ? (unsigned)(key >> 32) : 0xffffffffu;
+    const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
+    const unsigned lo = (mine && hi == mhi) ? (unsigned)key : 0xffffffffu;
+    const unsigned mlo = __reduce_min_sync(0xffffffffu, lo);
+    if (lane == leader) atomicMin(&a.bins[b], ((unsigned long long)mhi << 32) | mlo);
+    pending &= ~__ballot_sync(0xffffffffu, mine);
+  }
+}
+
 // warp-reduce the extrema, one shared atomic per warp and value
 __device__ __forceinline__ void lacc_finish(LocalAcc& l, BlockAcc& a) {
-  if (l.curbin >= 0) atomicMin(&a.bins[l.curbin], l.curkey);
+  warp_bin_flush(a, l.curbin, l.curkey);
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) {
     l.amin = min(l.amin, __shfl_xor_sync(0xffffffffu, l.amin, off));
@@ -177,31 +201,218 @@ __device__ __forceinline__ int to_u8(float x) { return min(max(__float2int_rn(x)
 
 constexpr int SCAN_THREADS = 256;
 
-// grid (ceil(W/256), rows-per-block tiles, frames)
-__global__ void __launch_bounds__(SCAN_THREADS)
-scan_kernel(ScanConst c, const float* __restrict__ D, const uint8_t* __restrict__ gate,
-            unsigned long long* __restrict__ acc, uint8_t* __restrict__ dmap_u8, int rows_per_block) {
-  __shared__ BlockAcc s;
-  const int tid = threadIdx.x, frame = blockIdx.z;
-  acc_init(s, tid, SCAN_THREADS);
-  __syncthreads();
-  const int i = blockIdx.x * SCAN_THREADS + tid;
-  const size_t fp = (size_t)frame * c.W * c.H;
-  LocalAcc l;
-  lacc_init(l);
-  if (i < c.W) {
-    const int j0 = blockIdx.y * rows_per_block, j1 = min(j0 + rows_per_block, c.H);
-    for (int j = j0; j < j1; j++) {
-      const size_t a = (size_t)j * c.W + i;
-      const int d = to_u8(D[fp + a]);
-      if (dmap_u8) dmap_u8[fp + a] = (uint8_t)d;
-      const int g0 = gate[2 * a], g1 = gate[2 * a + 1];
-      if (d < g0 || d > g1) continue;
-      double r[3];
-      reproject(c, (double)(i + c.ox), (double)(j + c.oy), (double)d, r);
-      lacc_add(l, s, r[0], r[1]);
+// ---- fast path of scan_kernel (stereoRectify's sparse Q) -------------------------------------------
+// The u8 disparity takes 256 values, so the divisor W = Q32*d of the reprojection, its correctly rounded
+// reciprocal and the d-only terms XR[.]*Z come from a 256-entry table.  With r = RN(1/b) the quotient
+// a/b is q0 = RN(a*r), rem = a - q0*b (exact in one FMA), q = RN(q0 + rem*r): three operations instead
+// of the ~25 of the IEEE division sequence, and correctly rounded (Markstein).  The theorem's
+// precondition (q0 faithful) is not taken on trust: scan_verify_kernel compares the sequence with the
+// real division for EVERY numerator the image can produce (W + H of them) x 255 divisors when the
+// object is created and clears fast_ok on any difference.
+//
+// atan2 is only evaluated in double where its value can matter: the bin index comes from a float
+// atan2f unless the angle lies within BIN_MARGIN degrees of a bin border (float error bound 7e-5
+// degrees: 2 ulp of atan2f, input roundings, the degree conversion), and angle_min / angle_max only
+// need the exact angle of the points whose float angle is within ANG_MARGIN (>= 2 x 6e-7 rad error) of
+// the running float extremum -- the one clearly extreme point is kept as a deferred candidate and
+// evaluated once per thread at the end.  Every skipped evaluation provably cannot change a bin index or
+// an extremum, so the result is the all-double result bit for bit.
+constexpr float BIN_MARGIN = 1e-3f, ANG_MARGIN = 4e-6f;
+
+__device__ __forceinline__ double table_div(double a, double b, double r) {
+  const double q0 = a * r;
+  const double rem = fma(-q0, b, a);
+  return fma(rem, r, q0);
+}
+
+__global__ void scan_tab_kernel(ScanConst c, double* __restrict__ tab) {
+  const int d = threadIdx.x;
+  const double b = c.Q[14] * (double)d + 0.0;
+  const double Z = c.Q[11] / b;
+  tab[d] = b;
+  tab[256 + d] = 1.0 / b;
+  tab[512 + d] = c.XR[2] * Z;
+  tab[768 + d] = c.XR[5] * Z;
+}
+
+// ok[0] is cleared if the table division differs from the IEEE division for any numerator / divisor pair
+__global__ void scan_verify_kernel(ScanConst c, const double* __restrict__ tab, int* __restrict__ ok) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  bool good = true;
+  for (int axis = 0; axis < 2; axis++) {
+    if (t >= (axis ? c.H : c.W)) continue;
+    const double a = (double)(t + (axis ? c.oy : c.ox)) + (axis ? c.Q[7] : c.Q[3]);
+    for (int d = 1; d < 256; d++) {
+      const double b = tab[d], r = tab[256 + d];
+      const double q = table_div(a, b, r), e = a / b;
+      good = good && (__double_as_longlong(q) == __double_as_longlong(e)) && (b == b) && (b != 0.0) &&
+             (fabs(r) < 1e300) && (fabs(e) < 1e30);
     }
   }
+  if (!good) atomicExch(ok, 0);
+}
+
+// order-preserving float -> int key (for shared-memory atomicMin / atomicMax on floats)
+__device__ __forceinline__ int fkey(float x) {
+  const int b = __float_as_int(x);
+  return b >= 0 ? b : (b ^ 0x7fffffff);
+}
+
+struct FastAcc {
+  float fmin, fmax;        // running float extrema of the angle
+  float camin, camax;      // float angle of the deferred candidates (+/-inf: none)
+  double minX, minY, maxX, maxY;
+};
+__device__ __forceinline__ void facc_init(FastAcc& f) {
+  f.fmin = __int_as_float(0x7f800000); f.fmax = __int_as_float(0xff800000);
+  f.camin = f.fmin; f.camax = f.fmax;
+  f.minX = f.minY = f.maxX = f.maxY = 0.0;
+}
+
+__device__ __forceinline__ void lacc_bin(LocalAcc& l, BlockAcc& a, int k, unsigned long long kr) {
+  if (k != l.curbin) {
+    if (l.curbin >= 0) atomicMin(&a.bins[l.curbin], l.curkey);
+    l.curbin = k;
+    l.curkey = kr;
+  } else {
+    l.curkey = min(l.curkey, kr);
+  }
+}
+
+// one point with finite coordinates (d >= 1 through the verified table)
+__device__ __forceinline__ void lacc_add_fast(LocalAcc& l, FastAcc& f, BlockAcc& a, double X, double Y) {
+  const double r2 = Y * Y + X * X;                       // >= +0, never NaN here
+  const unsigned long long kr = (unsigned long long)__double_as_longlong(r2) | 0x8000000000000000ull;   // = okey(r2)
+  l.rmin = min(l.rmin, kr);
+  l.rmax = max(l.rmax, kr);
+  l.npts++;
+  const float Xf = (float)X, Yf = (float)Y;
+  const float mag = fmaxf(fabsf(Xf), fabsf(Yf));
+  const float af = atan2f(Yf, Xf);
+  const float t = 45.0f - af * 57.29746936f;             // 180 / 3.1415
+  const float fl = floorf(t), fr = t - fl;
+  bool exact = !(mag > 1e-30f && mag < 1e30f);           // float image of the point degenerate: no float reasoning
+  if (!exact) {
+    if (fr < BIN_MARGIN || fr > 1.0f - BIN_MARGIN) exact = true;
+    if (af < f.fmin - ANG_MARGIN) { f.fmin = af; f.camin = af; f.minX = X; f.minY = Y; }
+    else if (af <= f.fmin + ANG_MARGIN) { exact = true; f.fmin = fminf(f.fmin, af); }
+    if (af > f.fmax + ANG_MARGIN) { f.fmax = af; f.camax = af; f.maxX = X; f.maxY = Y; }
+    else if (af >= f.fmax - ANG_MARGIN) { exact = true; f.fmax = fmaxf(f.fmax, af); }
+  }
+  int k;
+  if (exact) {
+    const double th = atan2(Y, X);
+    const double deg = th * 180. / 3.1415;
+    const unsigned long long kt = okey(th);
+    l.amin = min(l.amin, kt);
+    l.amax = max(l.amax, kt);
+    const double kf = floor((double)JN_SCAN_BINS * (90. / 2. - deg) / 90.);
+    k = (kf >= 0 && kf < (double)JN_SCAN_BINS) ? (int)kf : -1;
+  } else {
+    k = (fl >= 0.0f && fl < (float)JN_SCAN_BINS) ? (int)fl : -1;
+  }
+  if (k >= 0) lacc_bin(l, a, k, kr);
+}
+
+// the deferred candidates: only those within ANG_MARGIN of the CTA's float extremum can be the extremum
+__device__ __forceinline__ void facc_finish(LocalAcc& l, FastAcc& f, int* s_fext) {
+  float wmin = f.fmin, wmax = f.fmax;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    wmin = fminf(wmin, __shfl_xor_sync(0xffffffffu, wmin, off));
+    wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, off));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin(&s_fext[0], fkey(wmin));
+    atomicMax(&s_fext[1], fkey(wmax));
+  }
+  __syncthreads();
+  const int kmin = s_fext[0], kmax = s_fext[1];
+  // keys are monotone in the float, so compare floats recovered from the keys
+  const float bmin = __int_as_float(kmin >= 0 ? kmin : (kmin ^ 0x7fffffff));
+  const float bmax = __int_as_float(kmax >= 0 ? kmax : (kmax ^ 0x7fffffff));
+  if (f.camin <= bmin + ANG_MARGIN && f.camin < __int_as_float(0x7f800000)) {   // +inf: no candidate
+    const unsigned long long kt = okey(atan2(f.minY, f.minX));
+    l.amin = min(l.amin, kt);
+    l.amax = max(l.amax, kt);
+  }
+  if (f.camax >= bmax - ANG_MARGIN && f.camax > __int_as_float(0xff800000)) {
+    const unsigned long long kt = okey(atan2(f.maxY, f.maxX));
+    l.amin = min(l.amin, kt);
+    l.amax = max(l.amax, kt);
+  }
+}
+
+
+// grid (ceil(W/256), ceil(H/SCAN_ROWS), frames).  A thread walks SCAN_ROWS rows of one column; all of its
+// disparities and gate pairs are loaded up front (SCAN_ROWS independent loads in flight per thread: the
+// row loop then never waits for memory -- with a load at the top of every iteration the kernel was bound
+// by memory latency, not by its arithmetic).  FAST: see above (c.fast_ok); a pixel with d = 0 (only
+// reachable through a wrapped gate, H8) divides by zero and takes the general expressions.
+constexpr int SCAN_ROWS = 16;
+
+template <bool FAST>
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_kernel(ScanConst c, const float* __restrict__ D, const uint8_t* __restrict__ gate,
+            unsigned long long* __restrict__ acc, uint8_t* __restrict__ dmap_u8) {
+  __shared__ BlockAcc s;
+  __shared__ double s_tab[FAST ? 1024 : 1];
+  __shared__ int s_fext[2];
+  const int tid = threadIdx.x, frame = blockIdx.z;
+  const int i = blockIdx.x * SCAN_THREADS + tid;
+  const size_t fp = (size_t)frame * c.W * c.H;
+  const int j0 = blockIdx.y * SCAN_ROWS;
+  __shared__ float s_dv[SCAN_ROWS][SCAN_THREADS];
+  __shared__ unsigned short s_gv[SCAN_ROWS][SCAN_THREADS];
+  if (i < c.W) {
+    const unsigned short* gate2 = reinterpret_cast<const unsigned short*>(gate);
+    float dv[SCAN_ROWS];
+    unsigned short gv[SCAN_ROWS];
+#pragma unroll
+    for (int r = 0; r < SCAN_ROWS; r++) {
+      const int j = j0 + r;
+      const size_t a = (size_t)min(j, c.H - 1) * c.W + i;
+      dv[r] = D[fp + a];
+      gv[r] = (j < c.H) ? gate2[a] : (unsigned short)0x00ffu;   // g0 = 255, g1 = 0: nothing passes
+    }
+#pragma unroll
+    for (int r = 0; r < SCAN_ROWS; r++) { s_dv[r][tid] = dv[r]; s_gv[r][tid] = gv[r]; }
+  }
+  acc_init(s, tid, SCAN_THREADS);
+  if (FAST) {
+    for (int k = tid; k < 1024; k += SCAN_THREADS) s_tab[k] = c.tab[k];
+    if (tid == 0) { s_fext[0] = 0x7f800000; s_fext[1] = (int)0x807fffff; }   // fkey(+inf), fkey(-inf)
+  }
+  __syncthreads();
+  LocalAcc l;
+  lacc_init(l);
+  FastAcc f;
+  facc_init(f);
+  if (i < c.W) {
+    const double px = (double)(i + c.ox) + c.Q[3];
+#pragma unroll 1
+    for (int r = 0; r < SCAN_ROWS; r++) {
+      const int j = j0 + r;
+      const int d = to_u8(s_dv[r][tid]);          // own column only: no barrier needed for these
+      if (dmap_u8 && j < c.H) dmap_u8[fp + (size_t)j * c.W + i] = (uint8_t)d;
+      const unsigned gq = s_gv[r][tid];
+      const int g0 = gq & 0xff, g1 = gq >> 8;
+      if (d < g0 || d > g1) continue;
+      if (FAST && d != 0) {
+        const double py = (double)(j + c.oy) + c.Q[7];
+        const double b = s_tab[d], rb = s_tab[256 + d];
+        const double X = table_div(px, b, rb), Y = table_div(py, b, rb);
+        const double o0 = ((c.XR[0] * X + c.XR[1] * Y) + s_tab[512 + d]) + c.XT[0];
+        const double o1 = ((c.XR[3] * X + c.XR[4] * Y) + s_tab[768 + d]) + c.XT[1];
+        lacc_add_fast(l, f, s, o0, o1);
+      } else {
+        double rr[3];
+        reproject(c, (double)(i + c.ox), (double)(j + c.oy), (double)d, rr);
+        lacc_add(l, s, rr[0], rr[1]);
+      }
+    }
+  }
+  if (FAST) facc_finish(l, f, s_fext);
   lacc_finish(l, s);
   __syncthreads();
   acc_flush(s, acc + (size_t)frame * ACC_WORDS, tid, SCAN_THREADS);
@@ -385,6 +596,7 @@ struct jn_scan {
   // -g path scratch, allocated on first use and kept (no cudaMalloc per frame)
   uint8_t* dImg; size_t img_bytes; float* dXyz;
   int* dColBatch; int col_frames;   // batched -g path: per-column counts / offsets of n frames
+  double* dTab;                     // 4 x 256 table of the fast scan path (c.tab)
 };
 
 static int ensure_acc(jn_scan* s, int n) {
@@ -395,6 +607,10 @@ static int ensure_acc(jn_scan* s, int n) {
   s->cap_frames = n;
   return JN_OK;
 }
+
+static int g_scan_fast_override = -1;   // test hook (jn_debug_scan_fast): -1 default, 0 general expressions only
+extern "C" void jn_debug_scan_fast(int enable) { g_scan_fast_override = enable; }
+extern "C" int jn_scan_fast_path(const jn_scan* s) { return s ? s->c.fast_ok : 0; }
 
 extern "C" jn_scan* jn_scan_create(const jn_calib* cal, int width, int height, int ox, int oy, int device) {
   if (!cal || !cal->has_q || width <= 0 || height <= 0) { jn_set_error("jn_scan_create: bad arguments"); return nullptr; }
@@ -424,6 +640,26 @@ extern "C" jn_scan* jn_scan_create(const jn_calib* cal, int width, int height, i
   }
   gate_cache_kernel<<<dim3((width + 127) / 128, height), 128>>>(s->c, s->gate);
   g_jn_launches += 1;
+  // fast path of scan_kernel: reciprocal table, then the table division checked against the IEEE division
+  // for every numerator of this image size (JN_SCAN_FAST=0 keeps the general expressions)
+  s->c.fast_ok = 0;
+  s->c.tab = nullptr;
+  const char* fast_env = getenv("JN_SCAN_FAST");
+  const bool fast_off = g_scan_fast_override >= 0 ? g_scan_fast_override == 0 : (fast_env && fast_env[0] == '0');
+  if (s->c.q_simple && !fast_off) {
+    int* dOk = s->dTotal;
+    const int one = 1;
+    int ok = 0;
+    if (cudaMalloc(&s->dTab, 1024 * sizeof(double)) == cudaSuccess &&
+        cudaMemcpy(dOk, &one, sizeof(int), cudaMemcpyHostToDevice) == cudaSuccess) {
+      s->c.tab = s->dTab;
+      scan_tab_kernel<<<1, 256>>>(s->c, s->dTab);
+      const int m = width > height ? width : height;
+      scan_verify_kernel<<<(m + 127) / 128, 128>>>(s->c, s->dTab, dOk);
+      g_jn_launches += 2;
+      if (cudaMemcpy(&ok, dOk, sizeof(int), cudaMemcpyDeviceToHost) == cudaSuccess) s->c.fast_ok = ok;
+    }
+  }
   if (cudaDeviceSynchronize() != cudaSuccess) {
     jn_set_error("jn_scan_create: gate cache kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
     jn_scan_destroy(s);
@@ -435,7 +671,7 @@ extern "C" jn_scan* jn_scan_create(const jn_calib* cal, int width, int height, i
 extern "C" void jn_scan_destroy(jn_scan* s) {
   if (!s) return;
   cudaSetDevice(s->device);
-  cudaFree(s->dImg); cudaFree(s->dXyz); cudaFree(s->dColBatch);
+  cudaFree(s->dImg); cudaFree(s->dXyz); cudaFree(s->dColBatch); cudaFree(s->dTab);
   cudaFree(s->gate); cudaFree(s->acc); cudaFree(s->dD); cudaFree(s->dRanges); cudaFree(s->dMeta);
   cudaFree(s->dU8); cudaFree(s->dCol); cudaFree(s->dTotal); cudaFree(s->dPts);
   delete s;
@@ -456,9 +692,11 @@ extern "C" int jn_scan_from_disparity_batch(jn_scan* s, int n, const float* D, d
   int rc = ensure_acc(s, n);
   if (rc) return rc;
   acc_reset_kernel<<<(n * ACC_WORDS + 255) / 256, 256, 0, st>>>(s->acc, n);
-  const int rows_per_block = 16;
-  dim3 grid((s->c.W + SCAN_THREADS - 1) / SCAN_THREADS, (s->c.H + rows_per_block - 1) / rows_per_block, n);
-  scan_kernel<<<grid, SCAN_THREADS, 0, st>>>(s->c, D, s->gate, s->acc, dmap_u8, rows_per_block);
+  dim3 grid((s->c.W + SCAN_THREADS - 1) / SCAN_THREADS, (s->c.H + SCAN_ROWS - 1) / SCAN_ROWS, n);
+  if (s->c.fast_ok)
+    scan_kernel<true><<<grid, SCAN_THREADS, 0, st>>>(s->c, D, s->gate, s->acc, dmap_u8);
+  else
+    scan_kernel<false><<<grid, SCAN_THREADS, 0, st>>>(s->c, D, s->gate, s->acc, dmap_u8);
   scan_finalize_kernel<<<n, 96, 0, st>>>(s->acc, ranges, meta);
   g_jn_launches += 3;
   JN_CUDA_CHECK(cudaGetLastError());

@@ -27,7 +27,10 @@
 
 namespace {
 
-constexpr int MATCH_THREADS = 512;
+#ifndef JN_MATCH_THREADS
+#define JN_MATCH_THREADS 512
+#endif
+constexpr int MATCH_THREADS = JN_MATCH_THREADS;
 constexpr int KG = 4;   // candidates matched together by one warp
 constexpr int KEY_EMPTY = 0x7fffffff;
 
@@ -112,14 +115,47 @@ __device__ __forceinline__ void match_group(const Geo& g, const int (&u)[KG], un
   // candidate and lane.
   const int j_end = (phi - plo) >> 5;
   int j_lo = 0, j_hi = -1;
-  if (allok && ihi - ilo >= 31) {
+  // Wrapped tiling (the common case: four live candidates away from the image border, so all ranges
+  // have the same length Lr, a multiple of 32): candidate k scores position P of the shared grid if
+  // P >= p0[k] and position P + Lr otherwise -- both lie in its range, and over P = plo .. plo+Lr-1
+  // every position of every range is visited exactly once.  Only the chunks below the largest
+  // range start need per-candidate loads; no lane is ever masked and Lr/32 chunks replace the
+  // Lr/32 + 1 (two of them masked) of the union tiling.
+  const int Lr = p1[0] - p0[0] + 1;
+  bool wrap = allok && Lr >= 32 && (Lr & 31) == 0;
+#pragma unroll
+  for (int k = 1; k < KG; k++) wrap = wrap && (p1[k] - p0[k] + 1 == Lr);
+  int jw = 0;
+  if (wrap) {
+    jw = min(Lr >> 5, (ilo - plo + 31) >> 5);
+    j_lo = jw;
+    j_hi = (Lr >> 5) - 1;
+  } else if (allok && ihi - ilo >= 31) {
     j_lo = (ilo - plo + 31) >> 5;
     j_hi = (ihi - 31 - plo) >> 5;          // >= j_lo - 1; empty if the intersection holds no whole chunk
   }
 #pragma unroll 1
   for (int part = 0; part < 2; part++) {
-    // border chunks: [0, j_lo) before the middle, (j_hi, j_end] after it (everything if there is no middle)
     const bool mid = j_hi >= j_lo;
+    if (wrap) {
+      if (part == 0) {
+#pragma unroll 1
+        for (int j = 0; j < jw; j++) {
+          const int P = plo + 32 * j + lane;
+#pragma unroll
+          for (int k = 0; k < KG; k++) {
+            const int pk = P + ((P < p0[k]) ? Lr : 0);
+            const uint4 s0 = rowB_t[pk - 2], s1 = rowB_t[pk + 2], s2 = rowB_b[pk - 2], s3 = rowB_b[pk + 2];
+            unsigned e = sad16(a[k][0], s0, 0u);
+            e = sad16(a[k][1], s1, e);
+            e = sad16(a[k][2], s2, e);
+            e = sad16(a[k][3], s3, e);
+            best2_update(best[k], (int)e * 65536 + DIR * pk);
+          }
+        }
+      }
+    } else {
+    // border chunks: [0, j_lo) before the middle, (j_hi, j_end] after it (everything if there is no middle)
     const int jb = part ? (mid ? j_hi + 1 : 0) : 0, je = part ? j_end : (mid ? j_lo - 1 : -1);
 #pragma unroll 1
     for (int j = jb; j <= je; j++) {
@@ -137,6 +173,7 @@ __device__ __forceinline__ void match_group(const Geo& g, const int (&u)[KG], un
         // p0 > p1 for a candidate that is not ok: never in range
         best2_update(best[k], (lane_in && p >= p0[k] && p <= p1[k]) ? (int)e * 65536 + shift : KEY_EMPTY);
       }
+    }
     }
     if (part == 0 && mid) {
       // middle: every candidate live at every lane -> 4 loads, 64 SADs, 4 keys, 12 min/max per chunk
@@ -355,11 +392,75 @@ support_filter_kernel(Geo g, const int16_t* __restrict__ dcan_all, int32_t* __re
   // ---- inconsistent points: frontier propagation -----------------------------
   if (tid == 0) { s_n[0] = 0; s_n[1] = 0; }
   __syncthreads();
+  int cur = 0, rounds = 0;
+  const int later = r + r * (2 * r + 1);  // cells after p in scan order (u outer, v inner)
+  // Fast path: the whole propagation runs on shared memory.  Disparities (<= 255) and counters
+  // (<= (2r+1)^2 <= 255) are bytes, NP each, in the region the redundancy passes use afterwards; a
+  // counter is decremented with a 32-bit shared atomic on its word (a valid point's counter never
+  // drops below 1 -- it counts the point itself and only EARLIER neighbours are ever taken away -- so
+  // no borrow crosses into the next byte, and "counter >= 1" doubles as the validity flag).  A warp
+  // fetches 32 frontier points with one coalesced load and walks them with shuffles.
+  const bool fast = use_smem && g.p.disp_max <= 255 && (2 * r + 1) * (2 * r + 1) <= 255 && later <= 128;
+  if (fast) {
+    uint8_t* d8 = reinterpret_cast<uint8_t*>(s_wk);
+    uint8_t* c8 = d8 + ((NP + 3) & ~3);
+    unsigned* c32 = reinterpret_cast<unsigned*>(c8);
+    for (int p = tid; p < NP; p += T) {
+      const int d = dc[p], c = cnt[p];
+      d8[p] = (uint8_t)d;
+      c8[p] = (d >= 0) ? (uint8_t)c : (uint8_t)0;
+      if (d >= 0 && c < minsup) fr[0][atomicAdd(&s_n[0], 1)] = p;
+    }
+    // this lane's cells of the "later" half window: offsets (du, dv), up to four per lane
+    int cdu[4], cdv[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int c = lane + 32 * k;
+      if (c < r) { cdu[k] = 0; cdv[k] = c + 1; }
+      else { const int kk = c - r; cdu[k] = 1 + kk / (2 * r + 1); cdv[k] = kk % (2 * r + 1) - r; }
+      if (c >= later) cdu[k] = 1 << 20;     // never inside the lattice
+    }
+    __syncthreads();
+    while (true) {
+      const int n = s_n[cur];
+      if (n == 0) break;
+      rounds++;
+      for (int base = warp * 32; base < n; base += nwarps * 32) {
+        const int mq = (base + lane < n) ? fr[cur][base + lane] : 0;
+        const int mqd = d8[mq], mqu = mq % Wc, mqv = mq / Wc;
+        const int m = min(32, n - base);
+        for (int j = 0; j < m; j++) {
+          const int qd = __shfl_sync(0xffffffffu, mqd, j), qu = __shfl_sync(0xffffffffu, mqu, j),
+                    qv = __shfl_sync(0xffffffffu, mqv, j);
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const int pu = qu + cdu[k], pv = qv + cdv[k];
+            if (pu < Wc && pv >= 0 && pv < Hc) {
+              const int p = pv * Wc + pu;
+              if (c8[p] >= 1 && abs((int)d8[p] - qd) <= thr) {
+                const int sh = 8 * (p & 3);
+                const unsigned old = (atomicSub(&c32[p >> 2], 1u << sh) >> sh) & 0xffu;
+                if ((int)old == minsup) fr[cur ^ 1][atomicAdd(&s_n[cur ^ 1], 1)] = p;
+              }
+            }
+          }
+        }
+      }
+      __syncthreads();
+      if (tid == 0) s_n[cur] = 0;
+      cur ^= 1;
+      __syncthreads();
+    }
+    for (int p = tid; p < NP; p += T) {
+      const int d = dc[p];
+      st1[p] = (d >= 0 && (int)c8[p] >= minsup) ? (int16_t)d : (int16_t)-1;
+    }
+    __syncthreads();                       // the byte arrays are dead: the region becomes wk
+    for (int p = tid; p < NP; p += T) wk[p] = st1[p];
+  } else {
   for (int p = tid; p < NP; p += T)
     if (dc[p] >= 0 && cnt[p] < minsup) fr[0][atomicAdd(&s_n[0], 1)] = p;
   __syncthreads();
-  int cur = 0, rounds = 0;
-  const int later = r + r * (2 * r + 1);  // cells after p in scan order (u outer, v inner)
   while (true) {
     int n = s_n[cur];
     if (n == 0) break;
@@ -392,6 +493,7 @@ support_filter_kernel(Geo g, const int16_t* __restrict__ dcan_all, int32_t* __re
     int16_t o = (d >= 0 && cnt[p] >= minsup) ? (int16_t)d : (int16_t)-1;
     st1[p] = o;
     wk[p] = o;
+  }
   }
   __syncthreads();
 

@@ -403,6 +403,37 @@ def test_reprojection_matches_opencv_golden(jn):
     sc.close()
 
 
+def test_scan_fast_path_is_bit_identical_to_general_expressions(jn, synth):
+    """scan_kernel's fast path (table division verified at create time, float-filtered atan2) against the same
+    kernel evaluating every pixel with the general double expressions: every output byte equal, on a smooth
+    map, a noisy map and a map with d = 0 pixels behind a wrapped gate (H8)."""
+    import ctypes as C
+    fx = scan_lib.fixtures()
+    rng = np.random.default_rng(5)
+    for qname, W, H, oxy in (("640x480", 640, 480, (0, 0)), ("1920x1200_Kx3", 1920, 1200, (0, 0)),
+                             ("640x480", 600, 400, (17, 29))):
+        cal = jn.Calibration(scan_lib.CALIB_YML)
+        cal.set_q_matrix(fx["Q"][qname])
+        yy, xx = np.mgrid[0:H, 0:W]
+        maps = [(3 + 0.02 * xx + 0.11 * yy).astype(np.float32),
+                rng.uniform(-3, 260, (H, W)).astype(np.float32),
+                np.where(rng.random((H, W)) < 0.3, 0, rng.integers(0, 256, (H, W))).astype(np.float32)]
+        jn.lib().jn_debug_scan_fast(C.c_int(0))
+        slow = jn.ObstacleScan(cal, W, H, *oxy)
+        jn.lib().jn_debug_scan_fast(C.c_int(-1))
+        fast = jn.ObstacleScan(cal, W, H, *oxy)
+        assert slow.fast_path() == 0 and fast.fast_path() == 1
+        assert np.array_equal(slow.gate_cache(), fast.gate_cache())
+        for D in maps:
+            r0, m0, u0 = slow.from_disparity(D, want_u8=True)
+            r1, m1, u1 = fast.from_disparity(D, want_u8=True)
+            assert np.array_equal(r0.view(np.int64), r1.view(np.int64))
+            assert bytes(m0) == bytes(m1)
+            assert np.array_equal(u0, u1)
+            assert m1.n_points > 0
+        slow.close(); fast.close()
+
+
 def test_scan_batch_and_empty_map(jn):
     import torch
     fx = scan_lib.fixtures()
