@@ -286,6 +286,10 @@ class Runner:
         self.dRanges = torch.empty((B, 90), dtype=torch.float64, device=self.dev)
         self.dMeta = torch.empty((B, 5), dtype=torch.float64, device=self.dev)   # jn_scan_meta = 40 bytes
         self.dU8 = torch.empty((B, self.H, self.W), dtype=torch.uint8, device=self.dev)
+        # second output set: two rolling submissions are in flight at a time
+        self.dOut = [(self.dD1, self.dStatus, self.dRanges, self.dMeta, self.dU8),
+                     (torch.empty_like(self.dD1), torch.zeros_like(self.dStatus), torch.empty_like(self.dRanges),
+                      torch.empty_like(self.dMeta), torch.empty_like(self.dU8))]
         # host result buffers of the end-to-end path, one set per in-flight submission
         self.hRanges = [torch.empty((B, 90), dtype=torch.float64).pin_memory() for _ in range(2)]
         self.hMeta = [torch.empty((B, 5), dtype=torch.float64).pin_memory() for _ in range(2)]
@@ -307,6 +311,16 @@ class Runner:
                                 self.dStatus.data_ptr(), self.dims, B, self.stream.cuda_stream)
         self.scan.from_disparity_batch(B, self.dD1.data_ptr(), self.dRanges.data_ptr(), self.dMeta.data_ptr(),
                                        self.dU8.data_ptr(), self.stream.cuda_stream)
+
+    def step_resident_rolling(self, k=0):
+        """Device-resident frames through jn_stereo_scan_submit_device: the same kernels as step_resident, queued
+        on the library's rolling sub-batch streams (no fork/join on a caller stream between steps)."""
+        B, n = self.B, self.W * self.H
+        D1, st, rg, mt, u8 = self.dOut[self.it & 1]
+        self.it += 1
+        self.elas.stereo_scan_submit_device(self.scan, B, self.dL.data_ptr() + k * B * n, self.dR.data_ptr() + k * B * n,
+                                            self.dims, D1.data_ptr(), st.data_ptr(), rg.data_ptr(), mt.data_ptr(),
+                                            u8.data_ptr())
 
     def step_e2e_scans(self, k=0):
         """Same call, the optional u8 disparity maps not requested: scans, meta and status come back."""
@@ -358,8 +372,12 @@ class Runner:
             for s in range(max(warmup, 3)):
                 self.step_resident(s % self.nb)
         torch.cuda.synchronize()
+        self.ms_forkjoin = self.timed(self.step_resident, steps)     # stream API: fork/join on the caller's stream
+        for s in range(max(warmup, 3)):
+            self.step_resident_rolling(s % self.nb)
+        self.elas.stereo_scan_wait()
         l0 = jn.launch_count()
-        ms = self.timed(self.step_resident, steps)
+        ms = self.timed(self.step_resident_rolling, steps, self.elas.stereo_scan_wait)
         launches = jn.launch_count() - l0
         for s in range(3):
             self.step_e2e(s % self.nb)
@@ -564,6 +582,12 @@ def run_ours(a):
                    "parallelism": "frames sharded across %d GPU(s), no data-path collective" % world,
                    "total_frames": a.total_frames or None},
         "mpix_per_s": value * n / 1e6, "ms_per_frame": ms / steps / B,
+        "value_what": "device-resident image pairs through jn_stereo_scan_submit_device / _wait (ELAS + scan kernels on "
+                      "the library's rolling sub-batch streams, two submissions in flight, outputs stay on the device)",
+        "stream_api": {"value": world * frames_done / (run.ms_forkjoin / 1000.0), "unit": UNIT,
+                       "ms_per_step": run.ms_forkjoin / steps,
+                       "what": "same frames through jn_elas_process_batch + jn_scan_from_disparity_batch on one caller "
+                               "stream (sub-batches fork from and join back into it every step)"},
         "frames_ok": int((status == 0).sum()), "frames_few_support": int((status == 1).sum()),
         "e2e": {"value": e2e_scans, "unit": UNIT, "h2d_bytes_per_step": run.h2d, "d2h_bytes_per_step": B * (90 * 8 + 40 + 4),
                 "ms_per_step": run.ms_e2e_scans / steps,

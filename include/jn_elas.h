@@ -204,6 +204,16 @@ int jn_stereo_scan_submit(jn_elas* e, jn_scan* s, int n, const uint8_t* I1, cons
                           const int32_t dims[3], float* D1, int32_t* status, double* ranges,
                           jn_scan_meta* meta, uint8_t* dmap_u8);
 int jn_stereo_scan_wait(jn_elas* e);
+/* The same pipeline for frames already in DEVICE memory (no copies, no caller stream): I1/I2 must be
+ * complete when the call is made; D1 (n*W*H floats), status (n int32), ranges (n*90 doubles) and meta (n)
+ * are device buffers too and required, dmap_u8 (n*W*H) is optional.  Submissions in flight need their own
+ * output buffers; everything passed belongs to the library until jn_stereo_scan_wait returns.
+ * Both submit calls cut a batch into sub-batches that roll through persistent internal streams one stage
+ * apart (JN_ELAS_SPLIT sub-batches, default 2), across consecutive submissions as well: call
+ * jn_stereo_scan_wait before using the handle through any other entry point. */
+int jn_stereo_scan_submit_device(jn_elas* e, jn_scan* s, int n, const uint8_t* I1, const uint8_t* I2,
+                                 const int32_t dims[3], float* D1, int32_t* status, double* ranges,
+                                 jn_scan_meta* meta, uint8_t* dmap_u8);
 
 /* -g path: every pixel with u8 disparity >= 2 -> robot-frame XYZ (double,
  * 3 per point, pixel order columns-outer like the reference) and the scan

@@ -122,6 +122,7 @@ def lib():
         _ss = [_P, _P, C.c_int, _P, _P, C.POINTER(C.c_int32), _P, _P, _P, _P, _P]
         l.jn_stereo_scan_batch_host.argtypes = _ss
         l.jn_stereo_scan_submit.argtypes = _ss
+        l.jn_stereo_scan_submit_device.argtypes = _ss
         l.jn_stereo_scan_wait.argtypes = [_P]
         l.jn_rectify_create.restype = _P
         l.jn_rectify_create.argtypes = [_P, _P, C.c_int32, C.c_int32, C.c_int32]
@@ -202,6 +203,15 @@ class Elas:
         P = lambda x: _P(int(x)) if x else None
         return _check(f(self._h, scan._h, int(n), P(I1), P(I2), d, P(D1), P(status), P(ranges), P(meta), P(dmap_u8)),
                       "jn_stereo_scan_submit")
+
+    def stereo_scan_submit_device(self, scan, n, I1, I2, dims, D1, status, ranges, meta, dmap_u8=0):
+        """Like stereo_scan_submit with every buffer in DEVICE memory (addresses as ints); no copies, no
+        caller stream: inputs complete at call time, results valid after stereo_scan_wait()."""
+        d = (C.c_int32 * 3)(*[int(x) for x in dims])
+        P = lambda x: _P(int(x)) if x else None
+        return _check(lib().jn_stereo_scan_submit_device(self._h, scan._h, int(n), P(I1), P(I2), d, P(D1), P(status),
+                                                         P(ranges), P(meta), P(dmap_u8)),
+                      "jn_stereo_scan_submit_device")
 
     def stereo_scan_wait(self):
         return _check(lib().jn_stereo_scan_wait(self._h), "jn_stereo_scan_wait")

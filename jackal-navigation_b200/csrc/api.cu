@@ -73,6 +73,11 @@ struct DevRes {
   unsigned long long submits;   // buffer parity of the next submission
   cudaStream_t s_in, s_out;
   cudaEvent_t ev_in[2], ev_done[2], ev_out[2], ev_copied[2];
+  // rolling pipeline of the submit entry points: one persistent stream per lane (= sub-batch slot with its
+  // own workspace); a lane's parts follow each other across submissions without any stream joining them
+  cudaStream_t lane[JN_MAX_PARTS];
+  cudaEvent_t ev_lstag[JN_MAX_PARTS];        // lane k's current part is past the stagger stage
+  cudaEvent_t ev_ldone[2][JN_MAX_PARTS];     // lane k finished its part of the submission using buffer set b
   // optional per-stage timing with CUDA events on the launching stream
   cudaEvent_t ev[JN_PROFILE_STAGES + 1];
 };
@@ -159,6 +164,11 @@ static void devres_free(DevRes* r) {
   if (r->ev_fork) cudaEventDestroy(r->ev_fork);
   for (int k = 0; k < JN_MAX_PARTS; k++)
     if (r->hi[k]) { cudaStreamDestroy(r->hi[k]); cudaEventDestroy(r->ev_hi_in[k]); cudaEventDestroy(r->ev_hi_out[k]); }
+  for (int k = 0; k < JN_MAX_PARTS; k++)
+    if (r->lane[k]) {
+      cudaStreamDestroy(r->lane[k]); cudaEventDestroy(r->ev_lstag[k]);
+      cudaEventDestroy(r->ev_ldone[0][k]); cudaEventDestroy(r->ev_ldone[1][k]);
+    }
   if (r->own) cudaStreamDestroy(r->own);
   if (r->s_in) cudaStreamDestroy(r->s_in);
   if (r->s_out) cudaStreamDestroy(r->s_out);
@@ -618,6 +628,79 @@ static int ensure_chunks(jn_elas* e, const int32_t dims[3], int n) {
 }
 
 struct jn_scan;
+int jn_scan_batch_at(jn_scan* s, int acc_frame0, int n, const float* D, double* ranges, jn_scan_meta* meta,
+                     uint8_t* dmap_u8, cudaStream_t st);
+int jn_scan_reserve(jn_scan* s, int n);
+
+static int ensure_lanes(DevRes* r, int K) {
+  int lo_p = 0, hi_p = 0;
+  cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p);
+  for (int k = 0; k < K; k++) {
+    if (!r->lane[k]) {
+      JN_CUDA_CHECK(cudaStreamCreateWithFlags(&r->lane[k], cudaStreamNonBlocking));
+      JN_CUDA_CHECK(cudaEventCreateWithFlags(&r->ev_lstag[k], cudaEventDisableTiming));
+      JN_CUDA_CHECK(cudaEventCreateWithFlags(&r->ev_ldone[0][k], cudaEventDisableTiming));
+      JN_CUDA_CHECK(cudaEventCreateWithFlags(&r->ev_ldone[1][k], cudaEventDisableTiming));
+    }
+    if (!r->hi[k]) {
+      JN_CUDA_CHECK(cudaStreamCreateWithPriority(&r->hi[k], cudaStreamNonBlocking, hi_p));
+      JN_CUDA_CHECK(cudaEventCreateWithFlags(&r->ev_hi_in[k], cudaEventDisableTiming));
+      JN_CUDA_CHECK(cudaEventCreateWithFlags(&r->ev_hi_out[k], cudaEventDisableTiming));
+    }
+  }
+  return JN_OK;
+}
+
+// One submission of n frames (device buffers) as K parts on the K lanes.  Lane k waits for `ready`
+// (inputs there, output buffers free), for its own previous part (stream order) and for the previous
+// part in the rolling order -- lane k-1 of this submission, or the last lane of the previous one -- to be
+// past support matching: at any time the parts in flight are in DIFFERENT stages, so the latency-bound
+// stages of one (support filter, Delaunay, planes + grid: a CTA or two per frame, on a high-priority
+// stream) run next to a throughput-bound stage of another, and -- unlike a fork/join on the caller's
+// stream -- the tail of one submission overlaps the head of the next.  ELAS, the zero map of an
+// unmatched frame and the scan of a part all run on its lane; ev_ldone[b][k] marks its end.
+static int run_rolling(jn_elas* e, jn_scan* sc, int n, int b, const uint8_t* I1, const uint8_t* I2, float* D,
+                       int32_t* status, double* ranges, jn_scan_meta* meta, uint8_t* u8, cudaEvent_t* ready,
+                       int n_ready) {
+  DevRes* r = e->r;
+  const Geo& g = r->g;
+  const int K = (e->parts < n) ? e->parts : n;
+  const int Bx = (K > 1) ? n / K : 0, B0 = n - (K - 1) * Bx;
+  const size_t pix = (size_t)g.Wd * g.Hd, ibytes = (size_t)g.bpl * g.H;
+  int rc = ensure_lanes(r, K);
+  if (rc) return rc;
+  if ((rc = jn_scan_reserve(sc, n))) return rc;
+  for (int k = 0; k < K; k++) {
+    cudaStream_t L = r->lane[k], hk = r->hi[k];
+    Workspace& wk = k ? r->wsx[k - 1] : r->ws;
+    const int Bk = k ? Bx : B0;
+    const size_t f0 = k ? (size_t)B0 + (size_t)(k - 1) * Bx : 0;
+    for (int i = 0; i < n_ready; i++) JN_CUDA_CHECK(cudaStreamWaitEvent(L, ready[i], 0));
+    if (K > 1) JN_CUDA_CHECK(cudaStreamWaitEvent(L, r->ev_lstag[(k + K - 1) % K], 0));   // never recorded yet: no-op
+    launch_descriptor(g, Bk, I1 + f0 * ibytes, I2 + f0 * ibytes, wk, L);
+    if ((rc = launch_support_match(g, Bk, wk, L))) return rc;
+    JN_CUDA_CHECK(cudaEventRecord(r->ev_lstag[k], L));
+    JN_CUDA_CHECK(cudaEventRecord(r->ev_hi_in[k], L));
+    JN_CUDA_CHECK(cudaStreamWaitEvent(hk, r->ev_hi_in[k], 0));
+    if ((rc = launch_support_filter(g, Bk, wk, hk))) return rc;
+    if ((rc = launch_delaunay(g, Bk, wk, hk))) return rc;
+    launch_planes_grid(g, Bk, wk, hk);
+    JN_CUDA_CHECK(cudaEventRecord(r->ev_hi_out[k], hk));
+    JN_CUDA_CHECK(cudaStreamWaitEvent(L, r->ev_hi_out[k], 0));
+    launch_raster(g, Bk, wk, L);
+    launch_dense_match(g, Bk, wk, L);
+    launch_post(g, Bk, wk, D + f0 * pix, nullptr, status + f0, L);
+    zero_unmatched_kernel<<<dim3(64, Bk), 256, 0, L>>>(D + f0 * pix, status + f0, pix);
+    g_jn_launches += 1;
+    if ((rc = jn_scan_batch_at(sc, (int)f0, Bk, D + f0 * pix, ranges + f0 * JN_SCAN_BINS, meta + f0,
+                               u8 ? u8 + f0 * pix : nullptr, L)))
+      return rc;
+    JN_CUDA_CHECK(cudaEventRecord(r->ev_ldone[b][k], L));
+  }
+  JN_CUDA_CHECK(cudaGetLastError());
+  return K;
+}
+
 extern "C" int jn_stereo_scan_submit(jn_elas* e, jn_scan* sc, int n, const uint8_t* I1, const uint8_t* I2,
                                      const int32_t dims[3], float* D1, int32_t* status, double* ranges,
                                      jn_scan_meta* meta, uint8_t* dmap_u8) {
@@ -633,24 +716,20 @@ extern "C" int jn_stereo_scan_submit(jn_elas* e, jn_scan* sc, int n, const uint8
   if ((rc = ensure_chunks(e, dims, n))) return rc;
   const int k = (int)(r->submits++ & 1);
   const size_t img = (size_t)dims[2] * dims[1], pix = (size_t)r->g.Wd * r->g.Hd;
-  // H2D of this call's frames as soon as buffer k is free again (the kernels of call i-2 are done with it)
+  // H2D of this call's frames as soon as buffer set k is free again (the lanes of call i-2 are done with it)
   JN_CUDA_CHECK(cudaStreamWaitEvent(r->s_in, r->ev_done[k], 0));
   JN_CUDA_CHECK(cudaMemcpyAsync(r->cI[k][0], I1, img * n, cudaMemcpyHostToDevice, r->s_in));
   JN_CUDA_CHECK(cudaMemcpyAsync(r->cI[k][1], I2, img * n, cudaMemcpyHostToDevice, r->s_in));
   JN_CUDA_CHECK(cudaEventRecord(r->ev_in[k], r->s_in));
   // compute: inputs arrived, outputs of call i-2 already read back
-  JN_CUDA_CHECK(cudaStreamWaitEvent(r->own, r->ev_in[k], 0));
-  JN_CUDA_CHECK(cudaStreamWaitEvent(r->own, r->ev_copied[k], 0));
-  rc = run_pipeline(e, n, r->cI[k][0], r->cI[k][1], r->cD[k], nullptr, r->cStatus[k], r->own);
-  if (rc) return rc;
-  zero_unmatched_kernel<<<dim3(64, n), 256, 0, r->own>>>(r->cD[k], r->cStatus[k], pix);
-  g_jn_launches += 1;
-  rc = jn_scan_from_disparity_batch(sc, n, r->cD[k], r->cRanges[k], r->cMeta[k], dmap_u8 ? r->cU8[k] : nullptr, r->own);
-  if (rc) return rc;
-  JN_CUDA_CHECK(cudaEventRecord(r->ev_done[k], r->own));
-  JN_CUDA_CHECK(cudaEventRecord(r->ev_out[k], r->own));
-  // D2H of the results
-  JN_CUDA_CHECK(cudaStreamWaitEvent(r->s_out, r->ev_out[k], 0));
+  cudaEvent_t ready[2] = {r->ev_in[k], r->ev_copied[k]};
+  const int K = run_rolling(e, sc, n, k, r->cI[k][0], r->cI[k][1], r->cD[k], r->cStatus[k], r->cRanges[k], r->cMeta[k],
+                            dmap_u8 ? r->cU8[k] : nullptr, ready, 2);
+  if (K < 0) return K;
+  // the staging buffers are free / the results complete when every lane is done with its part: the copy
+  // stream collects the lanes, nothing else does
+  for (int j = 0; j < K; j++) JN_CUDA_CHECK(cudaStreamWaitEvent(r->s_out, r->ev_ldone[k][j], 0));
+  JN_CUDA_CHECK(cudaEventRecord(r->ev_done[k], r->s_out));
   JN_CUDA_CHECK(cudaMemcpyAsync(ranges, r->cRanges[k], (size_t)n * JN_SCAN_BINS * sizeof(double), cudaMemcpyDeviceToHost, r->s_out));
   JN_CUDA_CHECK(cudaMemcpyAsync(meta, r->cMeta[k], (size_t)n * sizeof(jn_scan_meta), cudaMemcpyDeviceToHost, r->s_out));
   if (status) JN_CUDA_CHECK(cudaMemcpyAsync(status, r->cStatus[k], n * sizeof(int32_t), cudaMemcpyDeviceToHost, r->s_out));
@@ -660,12 +739,35 @@ extern "C" int jn_stereo_scan_submit(jn_elas* e, jn_scan* sc, int n, const uint8
   return JN_OK;
 }
 
+// The same rolling pipeline for frames that already live in DEVICE memory: no copies, no caller stream.
+// I1/I2 must be complete when the call is made and -- like every buffer passed here -- stay untouched until
+// jn_stereo_scan_wait returns; submissions in flight need their own output buffers.  D1 (n*W*H floats),
+// status (n), ranges (n*90), meta (n) are required, dmap_u8 (n*W*H) is optional.
+extern "C" int jn_stereo_scan_submit_device(jn_elas* e, jn_scan* sc, int n, const uint8_t* I1, const uint8_t* I2,
+                                            const int32_t dims[3], float* D1, int32_t* status, double* ranges,
+                                            jn_scan_meta* meta, uint8_t* dmap_u8) {
+  if (!e || !sc || n <= 0 || !I1 || !I2 || !dims || !D1 || !status || !ranges || !meta) {
+    jn_set_error("jn_stereo_scan_submit_device: bad arguments");
+    return JN_ERR_ARG;
+  }
+  if (e->p.subsampling) { jn_set_error("jn_stereo_scan_submit_device: the obstacle scan takes full-resolution maps"); return JN_ERR_UNSUPPORTED; }
+  int rc = ensure_workspace(e, dims, n);
+  if (rc) return rc;
+  DevRes* r = e->r;
+  if ((rc = ensure_own_stream(r))) return rc;
+  const int k = (int)(r->submits++ & 1);
+  const int K = run_rolling(e, sc, n, k, I1, I2, D1, status, ranges, meta, dmap_u8, nullptr, 0);
+  return K < 0 ? K : JN_OK;
+}
+
 // Blocks until every submitted batch has landed in the caller's buffers.
 extern "C" int jn_stereo_scan_wait(jn_elas* e) {
-  if (!e || !e->r->s_out) return JN_ERR_ARG;
+  if (!e) return JN_ERR_ARG;
   JN_CUDA_CHECK(cudaSetDevice(e->device));
-  JN_CUDA_CHECK(cudaStreamSynchronize(e->r->s_out));
-  JN_CUDA_CHECK(cudaStreamSynchronize(e->r->own));
+  if (e->r->s_out) JN_CUDA_CHECK(cudaStreamSynchronize(e->r->s_out));
+  for (int k = 0; k < JN_MAX_PARTS; k++)
+    if (e->r->lane[k]) JN_CUDA_CHECK(cudaStreamSynchronize(e->r->lane[k]));
+  if (e->r->own) JN_CUDA_CHECK(cudaStreamSynchronize(e->r->own));
   return JN_OK;
 }
 

@@ -84,8 +84,12 @@ __global__ void gate_cache_kernel(ScanConst c, uint8_t* __restrict__ gate) {
   gate[2 * ((size_t)j * c.W + i) + 1] = 255;
 }
 
-// per-frame accumulator: 90 range keys, then angle min/max, range min/max keys, n_points
-constexpr int ACC_WORDS = JN_SCAN_BINS + 5;
+// per-frame accumulator: 90 range keys, then angle min/max, range min/max keys, n_points, and one word
+// holding the running FLOAT extrema of the angle (fkey(min) in the low half, fkey(max) in the high half):
+// CTAs of the fast scan kernel start from what earlier CTAs of the frame have seen, so only points near the
+// frame's extrema are ever evaluated in double
+constexpr int ACC_WORDS = JN_SCAN_BINS + 6;
+constexpr int ACC_FEXT = JN_SCAN_BINS + 5;
 
 struct BlockAcc {
   unsigned long long bins[JN_SCAN_BINS];
@@ -194,6 +198,7 @@ __global__ void acc_reset_kernel(unsigned long long* acc, int n_frames) {
   int k = i % ACC_WORDS;
   unsigned long long v = ~0ull;
   if (k == JN_SCAN_BINS + 1 || k == JN_SCAN_BINS + 3 || k == JN_SCAN_BINS + 4) v = 0ull;
+  if (k == ACC_FEXT) v = 0x807fffff7f800000ull;     // fkey(-inf) : fkey(+inf)
   acc[i] = v;
 }
 
@@ -263,9 +268,11 @@ struct FastAcc {
   float camin, camax;      // float angle of the deferred candidates (+/-inf: none)
   double minX, minY, maxX, maxY;
 };
-__device__ __forceinline__ void facc_init(FastAcc& f) {
-  f.fmin = __int_as_float(0x7f800000); f.fmax = __int_as_float(0xff800000);
-  f.camin = f.fmin; f.camax = f.fmax;
+__device__ __forceinline__ float fkey_inv(int k) { return __int_as_float(k >= 0 ? k : (k ^ 0x7fffffff)); }
+// the running extrema start from the frame's (any float angle of a real point is a valid bound); no candidates yet
+__device__ __forceinline__ void facc_init(FastAcc& f, int kmin, int kmax) {
+  f.fmin = fkey_inv(kmin); f.fmax = fkey_inv(kmax);
+  f.camin = __int_as_float(0x7f800000); f.camax = __int_as_float(0xff800000);
   f.minX = f.minY = f.maxX = f.maxY = 0.0;
 }
 
@@ -315,7 +322,7 @@ __device__ __forceinline__ void lacc_add_fast(LocalAcc& l, FastAcc& f, BlockAcc&
 }
 
 // the deferred candidates: only those within ANG_MARGIN of the CTA's float extremum can be the extremum
-__device__ __forceinline__ void facc_finish(LocalAcc& l, FastAcc& f, int* s_fext) {
+__device__ __forceinline__ void facc_finish(LocalAcc& l, FastAcc& f, int* s_fext, unsigned long long* g_fext) {
   float wmin = f.fmin, wmax = f.fmax;
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) {
@@ -328,9 +335,11 @@ __device__ __forceinline__ void facc_finish(LocalAcc& l, FastAcc& f, int* s_fext
   }
   __syncthreads();
   const int kmin = s_fext[0], kmax = s_fext[1];
-  // keys are monotone in the float, so compare floats recovered from the keys
-  const float bmin = __int_as_float(kmin >= 0 ? kmin : (kmin ^ 0x7fffffff));
-  const float bmax = __int_as_float(kmax >= 0 ? kmax : (kmax ^ 0x7fffffff));
+  if (threadIdx.x == 0) {
+    atomicMin(reinterpret_cast<int*>(g_fext), kmin);
+    atomicMax(reinterpret_cast<int*>(g_fext) + 1, kmax);
+  }
+  const float bmin = fkey_inv(kmin), bmax = fkey_inv(kmax);
   if (f.camin <= bmin + ANG_MARGIN && f.camin < __int_as_float(0x7f800000)) {   // +inf: no candidate
     const unsigned long long kt = okey(atan2(f.minY, f.minX));
     l.amin = min(l.amin, kt);
@@ -349,7 +358,7 @@ __device__ __forceinline__ void facc_finish(LocalAcc& l, FastAcc& f, int* s_fext
 // row loop then never waits for memory -- with a load at the top of every iteration the kernel was bound
 // by memory latency, not by its arithmetic).  FAST: see above (c.fast_ok); a pixel with d = 0 (only
 // reachable through a wrapped gate, H8) divides by zero and takes the general expressions.
-constexpr int SCAN_ROWS = 16;
+constexpr int SCAN_ROWS = 32;
 
 template <bool FAST>
 __global__ void __launch_bounds__(SCAN_THREADS)
@@ -362,39 +371,46 @@ scan_kernel(ScanConst c, const float* __restrict__ D, const uint8_t* __restrict_
   const int i = blockIdx.x * SCAN_THREADS + tid;
   const size_t fp = (size_t)frame * c.W * c.H;
   const int j0 = blockIdx.y * SCAN_ROWS;
-  __shared__ float s_dv[SCAN_ROWS][SCAN_THREADS];
+  __shared__ uint8_t s_dv[SCAN_ROWS][SCAN_THREADS];   // u8 disparities (convertTo(CV_8U)) of the tile
   __shared__ unsigned short s_gv[SCAN_ROWS][SCAN_THREADS];
+  const int rows = min(SCAN_ROWS, c.H - j0);
+  unsigned long long* facc = acc + (size_t)frame * ACC_WORDS;
   if (i < c.W) {
-    const unsigned short* gate2 = reinterpret_cast<const unsigned short*>(gate);
+    const float* dp = D + fp + (size_t)j0 * c.W + i;
+    const unsigned short* gp = reinterpret_cast<const unsigned short*>(gate) + (size_t)j0 * c.W + i;
     float dv[SCAN_ROWS];
     unsigned short gv[SCAN_ROWS];
 #pragma unroll
     for (int r = 0; r < SCAN_ROWS; r++) {
-      const int j = j0 + r;
-      const size_t a = (size_t)min(j, c.H - 1) * c.W + i;
-      dv[r] = D[fp + a];
-      gv[r] = (j < c.H) ? gate2[a] : (unsigned short)0x00ffu;   // g0 = 255, g1 = 0: nothing passes
+      dv[r] = 0.f;
+      gv[r] = 0;
+      if (r < rows) { dv[r] = dp[r * c.W]; gv[r] = gp[r * c.W]; }
     }
 #pragma unroll
-    for (int r = 0; r < SCAN_ROWS; r++) { s_dv[r][tid] = dv[r]; s_gv[r][tid] = gv[r]; }
+    for (int r = 0; r < SCAN_ROWS; r++) { s_dv[r][tid] = (uint8_t)to_u8(dv[r]); s_gv[r][tid] = gv[r]; }
   }
   acc_init(s, tid, SCAN_THREADS);
   if (FAST) {
     for (int k = tid; k < 1024; k += SCAN_THREADS) s_tab[k] = c.tab[k];
-    if (tid == 0) { s_fext[0] = 0x7f800000; s_fext[1] = (int)0x807fffff; }   // fkey(+inf), fkey(-inf)
+    if (tid == 0) {
+      const unsigned long long w = __ldcg(facc + ACC_FEXT);
+      s_fext[0] = (int)(unsigned)w;
+      s_fext[1] = (int)(unsigned)(w >> 32);
+    }
   }
   __syncthreads();
   LocalAcc l;
   lacc_init(l);
   FastAcc f;
-  facc_init(f);
+  facc_init(f, FAST ? s_fext[0] : 0x7f800000, FAST ? s_fext[1] : (int)0x807fffff);
   if (i < c.W) {
     const double px = (double)(i + c.ox) + c.Q[3];
+    uint8_t* up = dmap_u8 ? dmap_u8 + fp + (size_t)j0 * c.W + i : nullptr;
 #pragma unroll 1
-    for (int r = 0; r < SCAN_ROWS; r++) {
+    for (int r = 0; r < rows; r++) {
       const int j = j0 + r;
-      const int d = to_u8(s_dv[r][tid]);          // own column only: no barrier needed for these
-      if (dmap_u8 && j < c.H) dmap_u8[fp + (size_t)j * c.W + i] = (uint8_t)d;
+      const int d = s_dv[r][tid];
+      if (up) up[r * c.W] = (uint8_t)d;
       const unsigned gq = s_gv[r][tid];
       const int g0 = gq & 0xff, g1 = gq >> 8;
       if (d < g0 || d > g1) continue;
@@ -412,7 +428,7 @@ scan_kernel(ScanConst c, const float* __restrict__ D, const uint8_t* __restrict_
       }
     }
   }
-  if (FAST) facc_finish(l, f, s_fext);
+  if (FAST) facc_finish(l, f, s_fext, facc + ACC_FEXT);
   lacc_finish(l, s);
   __syncthreads();
   acc_flush(s, acc + (size_t)frame * ACC_WORDS, tid, SCAN_THREADS);
@@ -684,23 +700,36 @@ extern "C" int jn_scan_gate_cache(jn_scan* s, uint8_t* out) {
   return JN_OK;
 }
 
-extern "C" int jn_scan_from_disparity_batch(jn_scan* s, int n, const float* D, double* ranges, jn_scan_meta* meta,
-                                            uint8_t* dmap_u8, void* stream) {
-  if (!s || n <= 0 || !D || !ranges || !meta) return JN_ERR_ARG;
-  cudaStream_t st = (cudaStream_t)stream;
-  JN_CUDA_CHECK(cudaSetDevice(s->device));
-  int rc = ensure_acc(s, n);
-  if (rc) return rc;
-  acc_reset_kernel<<<(n * ACC_WORDS + 255) / 256, 256, 0, st>>>(s->acc, n);
+// n frames on `stream`, accumulators acc_frame0 .. acc_frame0 + n - 1 (two calls on different streams must
+// use disjoint accumulator ranges; jn_scan_reserve sizes the array beforehand)
+int jn_scan_batch_at(jn_scan* s, int acc_frame0, int n, const float* D, double* ranges, jn_scan_meta* meta,
+                     uint8_t* dmap_u8, cudaStream_t st) {
+  if (acc_frame0 + n > s->cap_frames) { jn_set_error("jn_scan_batch_at: accumulators not reserved"); return JN_ERR_ARG; }
+  unsigned long long* acc = s->acc + (size_t)acc_frame0 * ACC_WORDS;
+  acc_reset_kernel<<<(n * ACC_WORDS + 255) / 256, 256, 0, st>>>(acc, n);
   dim3 grid((s->c.W + SCAN_THREADS - 1) / SCAN_THREADS, (s->c.H + SCAN_ROWS - 1) / SCAN_ROWS, n);
   if (s->c.fast_ok)
-    scan_kernel<true><<<grid, SCAN_THREADS, 0, st>>>(s->c, D, s->gate, s->acc, dmap_u8);
+    scan_kernel<true><<<grid, SCAN_THREADS, 0, st>>>(s->c, D, s->gate, acc, dmap_u8);
   else
-    scan_kernel<false><<<grid, SCAN_THREADS, 0, st>>>(s->c, D, s->gate, s->acc, dmap_u8);
-  scan_finalize_kernel<<<n, 96, 0, st>>>(s->acc, ranges, meta);
+    scan_kernel<false><<<grid, SCAN_THREADS, 0, st>>>(s->c, D, s->gate, acc, dmap_u8);
+  scan_finalize_kernel<<<n, 96, 0, st>>>(acc, ranges, meta);
   g_jn_launches += 3;
   JN_CUDA_CHECK(cudaGetLastError());
   return JN_OK;
+}
+int jn_scan_reserve(jn_scan* s, int n) {
+  JN_CUDA_CHECK(cudaSetDevice(s->device));
+  if (n > s->cap_frames) JN_CUDA_CHECK(cudaDeviceSynchronize());   // the array is replaced: nothing may still use it
+  return ensure_acc(s, n);
+}
+
+extern "C" int jn_scan_from_disparity_batch(jn_scan* s, int n, const float* D, double* ranges, jn_scan_meta* meta,
+                                            uint8_t* dmap_u8, void* stream) {
+  if (!s || n <= 0 || !D || !ranges || !meta) return JN_ERR_ARG;
+  JN_CUDA_CHECK(cudaSetDevice(s->device));
+  int rc = ensure_acc(s, n);
+  if (rc) return rc;
+  return jn_scan_batch_at(s, 0, n, D, ranges, meta, dmap_u8, (cudaStream_t)stream);
 }
 
 extern "C" int jn_scan_from_disparity(jn_scan* s, const float* D, double ranges[JN_SCAN_BINS], jn_scan_meta* meta,

@@ -497,42 +497,76 @@ support_filter_kernel(Geo g, const int16_t* __restrict__ dcan_all, int32_t* __re
   }
   __syncthreads();
 
-  // ---- redundant points, vertical pass (dependencies along a column only) ------
+  // ---- redundant points (elas.cpp:181-235): a point goes if it has a similar point within md cells on
+  // BOTH sides along the line; the pass runs in place, so the "before" side sees this pass's removals
+  // and the "after" side does not.  The "after" test therefore only needs the state at the start of the
+  // pass: it is evaluated for all points in parallel and parked in bit 14 of the entry (d < 4096); the
+  // serial walk along each line then carries the last md decided entries in registers and touches
+  // shared memory once per cell -- no data-dependent inner loops, no divergence.
   const int md = 5, rt = 1;  // redun_max_dist, redun_threshold (elas.cpp:421-422)
+  constexpr int FLAG = 0x4000, DMASK = 0x3fff;
+  // vertical pass: lines = columns
+  for (int p = tid; p < NP; p += T) {
+    const int e = wk[p];
+    if (e < 0) continue;
+    bool after = false;
+#pragma unroll
+    for (int j = 1; j <= md; j++) {
+      const int q = p + j * Wc;
+      if (q < NP) {
+        const int e2 = wk[q];            // its flag may or may not be set yet: masked
+        after = after || (e2 >= 0 && abs(e - (e2 & DMASK)) <= rt);
+      }
+    }
+    if (after) wk[p] = (int16_t)(e | FLAG);
+  }
+  __syncthreads();
   for (int u = tid; u < Wc; u += T) {
+    int r1 = -1, r2 = -1, r3 = -1, r4 = -1, r5 = -1;   // decided entries v-1 .. v-5
     for (int v = 0; v < Hc; v++) {
-      int d = wk[v * Wc + u];
-      if (d < 0) continue;
-      bool up = false, down = false;
-      for (int j = 1; j <= md && v - j >= 0; j++) {
-        int d2 = wk[(v - j) * Wc + u];
-        if (d2 >= 0 && abs(d - d2) <= rt) { up = true; break; }
+      const int e = wk[v * Wc + u];
+      int cur = -1;
+      if (e >= 0) {
+        const int d = e & DMASK;
+        const bool before = (r1 >= 0 && abs(d - r1) <= rt) || (r2 >= 0 && abs(d - r2) <= rt) ||
+                            (r3 >= 0 && abs(d - r3) <= rt) || (r4 >= 0 && abs(d - r4) <= rt) ||
+                            (r5 >= 0 && abs(d - r5) <= rt);
+        cur = (before && (e & FLAG)) ? -1 : d;
+        wk[v * Wc + u] = (int16_t)cur;
       }
-      if (!up) continue;
-      for (int j = 1; j <= md && v + j < Hc; j++) {
-        int d2 = wk[(v + j) * Wc + u];
-        if (d2 >= 0 && abs(d - d2) <= rt) { down = true; break; }
-      }
-      if (down) wk[v * Wc + u] = -1;
+      r5 = r4; r4 = r3; r3 = r2; r2 = r1; r1 = cur;
     }
   }
   __syncthreads();
-  // ---- horizontal pass (dependencies along a row only) --------------------------
+  // horizontal pass: lines = rows
+  for (int p = tid; p < NP; p += T) {
+    const int e = wk[p];
+    if (e < 0) continue;
+    const int left_in_row = Wc - 1 - p % Wc;
+    bool after = false;
+#pragma unroll
+    for (int j = 1; j <= md; j++)
+      if (j <= left_in_row) {
+        const int e2 = wk[p + j];
+        after = after || (e2 >= 0 && abs(e - (e2 & DMASK)) <= rt);
+      }
+    if (after) wk[p] = (int16_t)(e | FLAG);
+  }
+  __syncthreads();
   for (int v = tid; v < Hc; v += T) {
+    int r1 = -1, r2 = -1, r3 = -1, r4 = -1, r5 = -1;
     for (int u = 0; u < Wc; u++) {
-      int d = wk[v * Wc + u];
-      if (d < 0) continue;
-      bool lft = false, rgt = false;
-      for (int j = 1; j <= md && u - j >= 0; j++) {
-        int d2 = wk[v * Wc + u - j];
-        if (d2 >= 0 && abs(d - d2) <= rt) { lft = true; break; }
+      const int e = wk[v * Wc + u];
+      int cur = -1;
+      if (e >= 0) {
+        const int d = e & DMASK;
+        const bool before = (r1 >= 0 && abs(d - r1) <= rt) || (r2 >= 0 && abs(d - r2) <= rt) ||
+                            (r3 >= 0 && abs(d - r3) <= rt) || (r4 >= 0 && abs(d - r4) <= rt) ||
+                            (r5 >= 0 && abs(d - r5) <= rt);
+        cur = (before && (e & FLAG)) ? -1 : d;
+        wk[v * Wc + u] = (int16_t)cur;
       }
-      if (!lft) continue;
-      for (int j = 1; j <= md && u + j < Wc; j++) {
-        int d2 = wk[v * Wc + u + j];
-        if (d2 >= 0 && abs(d - d2) <= rt) { rgt = true; break; }
-      }
-      if (rgt) wk[v * Wc + u] = -1;
+      r5 = r4; r4 = r3; r3 = r2; r2 = r1; r1 = cur;
     }
   }
   __syncthreads();

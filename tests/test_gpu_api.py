@@ -90,6 +90,54 @@ def test_host_batch_equals_per_frame_calls(jn, oracle, synth, pinned):
     e.close(); sc.close()
 
 
+def test_rolling_device_submissions_equal_stream_api(jn, synth):
+    """jn_stereo_scan_submit_device: four submissions of five device-resident frames rolling through the
+    library's sub-batch streams (odd batch: sub-batches of 3 and 2 frames, one textureless frame) give byte
+    for byte what jn_elas_process_batch + jn_scan_from_disparity_batch give on a caller stream."""
+    import torch
+    W, H, dm, n = 320, 240, 64, 5
+    dev = torch.device("cuda", 0)
+    cal = jn.Calibration(scan_lib.CALIB_YML)
+    cal.set_q_matrix(scan_lib.fixtures()["Q"]["320x180"])
+    sc = jn.ObstacleScan(cal, W, H)
+    e = jn.Elas(jn.parameters(jn.ROBOTICS, disp_max=dm))
+    ins, outs = [], []
+    for call in range(4):
+        L, R = synth.scene_batch("textured" if call & 1 else "random_dot", W, H, dm, [200 + 7 * call + i for i in range(n)])
+        if call == 2:
+            L[3] = 9; R[3] = 9
+        ins.append((torch.from_numpy(L).to(dev), torch.from_numpy(R).to(dev)))
+        outs.append(dict(D1=torch.full((n, H, W), 5.0, device=dev), st=torch.full((n,), -9, dtype=torch.int32, device=dev),
+                         ranges=torch.zeros((n, 90), dtype=torch.float64, device=dev),
+                         meta=torch.zeros((n, 5), dtype=torch.float64, device=dev),
+                         u8=torch.zeros((n, H, W), dtype=torch.uint8, device=dev)))
+    torch.cuda.synchronize()
+    for (dL, dR), o in zip(ins, outs):
+        e.stereo_scan_submit_device(sc, n, dL.data_ptr(), dR.data_ptr(), (W, H, W), o["D1"].data_ptr(), o["st"].data_ptr(),
+                                    o["ranges"].data_ptr(), o["meta"].data_ptr(), o["u8"].data_ptr())
+    e.stereo_scan_wait()
+    got = [{k: v.cpu().numpy().copy() for k, v in o.items()} for o in outs]
+    # the same frames through the stream API (fresh handle: nothing shared with the rolling lanes)
+    e2 = jn.Elas(jn.parameters(jn.ROBOTICS, disp_max=dm))
+    for call, (dL, dR) in enumerate(ins):
+        D1 = torch.zeros((n, H, W), device=dev); st = torch.zeros((n,), dtype=torch.int32, device=dev)
+        rg = torch.zeros((n, 90), dtype=torch.float64, device=dev); mt = torch.zeros((n, 5), dtype=torch.float64, device=dev)
+        u8 = torch.zeros((n, H, W), dtype=torch.uint8, device=dev)
+        e2.process_batch(dL.data_ptr(), dR.data_ptr(), D1.data_ptr(), 0, st.data_ptr(), (W, H, W), n, 0)
+        torch.cuda.synchronize()
+        stn = st.cpu().numpy()
+        D1[torch.from_numpy(stn != 0).to(dev)] = 0.0            # the zero map the submit calls hand out for an unmatched frame
+        sc.from_disparity_batch(n, D1.data_ptr(), rg.data_ptr(), mt.data_ptr(), u8.data_ptr(), 0)
+        torch.cuda.synchronize()
+        g = got[call]
+        assert np.array_equal(g["st"], stn) and (stn[3] == 1) == (call == 2), call
+        assert np.array_equal(g["D1"], D1.cpu().numpy()), call
+        assert np.array_equal(g["u8"], u8.cpu().numpy()), call
+        assert np.array_equal(g["ranges"].view(np.int64), rg.cpu().numpy().view(np.int64)), call
+        assert np.array_equal(g["meta"].view(np.int64), mt.cpu().numpy().view(np.int64)), call
+    e.close(); e2.close(); sc.close()
+
+
 def test_c4_seeds_full_size(jn, oracle, synth):
     """BASELINE config C4: 1920x1200 pairs with seeds 1000.. -- 32 of them (spread over the 1024),
     final maps bit-exact against the oracle, in one batch through the device-resident entry point."""
