@@ -354,13 +354,13 @@ __global__ void __launch_bounds__(Q_THREADS) seg_apply4_kernel(Geo g, Workspace 
 // tile borders every link is made.
 constexpr int CT_W = 256, CT_H = 16, CT_THREADS = 256;
 
+// no path compression: the trees of a 16-row tile are shallow, and the only writes of the union phase stay
+// the atomicMin of sm_union (labels only ever decrease toward an ancestor)
 __device__ __forceinline__ int sm_find(volatile int* lab, int x) {
   int p = lab[x];
   while (p != x) {
-    const int gp = lab[p];
-    if (gp != p) lab[x] = gp;   // path halving; labels only ever decrease toward an ancestor
     x = p;
-    p = gp;
+    p = lab[x];
   }
   return x;
 }

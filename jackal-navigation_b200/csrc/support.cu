@@ -28,7 +28,7 @@
 namespace {
 
 #ifndef JN_MATCH_THREADS
-#define JN_MATCH_THREADS 512
+#define JN_MATCH_THREADS 256
 #endif
 constexpr int MATCH_THREADS = JN_MATCH_THREADS;
 constexpr int KG = 4;   // candidates matched together by one warp
@@ -82,7 +82,7 @@ __device__ __forceinline__ bool candidate_gate(const Geo& g, int u, const uint4*
 template <int DIR>
 __device__ __forceinline__ void match_group(const Geo& g, const int (&u)[KG], unsigned okmask, const uint4* rowA_t,
                                             const uint4* rowA_b, const uint4* rowB_t, const uint4* rowB_b,
-                                            int lane, int (&res)[KG]) {
+                                            int lane, int safe_u, int (&res)[KG]) {
   const int W = g.W;
   const int dmin = max(g.p.disp_min, 0);
 #pragma unroll
@@ -96,7 +96,7 @@ __device__ __forceinline__ void match_group(const Geo& g, const int (&u)[KG], un
 #pragma unroll
   for (int k = 0; k < KG; k++) {
     const bool ok = (okmask >> k) & 1u;
-    const int uk = ok ? u[k] : 8;             // any readable column: the scores are discarded
+    const int uk = ok ? u[k] : safe_u;        // any staged column: the scores are discarded
     a[k][0] = rowA_t[uk - 2]; a[k][1] = rowA_t[uk + 2];
     a[k][2] = rowA_b[uk - 2]; a[k][3] = rowA_b[uk + 2];
     best[k].k1 = KEY_EMPTY;
@@ -209,36 +209,58 @@ __device__ __forceinline__ void match_group(const Geo& g, const int (&u)[KG], un
   }
 }
 
-__global__ void __launch_bounds__(MATCH_THREADS, 1)
+// A CTA matches the candidates of PART of a candidate row: groups [g_lo, g_hi) of KG lattice neighbours.
+// It stages only the columns those candidates can touch -- their own columns +-2 and disp_max columns to
+// either side of the left-image rows (searched by the backward pass), disp_max columns to the left of the
+// right-image rows -- so that at 1920 px two half-row CTAs (91 KB each, 256 threads x 128 registers) share
+// an SM: while one waits for its bulk copy, runs its gates or compacts its list, the other one keeps the
+// integer pipe busy.  `nsplit` = parts per row, chosen by the launcher as the smallest that lets two CTAs
+// co-reside.  Row pointers are biased by the first staged column, so all indexing is by image column.
+__global__ void __launch_bounds__(MATCH_THREADS, 2)
 support_match_kernel(Geo g, const uint8_t* __restrict__ desc1, const uint8_t* __restrict__ desc2,
-                     int16_t* __restrict__ dcan) {
+                     int16_t* __restrict__ dcan, int nsplit, int groups_per_part, int lcols, int rcols) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ int s_nvalid;
   const int W = g.W, H = g.H, Wc = g.Wc;
-  const int vc = blockIdx.x, frame = blockIdx.y;
+  const int vc = blockIdx.x / nsplit, part = blockIdx.x - vc * nsplit, frame = blockIdx.y;
   const int step = g.p.candidate_stepsize;
   const int v = vc * step;
   int16_t* out = dcan + (size_t)frame * g.Wc * g.Hc + (size_t)vc * Wc;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = MATCH_THREADS / 32;
 
+  // this part's groups and candidates (candidate 0 is never matched; part 0 writes its 0)
+  const int ngroups = (Wc - 1 + KG - 1) / KG;
+  const int g_lo = part * groups_per_part, g_hi = min(g_lo + groups_per_part, ngroups);
+  const int uc_lo = 1 + g_lo * KG, uc_hi = min(1 + g_hi * KG, Wc);       // matched candidates [uc_lo, uc_hi)
+  const int uc_w0 = part == 0 ? 0 : uc_lo;                                // written candidates [uc_w0, uc_hi)
+  if (uc_lo >= uc_hi && part != 0) return;
+
   // rows 0 / column 0 of the candidate image are never matched and stay 0 (calloc, H3)
   const bool row_ok = (vc >= 1) && v >= 5 && v <= H - 6;
-  if (!row_ok) {
-    for (int uc = tid; uc < Wc; uc += MATCH_THREADS) out[uc] = (vc == 0 || uc == 0) ? 0 : -1;
+  if (!row_ok || uc_lo >= uc_hi) {
+    for (int uc = uc_w0 + tid; uc < uc_hi; uc += MATCH_THREADS) out[uc] = (vc == 0 || uc == 0) ? 0 : -1;
     return;
   }
 
-  const size_t rowbytes = (size_t)W * 16;
+  // staged column windows (inclusive), see above
+  const int dm = g.p.disp_max;
+  const int ua = uc_lo * step, ub = (uc_hi - 1) * step;
+  const int cL0 = max(ua - dm - 2, 0), cL1 = min(ub + dm + 2, W - 1);
+  const int cR0 = max(ua - dm - 2, 0), cR1 = min(ub + 2, W - 1);
+  const uint32_t nL = (uint32_t)(cL1 - cL0 + 1) * 16u, nR = (uint32_t)(cR1 - cR0 + 1) * 16u;
+  const size_t lbytes = (size_t)lcols * 16, rbytes = (size_t)rcols * 16;
   const size_t wcb = (size_t)((Wc * 4 + 15) & ~15);
-  uint4* L_t = reinterpret_cast<uint4*>(smem);
-  uint4* L_b = reinterpret_cast<uint4*>(smem + rowbytes);
-  uint4* R_t = reinterpret_cast<uint4*>(smem + 2 * rowbytes);
-  uint4* R_b = reinterpret_cast<uint4*>(smem + 3 * rowbytes);
-  int* fwd = reinterpret_cast<int*>(smem + 4 * rowbytes);             // forward disparity per candidate
-  int* list = reinterpret_cast<int*>(smem + 4 * rowbytes + wcb);      // candidates that go to the cross check
-  int* resv = reinterpret_cast<int*>(smem + 4 * rowbytes + 2 * wcb);  // gate flags, then final disparity
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 4 * rowbytes + 3 * wcb);
+  const uint4* L_t = reinterpret_cast<const uint4*>(smem) - cL0;
+  const uint4* L_b = reinterpret_cast<const uint4*>(smem + lbytes) - cL0;
+  const uint4* R_t = reinterpret_cast<const uint4*>(smem + 2 * lbytes) - cR0;
+  const uint4* R_b = reinterpret_cast<const uint4*>(smem + 2 * lbytes + rbytes) - cR0;
+  uint8_t* arrays = smem + 2 * lbytes + 2 * rbytes;
+  int* fwd = reinterpret_cast<int*>(arrays);              // forward disparity per candidate
+  int* list = reinterpret_cast<int*>(arrays + wcb);       // candidates that go to the cross check
+  int* resv = reinterpret_cast<int*>(arrays + 2 * wcb);   // gate flags, then final disparity
+  uint64_t* bar = reinterpret_cast<uint64_t*>(arrays + 3 * wcb);
 
+  const size_t rowbytes = (size_t)W * 16;
   const uint8_t* d1 = desc1 + (size_t)frame * W * H * 16;
   const uint8_t* d2 = desc2 + (size_t)frame * W * H * 16;
   if (tid == 0) {
@@ -247,16 +269,16 @@ support_match_kernel(Geo g, const uint8_t* __restrict__ desc1, const uint8_t* __
   }
   __syncthreads();
   if (tid == 0) {
-    mbar_arrive_expect_tx(bar, (uint32_t)(4 * rowbytes));
-    bulk_g2s(L_t, d1 + (size_t)(v - 2) * rowbytes, (uint32_t)rowbytes, bar);
-    bulk_g2s(L_b, d1 + (size_t)(v + 2) * rowbytes, (uint32_t)rowbytes, bar);
-    bulk_g2s(R_t, d2 + (size_t)(v - 2) * rowbytes, (uint32_t)rowbytes, bar);
-    bulk_g2s(R_b, d2 + (size_t)(v + 2) * rowbytes, (uint32_t)rowbytes, bar);
+    mbar_arrive_expect_tx(bar, 2u * nL + 2u * nR);
+    bulk_g2s(smem, d1 + (size_t)(v - 2) * rowbytes + (size_t)cL0 * 16, nL, bar);
+    bulk_g2s(smem + lbytes, d1 + (size_t)(v + 2) * rowbytes + (size_t)cL0 * 16, nL, bar);
+    bulk_g2s(smem + 2 * lbytes, d2 + (size_t)(v - 2) * rowbytes + (size_t)cR0 * 16, nR, bar);
+    bulk_g2s(smem + 2 * lbytes + rbytes, d2 + (size_t)(v + 2) * rowbytes + (size_t)cR0 * 16, nR, bar);
   }
   const uint4* c1 = reinterpret_cast<const uint4*>(d1 + (size_t)v * rowbytes);
   const uint4* c2 = reinterpret_cast<const uint4*>(d2 + (size_t)v * rowbytes);
   // while the rows are in flight: gates of the forward candidates (centre descriptors from L2)
-  for (int uc = tid; uc < Wc; uc += MATCH_THREADS) {
+  for (int uc = uc_w0 + tid; uc < uc_hi; uc += MATCH_THREADS) {
     resv[uc] = (uc >= 1 && candidate_gate<-1>(g, uc * step, c1)) ? 1 : 0;
     fwd[uc] = -1;
   }
@@ -264,8 +286,7 @@ support_match_kernel(Geo g, const uint8_t* __restrict__ desc1, const uint8_t* __
   mbar_wait(bar, 0);
 
   // forward: left pixels (u,v) -> right image, KG lattice neighbours per warp pass
-  const int ngroups = (Wc - 1 + KG - 1) / KG;
-  for (int gi = warp; gi < ngroups; gi += nwarps) {
+  for (int gi = g_lo + warp; gi < g_hi; gi += nwarps) {
     int u[KG], r[KG];
     unsigned okmask = 0u;
 #pragma unroll
@@ -274,7 +295,7 @@ support_match_kernel(Geo g, const uint8_t* __restrict__ desc1, const uint8_t* __
       u[k] = uc * step;
       if (uc < Wc && resv[uc]) okmask |= 1u << k;
     }
-    match_group<-1>(g, u, okmask, L_t, L_b, R_t, R_b, lane, r);
+    match_group<-1>(g, u, okmask, L_t, L_b, R_t, R_b, lane, ua, r);
     if (lane == 0) {
 #pragma unroll
       for (int k = 0; k < KG; k++) {
@@ -285,7 +306,7 @@ support_match_kernel(Geo g, const uint8_t* __restrict__ desc1, const uint8_t* __
   }
   __syncthreads();
   // gates of the backward candidates (right pixel u-d), all threads; then the final-result array
-  for (int uc = tid; uc < Wc; uc += MATCH_THREADS) {
+  for (int uc = uc_w0 + tid; uc < uc_hi; uc += MATCH_THREADS) {
     const int d = fwd[uc];
     const bool go = d >= 0 && candidate_gate<+1>(g, uc * step - d, c2);
     if (!go) fwd[uc] = -1;
@@ -295,9 +316,9 @@ support_match_kernel(Geo g, const uint8_t* __restrict__ desc1, const uint8_t* __
   // compact the candidates that go on (order preserved: neighbours stay together)
   if (warp == 0) {
     int n = 0;
-    for (int base = 1; base < Wc; base += 32) {
+    for (int base = uc_lo; base < uc_hi; base += 32) {
       int uc = base + lane;
-      bool f = uc < Wc && fwd[uc] >= 0;
+      bool f = uc < uc_hi && fwd[uc] >= 0;
       unsigned m = __ballot_sync(0xffffffffu, f);
       if (f) list[n + __popc(m & ((1u << lane) - 1))] = uc;
       n += __popc(m);
@@ -315,10 +336,10 @@ support_match_kernel(Geo g, const uint8_t* __restrict__ desc1, const uint8_t* __
       const int i = gi * KG + k;
       ucs[k] = (i < nvalid) ? list[i] : -1;
       df[k] = (ucs[k] >= 0) ? fwd[ucs[k]] : 0;
-      u[k] = (ucs[k] >= 0) ? ucs[k] * step - df[k] : 8;
+      u[k] = (ucs[k] >= 0) ? ucs[k] * step - df[k] : ua;
       if (ucs[k] >= 0) okmask |= 1u << k;
     }
-    match_group<+1>(g, u, okmask, R_t, R_b, L_t, L_b, lane, r);
+    match_group<+1>(g, u, okmask, R_t, R_b, L_t, L_b, lane, ua, r);
     if (lane == 0) {
 #pragma unroll
       for (int k = 0; k < KG; k++)
@@ -326,7 +347,7 @@ support_match_kernel(Geo g, const uint8_t* __restrict__ desc1, const uint8_t* __
     }
   }
   __syncthreads();
-  for (int uc = tid; uc < Wc; uc += MATCH_THREADS) out[uc] = (int16_t)resv[uc];
+  for (int uc = uc_w0 + tid; uc < uc_hi; uc += MATCH_THREADS) out[uc] = (int16_t)resv[uc];
 }
 
 // c0(p) = number of lattice points q in the (2r+1)^2 window (p included) that are
@@ -500,71 +521,85 @@ support_filter_kernel(Geo g, const int16_t* __restrict__ dcan_all, int32_t* __re
   // ---- redundant points (elas.cpp:181-235): a point goes if it has a similar point within md cells on
   // BOTH sides along the line; the pass runs in place, so the "before" side sees this pass's removals
   // and the "after" side does not.  The "after" test therefore only needs the state at the start of the
-  // pass: it is evaluated for all points in parallel and parked in bit 14 of the entry (d < 4096); the
+  // pass: it is evaluated for all points in parallel into a bit array; the
   // serial walk along each line then carries the last md decided entries in registers and touches
-  // shared memory once per cell -- no data-dependent inner loops, no divergence.
+  // shared memory once per cell (plus the flag word) -- no data-dependent inner loops, no divergence.
   const int md = 5, rt = 1;  // redun_max_dist, redun_threshold (elas.cpp:421-422)
-  constexpr int FLAG = 0x4000, DMASK = 0x3fff;
+  // one "after" bit per lattice point, next to the working copy (shared memory) or in the frontier
+  // buffer, which is free by now (global-memory mode); a warp's 32 points are one word: no atomics
+  const int NP32 = (NP + 31) & ~31;
+  unsigned* flagw = use_smem ? reinterpret_cast<unsigned*>(reinterpret_cast<uint8_t*>(s_wk) + (((size_t)2 * NP + 16 + 3) & ~(size_t)3))
+                             : reinterpret_cast<unsigned*>(fr[0]);
   // vertical pass: lines = columns
-  for (int p = tid; p < NP; p += T) {
-    const int e = wk[p];
-    if (e < 0) continue;
+  for (int p = tid; p < NP32; p += T) {
+    const int e = p < NP ? wk[p] : -1;
     bool after = false;
+    if (e >= 0) {
 #pragma unroll
-    for (int j = 1; j <= md; j++) {
-      const int q = p + j * Wc;
-      if (q < NP) {
-        const int e2 = wk[q];            // its flag may or may not be set yet: masked
-        after = after || (e2 >= 0 && abs(e - (e2 & DMASK)) <= rt);
+      for (int j = 1; j <= md; j++) {
+        const int q = p + j * Wc;
+        if (q < NP) {
+          const int e2 = wk[q];
+          after = after || (e2 >= 0 && abs(e - e2) <= rt);
+        }
       }
     }
-    if (after) wk[p] = (int16_t)(e | FLAG);
+    const unsigned m = __ballot_sync(0xffffffffu, after);
+    if (lane == 0) flagw[p >> 5] = m;
   }
   __syncthreads();
   for (int u = tid; u < Wc; u += T) {
     int r1 = -1, r2 = -1, r3 = -1, r4 = -1, r5 = -1;   // decided entries v-1 .. v-5
     for (int v = 0; v < Hc; v++) {
-      const int e = wk[v * Wc + u];
+      const int p = v * Wc + u;
+      const int d = wk[p];
       int cur = -1;
-      if (e >= 0) {
-        const int d = e & DMASK;
+      if (d >= 0) {
         const bool before = (r1 >= 0 && abs(d - r1) <= rt) || (r2 >= 0 && abs(d - r2) <= rt) ||
                             (r3 >= 0 && abs(d - r3) <= rt) || (r4 >= 0 && abs(d - r4) <= rt) ||
                             (r5 >= 0 && abs(d - r5) <= rt);
-        cur = (before && (e & FLAG)) ? -1 : d;
-        wk[v * Wc + u] = (int16_t)cur;
+        cur = d;
+        if (before && ((flagw[p >> 5] >> (p & 31)) & 1u)) {
+          cur = -1;
+          wk[p] = (int16_t)-1;
+        }
       }
       r5 = r4; r4 = r3; r3 = r2; r2 = r1; r1 = cur;
     }
   }
   __syncthreads();
   // horizontal pass: lines = rows
-  for (int p = tid; p < NP; p += T) {
-    const int e = wk[p];
-    if (e < 0) continue;
-    const int left_in_row = Wc - 1 - p % Wc;
+  for (int p = tid; p < NP32; p += T) {
+    const int e = p < NP ? wk[p] : -1;
     bool after = false;
+    if (e >= 0) {
+      const int left_in_row = Wc - 1 - p % Wc;
 #pragma unroll
-    for (int j = 1; j <= md; j++)
-      if (j <= left_in_row) {
-        const int e2 = wk[p + j];
-        after = after || (e2 >= 0 && abs(e - (e2 & DMASK)) <= rt);
-      }
-    if (after) wk[p] = (int16_t)(e | FLAG);
+      for (int j = 1; j <= md; j++)
+        if (j <= left_in_row) {
+          const int e2 = wk[p + j];
+          after = after || (e2 >= 0 && abs(e - e2) <= rt);
+        }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, after);
+    if (lane == 0) flagw[p >> 5] = m;
   }
   __syncthreads();
   for (int v = tid; v < Hc; v += T) {
     int r1 = -1, r2 = -1, r3 = -1, r4 = -1, r5 = -1;
     for (int u = 0; u < Wc; u++) {
-      const int e = wk[v * Wc + u];
+      const int p = v * Wc + u;
+      const int d = wk[p];
       int cur = -1;
-      if (e >= 0) {
-        const int d = e & DMASK;
+      if (d >= 0) {
         const bool before = (r1 >= 0 && abs(d - r1) <= rt) || (r2 >= 0 && abs(d - r2) <= rt) ||
                             (r3 >= 0 && abs(d - r3) <= rt) || (r4 >= 0 && abs(d - r4) <= rt) ||
                             (r5 >= 0 && abs(d - r5) <= rt);
-        cur = (before && (e & FLAG)) ? -1 : d;
-        wk[v * Wc + u] = (int16_t)cur;
+        cur = d;
+        if (before && ((flagw[p >> 5] >> (p & 31)) & 1u)) {
+          cur = -1;
+          wk[p] = (int16_t)-1;
+        }
       }
       r5 = r4; r4 = r3; r3 = r2; r2 = r1; r1 = cur;
     }
@@ -659,8 +694,30 @@ int launch_support(const Geo& g, int B, Workspace& ws, cudaStream_t s) {
   return launch_support_filter(g, B, ws, s);
 }
 
+// Parts per candidate row and the shared memory of one part (see support_match_kernel): the smallest
+// split that lets two CTAs share an SM (227 KB), else a single CTA per SM on whole rows.
+static size_t match_smem(const Geo& g, int nsplit, int* groups_per_part, int* lcols, int* rcols) {
+  const int step = g.p.candidate_stepsize, dm = g.p.disp_max;
+  const int ngroups = (g.Wc - 1 + KG - 1) / KG;
+  const int gpp = (ngroups + nsplit - 1) / nsplit;
+  const int span = (gpp * KG - 1) * step;                 // first to last candidate column of a part
+  const int lc = min(g.W, span + 2 * dm + 5), rc = min(g.W, span + dm + 5);
+  *groups_per_part = gpp; *lcols = lc; *rcols = rc;
+  return (size_t)2 * lc * 16 + (size_t)2 * rc * 16 + 3 * (size_t)((g.Wc * 4 + 15) & ~15) + 16;
+}
+
 int launch_support_match(const Geo& g, int B, Workspace& ws, cudaStream_t s) {
-  size_t smem = (size_t)4 * g.W * 16 + 3 * (size_t)((g.Wc * 4 + 15) & ~15) + 16;
+  int nsplit = 1, gpp = 0, lc = 0, rc = 0;
+  size_t smem = 0;
+  bool found = false;
+  for (int ns = 1; ns <= 8 && !found; ns++) {
+    smem = match_smem(g, ns, &gpp, &lc, &rc);
+    if (2 * (smem + 1024) <= 227 * 1024) { nsplit = ns; found = true; }
+  }
+  if (!found) {
+    nsplit = 1;
+    smem = match_smem(g, 1, &gpp, &lc, &rc);
+  }
   if (smem > 226 * 1024 || g.Wc > 2048) {   // 227 KB per CTA minus the static shared memory
     jn_set_error("image width %d too large for the shared-memory support matcher", g.W);
     return JN_ERR_UNSUPPORTED;
@@ -668,7 +725,10 @@ int launch_support_match(const Geo& g, int B, Workspace& ws, cudaStream_t s) {
   // per device (context), not per process: set on every launch, it is a host-side table write
   JN_CUDA_CHECK(cudaFuncSetAttribute(support_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      226 * 1024));
-  support_match_kernel<<<dim3(g.Hc, B), MATCH_THREADS, smem, s>>>(g, ws.desc[0], ws.desc[1], ws.dcan);
+  JN_CUDA_CHECK(cudaFuncSetAttribute(support_match_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     cudaSharedmemCarveoutMaxShared));
+  support_match_kernel<<<dim3(g.Hc * nsplit, B), MATCH_THREADS, smem, s>>>(g, ws.desc[0], ws.desc[1], ws.dcan, nsplit,
+                                                                           gpp, lc, rc);
   g_jn_launches += 1;
   return JN_OK;
 }
@@ -677,7 +737,10 @@ int launch_support_match(const Geo& g, int B, Workspace& ws, cudaStream_t s) {
 int launch_support_filter(const Geo& g, int B, Workspace& ws, cudaStream_t s) {
   dim3 cb(32, 8), cg((g.Wc + 31) / 32, (g.Hc + 7) / 8, B);
   incon_count_kernel<<<cg, cb, 0, s>>>(g, ws.dcan, ws.cnt);
-  const size_t wk_bytes = (size_t)g.Wc * g.Hc * sizeof(int16_t);
+  // + 16: the byte arrays of the frontier phase (two of NP bytes, the second one word aligned) end up to
+  // three bytes past 2 * NP
+  const size_t np = (size_t)g.Wc * g.Hc;
+  const size_t wk_bytes = ((np * sizeof(int16_t) + 16 + 3) & ~(size_t)3) + ((np + 31) / 32) * 4;   // + the "after" bits
   const int use_smem = wk_bytes <= 212 * 1024;
   // per device (context), not per process: set on every launch, it is a host-side table write
   JN_CUDA_CHECK(cudaFuncSetAttribute(support_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
