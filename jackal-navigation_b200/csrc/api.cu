@@ -78,6 +78,7 @@ struct DevRes {
   cudaStream_t lane[JN_MAX_PARTS];
   cudaEvent_t ev_lstag[JN_MAX_PARTS];        // lane k's current part is past the stagger stage
   cudaEvent_t ev_ldone[2][JN_MAX_PARTS];     // lane k finished its part of the submission using buffer set b
+  int lanes_busy;                            // a submit call queued work on the lanes since the last wait
   // optional per-stage timing with CUDA events on the launching stream
   cudaEvent_t ev[JN_PROFILE_STAGES + 1];
 };
@@ -239,6 +240,13 @@ extern "C" jn_elas* jn_elas_create(const jn_elas_params* p, int device) {
 // ordered after it (same stream, or a synchronisation in between).
 extern "C" void jn_elas_destroy(jn_elas* e) {
   if (!e) return;
+  if (e->r->lanes_busy) {   // submissions still rolling on the internal streams: nobody else can order after them
+    cudaSetDevice(e->device);
+    if (e->r->s_out) cudaStreamSynchronize(e->r->s_out);
+    for (int k = 0; k < JN_MAX_PARTS; k++)
+      if (e->r->lane[k]) cudaStreamSynchronize(e->r->lane[k]);
+    e->r->lanes_busy = 0;
+  }
   devres_release(e->r);
   delete e;
 }
@@ -670,6 +678,7 @@ static int run_rolling(jn_elas* e, jn_scan* sc, int n, int b, const uint8_t* I1,
   int rc = ensure_lanes(r, K);
   if (rc) return rc;
   if ((rc = jn_scan_reserve(sc, n))) return rc;
+  r->lanes_busy = 1;
   for (int k = 0; k < K; k++) {
     cudaStream_t L = r->lane[k], hk = r->hi[k];
     Workspace& wk = k ? r->wsx[k - 1] : r->ws;
@@ -768,6 +777,7 @@ extern "C" int jn_stereo_scan_wait(jn_elas* e) {
   for (int k = 0; k < JN_MAX_PARTS; k++)
     if (e->r->lane[k]) JN_CUDA_CHECK(cudaStreamSynchronize(e->r->lane[k]));
   if (e->r->own) JN_CUDA_CHECK(cudaStreamSynchronize(e->r->own));
+  e->r->lanes_busy = 0;
   return JN_OK;
 }
 

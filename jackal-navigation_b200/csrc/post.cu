@@ -388,14 +388,28 @@ __global__ void __launch_bounds__(CT_THREADS) seg_tile_kernel(Geo g, Workspace w
   const float* __restrict__ D = ws.Dlr[side] + fp;
   const float thr = g.p.speckle_sim_threshold;
   const unsigned le_mask = 0xFFFFFFFFu >> (31 - lane);   // lanes 0..lane
-  // rows of the tile: a warp per row, 32 pixels per step; pixels outside the map are invalid
-  for (int r = warp; r < CT_H; r += CT_THREADS / 32) {
-    const int y = y0 + r;
+  // rows of the tile: a warp per row, 32 pixels per step; pixels outside the map are invalid.  All loads
+  // of a warp's rows are issued before the (serial, shuffle-linked) run detection starts.
+  constexpr int RPW = CT_H / (CT_THREADS / 32), CPR = CT_W / 32;   // rows per warp, chunks per row
+  float dv[RPW][CPR];
+#pragma unroll
+  for (int i = 0; i < RPW; i++) {
+    const int y = y0 + warp + i * (CT_THREADS / 32);
+#pragma unroll
+    for (int k = 0; k < CPR; k++) {
+      const int x = x0 + 32 * k + lane;
+      dv[i][k] = (y < H && x < W) ? D[(size_t)y * W + x] : -10.f;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < RPW; i++) {
+    const int r = warp + i * (CT_THREADS / 32);
     int cur = -1;
     float prev = -10.f;
-    for (int u0 = 0; u0 < CT_W; u0 += 32) {
-      const int c = u0 + lane, x = x0 + c;
-      const float d = (y < H && x < W) ? D[(size_t)y * W + x] : -10.f;
+#pragma unroll
+    for (int k = 0; k < CPR; k++) {
+      const int u0 = 32 * k, c = u0 + lane;
+      const float d = dv[i][k];
       sD[r * CT_W + c] = d;
       float dl = __shfl_up_sync(0xffffffffu, d, 1);
       if (lane == 0) dl = prev;
@@ -722,21 +736,22 @@ __device__ __forceinline__ float div_weight_sum(float fs, float ws) {
 // into ring order with selects instead of a four-way divergent branch.
 template <bool UNIFORM>
 __device__ __forceinline__ bool mean8(const float x[8], float centre, int rot, float& out) {
-  float w[8], f[8];
+  float w[8];
 #pragma unroll
   for (int k = 0; k < 8; k++) {
     if (k == 4) {   // the centre sample itself (both callers pass centre = x[4]): difference 0, weight 4
       w[k] = 4.0f;
-      f[k] = x[k] * 4.0f;
       continue;
     }
     float t = 4.0f - buggy_abs(x[k] - centre);
     w[k] = fmaxf(0.0f, t);
-    f[k] = x[k] * w[k];
   }
+  // The weights are exactly 0, 2 or 4 (buggy_abs returns a power of two >= 8, 2, or something below 2^-96), so
+  // every product x * w is exact and the pair sum x[k]*w[k] + x[k+4]*w[k+4] is one multiply and one FMA with
+  // the reference's rounding (the file is compiled with -fmad=false; this FMA is explicit).
   float wq[4], fq[4];
 #pragma unroll
-  for (int k = 0; k < 4; k++) { wq[k] = w[k] + w[k + 4]; fq[k] = f[k] + f[k + 4]; }
+  for (int k = 0; k < 4; k++) { wq[k] = w[k] + w[k + 4]; fq[k] = __fmaf_rn(x[k + 4], w[k + 4], x[k] * w[k]); }
   // lane s holds pair k with (rot + k) & 3 == s  ->  k = (s - rot) & 3
   float ws, fs;
   if (UNIFORM) {
@@ -769,31 +784,15 @@ __device__ __forceinline__ bool mean8(const float x[8], float centre, int rot, f
 // touch HBM: one read and one write of the map instead of three reads and two writes.
 constexpr int MT_W = 64, MT_H = 32, MT_IN_W = MT_W + 7, MT_ROWS = MT_H + 7;
 
-__global__ void __launch_bounds__(256)
-mean_fused_kernel(Geo g, Workspace ws, const float* __restrict__ in, float* __restrict__ out,
-                  size_t out_frame_stride) {
-  __shared__ __align__(16) float s_in[MT_ROWS][MT_IN_W + 1];   // rows y0-4 .. y0+MT_H+2, columns x0-4 .. x0+MT_W+2
-  __shared__ __align__(16) float s_tmp[MT_ROWS][MT_W];         // horizontally filtered (the reference's D_tmp)
-  const int frame = blockIdx.z;
-  if (ws.info[frame].status != JN_OK) return;
-  const int W = g.Wd, H = g.Hd, tid = threadIdx.x;
-  const int x0 = blockIdx.x * MT_W, y0 = blockIdx.y * MT_H;
-  const float* src = in + (size_t)frame * W * H;
-  // a warp per tile row, lanes along the row (71 columns = 3 passes): no index division
-  for (int r = tid >> 5; r < MT_ROWS; r += 8) {
-    const int y = y0 - 4 + r;
-    const bool yin = y >= 0 && y < H;
-    const float* row = src + (size_t)(yin ? y : 0) * W;
-#pragma unroll
-    for (int c = tid & 31; c < MT_IN_W; c += 32) {
-      const int x = x0 - 4 + c;
-      s_in[r][c] = (yin && x >= 0 && x < W) ? row[x] : 0.f;
-    }
-  }
-  __syncthreads();
-  // Four neighbouring outputs per thread in both passes: their 8-tap windows overlap (11 samples instead
-  // of 32) and the ring rotation (c-4) & 3 of output s is s itself (tile origins are multiples of 4),
-  // a compile-time constant, so the summation order needs no selects.
+constexpr int MI_S = MT_IN_W + 1;    // row stride of the input tile (16-byte aligned rows)
+
+// The two filter passes on a staged tile.  s_in: MT_ROWS x MI_S, rows y0-4 .. y0+MT_H+2, columns x0-4 ..
+// x0+MT_W+2 (0 outside the map); s_tmp: MT_ROWS x MT_W scratch for the horizontally filtered rows (the
+// reference's D_tmp).  Four neighbouring outputs per thread in both passes: their 8-tap windows overlap
+// (11 samples instead of 32) and the ring rotation (c-4) & 3 of output s is s itself (tile origins are
+// multiples of 4), a compile-time constant, so the summation order needs no selects.
+__device__ __forceinline__ void mean_tile_passes(const float* __restrict__ s_in, float* __restrict__ s_tmp, int W, int H,
+                                                 int x0, int y0, int tid, float* __restrict__ dst) {
   // D_tmp: filtered for rows 3..H-4 and centres 4..W-4, otherwise -10 (invalid input) or 0 (H1)
   for (int i = tid; i < MT_ROWS * (MT_W / 4); i += 256) {
     const int r = i / (MT_W / 4), c = 4 * (i - r * (MT_W / 4));
@@ -802,9 +801,9 @@ mean_fused_kernel(Geo g, Workspace ws, const float* __restrict__ in, float* __re
     // the reference first sets every negative sample to -10 (elas.cpp:1304-1309); after the L/R check
     // (always run before, elas.cpp:108-118) -10 is the only negative value there is
     float v[12];
-    const float4 q0 = *reinterpret_cast<const float4*>(&s_in[r][c]);
-    const float4 q1 = *reinterpret_cast<const float4*>(&s_in[r][c + 4]);
-    const float4 q2 = *reinterpret_cast<const float4*>(&s_in[r][c + 8]);
+    const float4 q0 = *reinterpret_cast<const float4*>(&s_in[r * MI_S + c]);
+    const float4 q1 = *reinterpret_cast<const float4*>(&s_in[r * MI_S + c + 4]);
+    const float4 q2 = *reinterpret_cast<const float4*>(&s_in[r * MI_S + c + 8]);
     v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w; v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
     v[8] = q2.x; v[9] = q2.y; v[10] = q2.z; v[11] = q2.w;
     float o[4];
@@ -818,10 +817,9 @@ mean_fused_kernel(Geo g, Workspace ws, const float* __restrict__ in, float* __re
         if (mean8<true>(v + s4, d, s4, m)) o[s4] = m;
       }
     }
-    *reinterpret_cast<float4*>(&s_tmp[r][c]) = make_float4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<float4*>(&s_tmp[r * MT_W + c]) = make_float4(o[0], o[1], o[2], o[3]);
   }
   __syncthreads();
-  float* dst = out + (size_t)frame * out_frame_stride;
   for (int i = tid; i < (MT_H / 4) * MT_W; i += 256) {
     const int rq = i / MT_W, c = i - rq * MT_W;
     const int x = x0 + c;
@@ -829,12 +827,12 @@ mean_fused_kernel(Geo g, Workspace ws, const float* __restrict__ in, float* __re
     const bool xok = H >= 8 && x >= 3 && x <= W - 4;
     float v[11];
 #pragma unroll
-    for (int k = 0; k < 11; k++) v[k] = s_tmp[4 * rq + k][c];   // rows y-4 .. y+3 of the four outputs
+    for (int k = 0; k < 11; k++) v[k] = s_tmp[(4 * rq + k) * MT_W + c];   // rows y-4 .. y+3 of the four outputs
 #pragma unroll
     for (int s4 = 0; s4 < 4; s4++) {
       const int r = 4 * rq + s4, y = y0 + r;
       if (y >= H) continue;
-      float o = s_in[r + 4][c + 4];
+      float o = s_in[(r + 4) * MI_S + c + 4];
       if (xok && y >= 4 && y <= H - 4) {
         float m;
         if (mean8<true>(v + s4, v[s4 + 4], s4, m)) o = m;
@@ -842,6 +840,113 @@ mean_fused_kernel(Geo g, Workspace ws, const float* __restrict__ in, float* __re
       dst[(size_t)y * W + x] = o;
     }
   }
+}
+
+__global__ void __launch_bounds__(256)
+mean_fused_kernel(Geo g, Workspace ws, const float* __restrict__ in, float* __restrict__ out,
+                  size_t out_frame_stride) {
+  __shared__ __align__(16) float s_in[MT_ROWS * MI_S];
+  __shared__ __align__(16) float s_tmp[MT_ROWS * MT_W];
+  const int frame = blockIdx.z;
+  if (ws.info[frame].status != JN_OK) return;
+  const int W = g.Wd, H = g.Hd, tid = threadIdx.x;
+  const int x0 = blockIdx.x * MT_W, y0 = blockIdx.y * MT_H;
+  const float* src = in + (size_t)frame * W * H;
+  // a warp per tile row, lanes along the row (71 columns = 3 passes): no index division
+  for (int r = tid >> 5; r < MT_ROWS; r += 8) {
+    const int y = y0 - 4 + r;
+    const bool yin = y >= 0 && y < H;
+    const float* row = src + (size_t)(yin ? y : 0) * W;
+#pragma unroll
+    for (int c = tid & 31; c < MT_IN_W; c += 32) {
+      const int x = x0 - 4 + c;
+      s_in[r * MI_S + c] = (yin && x >= 0 && x < W) ? row[x] : 0.f;
+    }
+  }
+  __syncthreads();
+  mean_tile_passes(s_in, s_tmp, W, H, x0, y0, tid, out + (size_t)frame * out_frame_stride);
+}
+
+// gapInterpolation (widths up to SMALL_GAP, no border extrapolation) and adaptiveMean in one kernel: the
+// tile the mean needs is produced in shared memory from the raw tile + `gap` more rows and columns of halo
+// -- row pass, then column pass, exactly gap_small_kernel<true> and <false> (an invalid pixel outside the
+// map can never be filled and never counts as a valid neighbour, which is what their position tests say) --
+// so the map is read once and written once instead of three reads and three writes.
+constexpr int GM_RAW_H = MT_ROWS + 2 * 8, GM_RAW_S = MT_IN_W + 2 * 8 + 1;   // SMALL_GAP = 8 (asserted below)
+
+static_assert(SMALL_GAP == 8, "GM_RAW_* are sized for SMALL_GAP = 8");
+
+__global__ void __launch_bounds__(256)
+gap_mean_fused_kernel(Geo g, Workspace ws, const float* __restrict__ in, float* __restrict__ out,
+                      size_t out_frame_stride) {
+  __shared__ __align__(16) float bufA[GM_RAW_H * GM_RAW_S];   // raw tile; later the mean's input tile (MT_ROWS x MI_S)
+  __shared__ __align__(16) float bufB[GM_RAW_H * MI_S];       // row-pass output; later the mean's scratch (MT_ROWS x MT_W)
+  const int frame = blockIdx.z;
+  if (ws.info[frame].status != JN_OK) return;
+  const int W = g.Wd, H = g.Hd, tid = threadIdx.x, gap = g.gap_eff;
+  const int x0 = blockIdx.x * MT_W, y0 = blockIdx.y * MT_H;
+  const float* src = in + (size_t)frame * W * H;
+  const int RH = MT_ROWS + 2 * gap, RW = MT_IN_W + 2 * gap;
+  const int xr = x0 - 4 - gap, yr = y0 - 4 - gap;             // map coordinates of raw[0][0]
+  for (int r = tid >> 5; r < RH; r += 8) {
+    const int y = yr + r;
+    const bool yin = y >= 0 && y < H;
+    const float* row = src + (size_t)(yin ? y : 0) * W;
+    for (int c = tid & 31; c < RW; c += 32) {
+      const int x = xr + c;
+      bufA[r * GM_RAW_S + c] = (yin && x >= 0 && x < W) ? row[x] : -10.f;
+    }
+  }
+  __syncthreads();
+  // row pass on every staged row, for the MT_IN_W columns the mean tile has: bufB[r][c] = column x0-4+c
+  for (int i = tid; i < RH * MT_IN_W; i += 256) {
+    const int r = i / MT_IN_W, c = i - r * MT_IN_W;
+    const float* p = bufA + r * GM_RAW_S + c + gap;
+    float d = p[0];
+    if (d < 0) {
+      int l = 0, rr = 0;
+      float dl = -1.f, dr = -1.f;
+      for (int k = 1; k <= gap; k++) {
+        const float t = p[-k];
+        if (t >= 0) { l = k; dl = t; break; }
+      }
+      if (l > 0) {
+        for (int k = 1; k <= gap + 1 - l; k++) {
+          const float t = p[k];
+          if (t >= 0) { rr = k; dr = t; break; }
+        }
+        if (rr > 0) d = ipol(dl, dr);   // run length l + rr - 1 <= gap
+      }
+    }
+    bufB[r * MI_S + c] = d;
+  }
+  __syncthreads();
+  // column pass for the MT_ROWS rows of the mean tile (row r of it = staged row r + gap); outside the map
+  // the mean's tile holds 0
+  for (int i = tid; i < MT_ROWS * MT_IN_W; i += 256) {
+    const int r = i / MT_IN_W, c = i - r * MT_IN_W;
+    const float* p = bufB + (r + gap) * MI_S + c;
+    float d = p[0];
+    if (d < 0) {
+      int l = 0, rr = 0;
+      float dl = -1.f, dr = -1.f;
+      for (int k = 1; k <= gap; k++) {
+        const float t = p[-k * MI_S];
+        if (t >= 0) { l = k; dl = t; break; }
+      }
+      if (l > 0) {
+        for (int k = 1; k <= gap + 1 - l; k++) {
+          const float t = p[k * MI_S];
+          if (t >= 0) { rr = k; dr = t; break; }
+        }
+        if (rr > 0) d = ipol(dl, dr);
+      }
+    }
+    const int x = x0 - 4 + c, y = y0 - 4 + r;
+    bufA[r * MI_S + c] = (x >= 0 && x < W && y >= 0 && y < H) ? d : 0.f;
+  }
+  __syncthreads();
+  mean_tile_passes(bufA, bufB, W, H, x0, y0, tid, out + (size_t)frame * out_frame_stride);
 }
 
 // Half-resolution branch (elas.cpp:1323-1391): 4 taps at coordinates c-2 .. c+1, centre c.  The
@@ -1074,9 +1179,13 @@ void launch_post(const Geo& g, int B, Workspace& ws, float* D1out, float* D2out,
   const size_t n = (size_t)g.Wd * g.Hd;
   const int sides = g.p.postprocess_only_left ? 1 : 2;
   post_lr(g, B, ws, s, sides == 2 || D2out != nullptr);
+  // ROBOTICS-style tail (small gaps, no border extrapolation, adaptive mean, full resolution): gap interpolation
+  // and the mean run as one kernel per output map (JN_POST_FUSED=0: the step-wise kernels)
+  static const bool fuse_env = !(getenv("JN_POST_FUSED") && getenv("JN_POST_FUSED")[0] == '0');
+  const bool fused = fuse_env && g.gap_eff <= SMALL_GAP && !g.p.add_corners && !g.p.subsampling && g.p.filter_adaptive_mean;
   for (int side = 0; side < sides; side++) {
     post_segments(g, B, ws, side, s);
-    post_gap(g, B, ws, side, s);
+    if (!fused) post_gap(g, B, ws, side, s);
   }
   for (int side = 0; side < 2; side++) {
     float* out = side ? D2out : D1out;
@@ -1084,7 +1193,13 @@ void launch_post(const Geo& g, int B, Workspace& ws, float* D1out, float* D2out,
     const float* cur = ws.Dlr[side];
     const bool filt = side < sides;
     const bool do_mean = filt && g.p.filter_adaptive_mean, do_med = filt && g.p.filter_median;
-    if (do_mean && do_med) {
+    if (fused && filt) {
+      dim3 grid((g.Wd + MT_W - 1) / MT_W, (g.Hd + MT_H - 1) / MT_H, B);
+      float* mo = do_med ? ws.Dtmp2[side] : out;
+      gap_mean_fused_kernel<<<grid, 256, 0, s>>>(g, ws, cur, mo, n);
+      g_jn_launches += 1;
+      if (do_med) post_median(g, B, ws, ws.Dtmp2[side], ws.Dtmp[side], out, n, s);
+    } else if (do_mean && do_med) {
       post_mean(g, B, ws, cur, ws.Dtmp[side], ws.Dtmp2[side], n, s);
       post_median(g, B, ws, ws.Dtmp2[side], ws.Dtmp[side], out, n, s);
     } else if (do_mean) {
