@@ -867,88 +867,6 @@ mean_fused_kernel(Geo g, Workspace ws, const float* __restrict__ in, float* __re
   mean_tile_passes(s_in, s_tmp, W, H, x0, y0, tid, out + (size_t)frame * out_frame_stride);
 }
 
-// gapInterpolation (widths up to SMALL_GAP, no border extrapolation) and adaptiveMean in one kernel: the
-// tile the mean needs is produced in shared memory from the raw tile + `gap` more rows and columns of halo
-// -- row pass, then column pass, exactly gap_small_kernel<true> and <false> (an invalid pixel outside the
-// map can never be filled and never counts as a valid neighbour, which is what their position tests say) --
-// so the map is read once and written once instead of three reads and three writes.
-constexpr int GM_RAW_H = MT_ROWS + 2 * 8, GM_RAW_S = MT_IN_W + 2 * 8 + 1;   // SMALL_GAP = 8 (asserted below)
-
-static_assert(SMALL_GAP == 8, "GM_RAW_* are sized for SMALL_GAP = 8");
-
-__global__ void __launch_bounds__(256)
-gap_mean_fused_kernel(Geo g, Workspace ws, const float* __restrict__ in, float* __restrict__ out,
-                      size_t out_frame_stride) {
-  __shared__ __align__(16) float bufA[GM_RAW_H * GM_RAW_S];   // raw tile; later the mean's input tile (MT_ROWS x MI_S)
-  __shared__ __align__(16) float bufB[GM_RAW_H * MI_S];       // row-pass output; later the mean's scratch (MT_ROWS x MT_W)
-  const int frame = blockIdx.z;
-  if (ws.info[frame].status != JN_OK) return;
-  const int W = g.Wd, H = g.Hd, tid = threadIdx.x, gap = g.gap_eff;
-  const int x0 = blockIdx.x * MT_W, y0 = blockIdx.y * MT_H;
-  const float* src = in + (size_t)frame * W * H;
-  const int RH = MT_ROWS + 2 * gap, RW = MT_IN_W + 2 * gap;
-  const int xr = x0 - 4 - gap, yr = y0 - 4 - gap;             // map coordinates of raw[0][0]
-  for (int r = tid >> 5; r < RH; r += 8) {
-    const int y = yr + r;
-    const bool yin = y >= 0 && y < H;
-    const float* row = src + (size_t)(yin ? y : 0) * W;
-    for (int c = tid & 31; c < RW; c += 32) {
-      const int x = xr + c;
-      bufA[r * GM_RAW_S + c] = (yin && x >= 0 && x < W) ? row[x] : -10.f;
-    }
-  }
-  __syncthreads();
-  // row pass on every staged row, for the MT_IN_W columns the mean tile has: bufB[r][c] = column x0-4+c
-  for (int i = tid; i < RH * MT_IN_W; i += 256) {
-    const int r = i / MT_IN_W, c = i - r * MT_IN_W;
-    const float* p = bufA + r * GM_RAW_S + c + gap;
-    float d = p[0];
-    if (d < 0) {
-      int l = 0, rr = 0;
-      float dl = -1.f, dr = -1.f;
-      for (int k = 1; k <= gap; k++) {
-        const float t = p[-k];
-        if (t >= 0) { l = k; dl = t; break; }
-      }
-      if (l > 0) {
-        for (int k = 1; k <= gap + 1 - l; k++) {
-          const float t = p[k];
-          if (t >= 0) { rr = k; dr = t; break; }
-        }
-        if (rr > 0) d = ipol(dl, dr);   // run length l + rr - 1 <= gap
-      }
-    }
-    bufB[r * MI_S + c] = d;
-  }
-  __syncthreads();
-  // column pass for the MT_ROWS rows of the mean tile (row r of it = staged row r + gap); outside the map
-  // the mean's tile holds 0
-  for (int i = tid; i < MT_ROWS * MT_IN_W; i += 256) {
-    const int r = i / MT_IN_W, c = i - r * MT_IN_W;
-    const float* p = bufB + (r + gap) * MI_S + c;
-    float d = p[0];
-    if (d < 0) {
-      int l = 0, rr = 0;
-      float dl = -1.f, dr = -1.f;
-      for (int k = 1; k <= gap; k++) {
-        const float t = p[-k * MI_S];
-        if (t >= 0) { l = k; dl = t; break; }
-      }
-      if (l > 0) {
-        for (int k = 1; k <= gap + 1 - l; k++) {
-          const float t = p[k * MI_S];
-          if (t >= 0) { rr = k; dr = t; break; }
-        }
-        if (rr > 0) d = ipol(dl, dr);
-      }
-    }
-    const int x = x0 - 4 + c, y = y0 - 4 + r;
-    bufA[r * MI_S + c] = (x >= 0 && x < W && y >= 0 && y < H) ? d : 0.f;
-  }
-  __syncthreads();
-  mean_tile_passes(bufA, bufB, W, H, x0, y0, tid, out + (size_t)frame * out_frame_stride);
-}
-
 // Half-resolution branch (elas.cpp:1323-1391): 4 taps at coordinates c-2 .. c+1, centre c.  The
 // reference's ring is indexed by coordinate mod 4 and summed ((l0+l1)+l2)+l3; rot = (c-2) & 3.
 __device__ __forceinline__ bool mean4(const float x[4], float centre, int rot, float& out) {
@@ -1179,13 +1097,9 @@ void launch_post(const Geo& g, int B, Workspace& ws, float* D1out, float* D2out,
   const size_t n = (size_t)g.Wd * g.Hd;
   const int sides = g.p.postprocess_only_left ? 1 : 2;
   post_lr(g, B, ws, s, sides == 2 || D2out != nullptr);
-  // ROBOTICS-style tail (small gaps, no border extrapolation, adaptive mean, full resolution): gap interpolation
-  // and the mean run as one kernel per output map (JN_POST_FUSED=0: the step-wise kernels)
-  static const bool fuse_env = !(getenv("JN_POST_FUSED") && getenv("JN_POST_FUSED")[0] == '0');
-  const bool fused = fuse_env && g.gap_eff <= SMALL_GAP && !g.p.add_corners && !g.p.subsampling && g.p.filter_adaptive_mean;
   for (int side = 0; side < sides; side++) {
     post_segments(g, B, ws, side, s);
-    if (!fused) post_gap(g, B, ws, side, s);
+    post_gap(g, B, ws, side, s);
   }
   for (int side = 0; side < 2; side++) {
     float* out = side ? D2out : D1out;
@@ -1193,13 +1107,7 @@ void launch_post(const Geo& g, int B, Workspace& ws, float* D1out, float* D2out,
     const float* cur = ws.Dlr[side];
     const bool filt = side < sides;
     const bool do_mean = filt && g.p.filter_adaptive_mean, do_med = filt && g.p.filter_median;
-    if (fused && filt) {
-      dim3 grid((g.Wd + MT_W - 1) / MT_W, (g.Hd + MT_H - 1) / MT_H, B);
-      float* mo = do_med ? ws.Dtmp2[side] : out;
-      gap_mean_fused_kernel<<<grid, 256, 0, s>>>(g, ws, cur, mo, n);
-      g_jn_launches += 1;
-      if (do_med) post_median(g, B, ws, ws.Dtmp2[side], ws.Dtmp[side], out, n, s);
-    } else if (do_mean && do_med) {
+    if (do_mean && do_med) {
       post_mean(g, B, ws, cur, ws.Dtmp[side], ws.Dtmp2[side], n, s);
       post_median(g, B, ws, ws.Dtmp2[side], ws.Dtmp[side], out, n, s);
     } else if (do_mean) {
