@@ -852,15 +852,30 @@ mean_fused_kernel(Geo g, Workspace ws, const float* __restrict__ in, float* __re
   const int W = g.Wd, H = g.Hd, tid = threadIdx.x;
   const int x0 = blockIdx.x * MT_W, y0 = blockIdx.y * MT_H;
   const float* src = in + (size_t)frame * W * H;
-  // a warp per tile row, lanes along the row (71 columns = 3 passes): no index division
-  for (int r = tid >> 5; r < MT_ROWS; r += 8) {
-    const int y = y0 - 4 + r;
-    const bool yin = y >= 0 && y < H;
-    const float* row = src + (size_t)(yin ? y : 0) * W;
+  // a warp per tile row, lanes along the row (71 columns = 3 passes): no index division; all 15 loads of a
+  // thread are issued before the first one is stored
+  {
+    constexpr int NR = (MT_ROWS + 7) / 8, NC = (MT_IN_W + 31) / 32;
+    float t[NR][NC];
 #pragma unroll
-    for (int c = tid & 31; c < MT_IN_W; c += 32) {
-      const int x = x0 - 4 + c;
-      s_in[r * MI_S + c] = (yin && x >= 0 && x < W) ? row[x] : 0.f;
+    for (int i = 0; i < NR; i++) {
+      const int r = (tid >> 5) + 8 * i, y = y0 - 4 + r;
+      const bool yin = r < MT_ROWS && y >= 0 && y < H;
+      const float* row = src + (size_t)(yin ? y : 0) * W;
+#pragma unroll
+      for (int k = 0; k < NC; k++) {
+        const int c = (tid & 31) + 32 * k, x = x0 - 4 + c;
+        t[i][k] = (yin && c < MT_IN_W && x >= 0 && x < W) ? row[x] : 0.f;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NR; i++) {
+      const int r = (tid >> 5) + 8 * i;
+#pragma unroll
+      for (int k = 0; k < NC; k++) {
+        const int c = (tid & 31) + 32 * k;
+        if (r < MT_ROWS && c < MT_IN_W) s_in[r * MI_S + c] = t[i][k];
+      }
     }
   }
   __syncthreads();
