@@ -258,7 +258,8 @@ static int make_geo(const jn_elas_params& p, const int32_t dims[3], Geo* out) {
   g.W = dims[0]; g.H = dims[1]; g.bpl = dims[2];
   if (g.W < 16 || g.H < 16 || g.bpl < g.W) { jn_set_error("bad dims %dx%d stride %d", g.W, g.H, g.bpl); return JN_ERR_ARG; }
   if (p.disp_max < 10 || p.disp_max > 4095 || p.disp_min > p.disp_max || p.candidate_stepsize < 1 ||
-      p.grid_size < 1 || p.incon_window_size < 0 || p.incon_window_size > 16) {
+      p.grid_size < 1 || p.incon_window_size < 0 || p.incon_window_size > 16 || p.incon_threshold < 0 ||
+      p.incon_threshold > 8191) {
     jn_set_error("parameter out of the supported range");
     return JN_ERR_ARG;
   }

@@ -366,7 +366,10 @@ __global__ void __launch_bounds__(256) incon_count_kernel(Geo g, const int16_t* 
   for (int i = tid; i < TWD * THT; i += 256) {
     const int ty = i / TWD, tx = i - ty * TWD;
     const int uu = u0 + tx, vv = v0 + ty;
-    tile[i] = (uu >= 0 && uu < Wc && vv >= 0 && vv < Hc) ? dc[vv * Wc + uu] : (int16_t)-1;
+    // invalid (-1) and out-of-lattice entries become a far value: "valid and within thr" is then ONE unsigned
+    // comparison, (unsigned)(d2 - (d - thr)) <= 2 * thr
+    const int16_t t = (uu >= 0 && uu < Wc && vv >= 0 && vv < Hc) ? dc[vv * Wc + uu] : (int16_t)-1;
+    tile[i] = t >= 0 ? t : (int16_t)-30000;
   }
   __syncthreads();
   const int u = blockIdx.x * 32 + threadIdx.x, v = blockIdx.y * 8 + threadIdx.y;
@@ -374,12 +377,11 @@ __global__ void __launch_bounds__(256) incon_count_kernel(Geo g, const int16_t* 
   const int d = tile[(threadIdx.y + r) * TWD + threadIdx.x + r];
   int c = 0;
   if (d >= 0) {
+    const int dlo = d - thr;
+    const unsigned span = 2u * (unsigned)thr;
     for (int dv = 0; dv <= 2 * r; dv++) {
       const int16_t* row = tile + (threadIdx.y + dv) * TWD + threadIdx.x;
-      for (int du = 0; du <= 2 * r; du++) {
-        const int d2 = row[du];
-        c += (d2 >= 0 && abs(d - d2) <= thr) ? 1 : 0;
-      }
+      for (int du = 0; du <= 2 * r; du++) c += ((unsigned)((int)row[du] - dlo) <= span) ? 1 : 0;
     }
   }
   cnt[(size_t)frame * Wc * Hc + v * Wc + u] = c;
