@@ -6,10 +6,9 @@
 //
 // All five are HBM-bound streaming passes over H*W floats.
 //   L/R check        one thread per pixel, out of place (the reference copies both maps first).
-//   small segments   4-connected components by union-find over horizontal RUNS: a warp per
-//                    row links every pixel to its run start and records the run length,
-//                    vertical unions use atomicMin with path halving, every non-root run
-//                    adds its length to its root.  At this stage every
+//   small segments   4-connected components, tiled: horizontal runs and the union-find of a
+//                    256 x 16 tile in shared memory, tile components linked across tile borders
+//                    by a global union-find, sizes summed at the roots.  At this stage every
 //                    invalid pixel is exactly -10 and similarity is symmetric, so the
 //                    components equal the reference's breadth-first segments.
 //   gap interpolation rows: one CTA per row (previous/next valid index by scans, any
@@ -88,63 +87,6 @@ __global__ void __launch_bounds__(Q_THREADS) lr4_kernel(Geo g, Workspace ws) {
 // ------------------------------------------------------------ small segments
 constexpr int ROW_THREADS = 256;
 
-// One warp per map row, 32 pixels per iteration, left to right.
-//   label[i]   = index of the first pixel of i's horizontal run of similar valid pixels; -1 if invalid
-//   segsize[s] = length of the run, written (once) for run starts s only -- the union-find below
-//                works on runs, so these are the initial component sizes and nothing else of
-//                segsize is ever read: no clearing pass.
-// Run starts come from one ballot per chunk; a run that crosses a chunk border is carried in
-// (warp-uniform) registers.  All accesses are fully coalesced.
-constexpr int SEG_ROWS_PER_CTA = 8;
-
-__global__ void __launch_bounds__(32 * SEG_ROWS_PER_CTA) seg_rows_kernel(Geo g, Workspace ws, int side) {
-  const int frame = blockIdx.y;
-  if (ws.info[frame].status != JN_OK) return;
-  const int W = g.Wd, H = g.Hd, lane = threadIdx.x & 31;
-  const int v = blockIdx.x * SEG_ROWS_PER_CTA + (threadIdx.x >> 5);
-  if (v >= H) return;
-  const size_t base = (size_t)frame * W * H + (size_t)v * W;
-  const float* __restrict__ D = ws.Dlr[side] + base;
-  int* __restrict__ label = ws.label + base;
-  int* __restrict__ segsize = ws.segsize + base;
-  const float thr = g.p.speckle_sim_threshold;
-  const unsigned le_mask = 0xFFFFFFFFu >> (31 - lane);   // lanes 0..lane
-  int cur = -1, cur_len = 0;   // start column / length so far of the run reaching the current chunk
-  float prev = -10.f;          // last pixel of the previous chunk
-  for (int u0 = 0; u0 < W; u0 += 32) {
-    const int u = u0 + lane;
-    const float d = (u < W) ? D[u] : -10.f;
-    float dl = __shfl_up_sync(0xffffffffu, d, 1);
-    if (lane == 0) dl = prev;
-    prev = __shfl_sync(0xffffffffu, d, 31);
-    const bool valid = d >= 0;
-    const bool start = valid && (u == 0 || !(dl >= 0) || fabsf(d - dl) > thr);
-    const unsigned sm = __ballot_sync(0xffffffffu, start);
-    const unsigned bm = sm | ~__ballot_sync(0xffffffffu, valid);   // a run cannot continue INTO these pixels
-    const unsigned below = sm & le_mask;
-    if (u < W) label[u] = valid ? v * W + (below ? u0 + 31 - __clz(below) : cur) : -1;
-    if (start) {
-      const unsigned above = bm & ~le_mask;
-      if (above) segsize[u] = __ffs(above) - 1 - lane;   // run ends inside this chunk
-    }
-    if (cur >= 0) {                 // the carried run covers the pixels before the first break
-      const int fb = bm ? __ffs(bm) - 1 : 32;
-      cur_len += fb;
-      if (fb < 32) {
-        if (lane == 0) segsize[cur] = cur_len;
-        cur = -1;
-      }
-    }
-    if (sm) {                       // the last start of the chunk may reach the chunk's end
-      const int ls = 31 - __clz(sm);
-      if (ls == 31 || (bm >> (ls + 1)) == 0u) { cur = u0 + ls; cur_len = 32 - ls; }
-    }
-  }
-  // pixels beyond W count as invalid, so a run touching the right border was closed in the loop
-  // unless W is a multiple of 32
-  if (cur >= 0 && lane == 0) segsize[cur] = cur_len;
-}
-
 __device__ __forceinline__ int uf_find(int* label, int x) {
   int p = __ldcg(label + x);   // L2 reads: other SMs update labels with atomics
   while (p != x) {
@@ -167,69 +109,8 @@ __device__ __forceinline__ void uf_union(int* label, int a, int b) {
   }
 }
 
-// Vertical links.  Pixel (u,v) and the pixel below are linked if both valid and similar.  Only one
-// thread per pair of horizontal runs has to do the union: a thread skips it if its left neighbour
-// makes the same link between the same two runs (both rows continue their runs to the left and
-// the left pixels are vertically similar too).  The left neighbours come from warp shuffles.
-__global__ void seg_merge_kernel(Geo g, Workspace ws, int side) {
-  const int frame = blockIdx.z;
-  if (ws.info[frame].status != JN_OK) return;
-  const int W = g.Wd, H = g.Hd;
-  const int u = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y;
-  if (v + 1 >= H) return;
-  const size_t fp = (size_t)frame * W * H;
-  const float* D = ws.Dlr[side] + fp;
-  const float thr = g.p.speckle_sim_threshold;
-  const int i = v * W + u;
-  const bool in = u < W;
-  const float d = in ? D[i] : -10.f, e = in ? D[i + W] : -10.f;
-  float dl = __shfl_up_sync(0xffffffffu, d, 1), el = __shfl_up_sync(0xffffffffu, e, 1);
-  if ((threadIdx.x & 31) == 0) {
-    dl = (in && u > 0) ? D[i - 1] : -10.f;
-    el = (in && u > 0) ? D[i + W - 1] : -10.f;
-  }
-  if (d >= 0 && e >= 0 && fabsf(d - e) <= thr) {
-    if (dl >= 0 && el >= 0 && fabsf(d - dl) <= thr && fabsf(e - el) <= thr && fabsf(dl - el) <= thr) return;
-    uf_union(ws.label + fp, i, i + W);
-  }
-}
-
-// Only the first pixel of every horizontal run walks to its root (runs, not pixels, are the
-// union-find elements); a start that is not a root adds its run length to the root's size and
-// leaves label[start] = root.  Starts are recognised from the map itself.
-__global__ void seg_count_kernel(Geo g, Workspace ws, int side) {
-  const int frame = blockIdx.z;
-  if (ws.info[frame].status != JN_OK) return;
-  const int W = g.Wd, H = g.Hd;
-  const int u = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y;
-  if (u >= W) return;
-  const size_t fp = (size_t)frame * W * H;
-  const int i = v * W + u;
-  const float* __restrict__ D = ws.Dlr[side] + fp;
-  const float d = D[i];
-  if (!(d >= 0)) return;
-  if (u > 0) {
-    const float dl = D[i - 1];
-    if (dl >= 0 && fabsf(d - dl) <= g.p.speckle_sim_threshold) return;   // not a run start
-  }
-  int* label = ws.label + fp;
-  // A component's root is its smallest pixel index and labels only decrease towards it, so
-  // compressing with atomicMin can never replace a root by a larger ancestor.
-  int x = i, p = __ldcg(label + x);
-  while (p != x) {
-    int gp = __ldcg(label + p);
-    if (gp != p) atomicMin(label + x, gp);
-    x = p;
-    p = gp;
-  }
-  if (x == i) return;                   // a root keeps its own run length
-  atomicMin(label + i, x);
-  // i is not a root, so nobody adds to segsize[i]: a plain read is safe
-  atomicAdd(ws.segsize + fp + x, ws.segsize[fp + i]);
-}
-
-// label[i] is i's run start or one of its ancestors (always a run start), and after
-// seg_count_kernel every run start points straight at its root: two hops at most.
+// label[i] is the root of i's tile component, and after seg_roots_kernel every tile root points straight
+// at its global root: two hops at most.
 __global__ void seg_apply_kernel(Geo g, Workspace ws, int side) {
   const int frame = blockIdx.z;
   if (ws.info[frame].status != JN_OK) return;
@@ -243,72 +124,7 @@ __global__ void seg_apply_kernel(Geo g, Workspace ws, int side) {
   if (ws.segsize[fp + root] < g.speckle_eff) ws.Dlr[side][a] = -10.f;
 }
 
-// Quad versions of the three kernels above (map width a multiple of 4).
-__global__ void __launch_bounds__(Q_THREADS) seg_merge4_kernel(Geo g, Workspace ws, int side) {
-  const int frame = blockIdx.z;
-  if (ws.info[frame].status != JN_OK) return;
-  const int W = g.Wd, H = g.Hd;
-  const int q = blockIdx.x * Q_THREADS + threadIdx.x, v = blockIdx.y;
-  if (v + 1 >= H) return;                       // uniform per CTA
-  const size_t fp = (size_t)frame * W * H;
-  const float* __restrict__ D = ws.Dlr[side] + fp;
-  const float thr = g.p.speckle_sim_threshold;
-  const int i0 = v * W + 4 * q;
-  const bool in = 4 * q < W;
-  const float4 none = make_float4(-10.f, -10.f, -10.f, -10.f);
-  const float4 dq = in ? *reinterpret_cast<const float4*>(D + i0) : none;
-  const float4 eq = in ? *reinterpret_cast<const float4*>(D + i0 + W) : none;
-  float dl = __shfl_up_sync(0xffffffffu, dq.w, 1), el = __shfl_up_sync(0xffffffffu, eq.w, 1);
-  if ((threadIdx.x & 31) == 0) {
-    dl = (in && q > 0) ? D[i0 - 1] : -10.f;
-    el = (in && q > 0) ? D[i0 + W - 1] : -10.f;
-  }
-  const float d[4] = {dq.x, dq.y, dq.z, dq.w}, e[4] = {eq.x, eq.y, eq.z, eq.w};
-#pragma unroll
-  for (int j = 0; j < 4; j++) {
-    if (d[j] >= 0 && e[j] >= 0 && fabsf(d[j] - e[j]) <= thr &&
-        !(dl >= 0 && el >= 0 && fabsf(d[j] - dl) <= thr && fabsf(e[j] - el) <= thr && fabsf(dl - el) <= thr))
-      uf_union(ws.label + fp, i0 + j, i0 + j + W);
-    dl = d[j];
-    el = e[j];
-  }
-}
-
-__global__ void __launch_bounds__(Q_THREADS) seg_count4_kernel(Geo g, Workspace ws, int side) {
-  const int frame = blockIdx.z;
-  if (ws.info[frame].status != JN_OK) return;
-  const int W = g.Wd, H = g.Hd;
-  const int q = blockIdx.x * Q_THREADS + threadIdx.x, v = blockIdx.y;
-  const size_t fp = (size_t)frame * W * H;
-  const float* __restrict__ D = ws.Dlr[side] + fp;
-  const float thr = g.p.speckle_sim_threshold;
-  const int i0 = v * W + 4 * q;
-  const bool in = 4 * q < W;
-  const float4 dq = in ? *reinterpret_cast<const float4*>(D + i0) : make_float4(-10.f, -10.f, -10.f, -10.f);
-  float prev = __shfl_up_sync(0xffffffffu, dq.w, 1);
-  if ((threadIdx.x & 31) == 0) prev = (in && q > 0) ? D[i0 - 1] : -10.f;
-  if (q == 0) prev = -10.f;
-  const float d[4] = {dq.x, dq.y, dq.z, dq.w};
-  int* label = ws.label + fp;
-#pragma unroll
-  for (int j = 0; j < 4; j++) {
-    const bool start = d[j] >= 0 && !(prev >= 0 && fabsf(d[j] - prev) <= thr);
-    prev = d[j];
-    if (!start) continue;
-    const int i = i0 + j;
-    int x = i, p = __ldcg(label + x);
-    while (p != x) {
-      int gp = __ldcg(label + p);
-      if (gp != p) atomicMin(label + x, gp);
-      x = p;
-      p = gp;
-    }
-    if (x == i) continue;
-    atomicMin(label + i, x);
-    atomicAdd(ws.segsize + fp + x, ws.segsize[fp + i]);
-  }
-}
-
+// Quad version of seg_apply_kernel (map width a multiple of 4).
 __global__ void __launch_bounds__(Q_THREADS) seg_apply4_kernel(Geo g, Workspace ws, int side) {
   const int frame = blockIdx.z;
   if (ws.info[frame].status != JN_OK) return;
@@ -340,15 +156,16 @@ __global__ void __launch_bounds__(Q_THREADS) seg_apply4_kernel(Geo g, Workspace 
 }
 
 // ---- tiled components: the union-find of a 256 x 16 tile runs in shared memory ----------------------
-// seg_tile_kernel labels the 4-connected components of ONE tile: horizontal runs from ballots (as
-// seg_rows_kernel), vertical links by a union-find on the run starts with shared-memory atomics (tens
+// seg_tile_kernel labels the 4-connected components of ONE tile: horizontal runs from one ballot per 32 pixels (a run
+// crossing a chunk border is carried in warp-uniform registers), vertical links by a union-find on the run starts with shared-memory atomics (tens
 // of cycles per hop instead of an L2 round trip), then every pixel's label is its tile component's
 // root (the smallest pixel index of the component, as a global index) and segsize is the tile
 // component's size at the root and 0 everywhere else.  seg_border_kernel then links tile components
 // across tile borders (1/16 of the row pairs, 1/256 of the column pairs) with the global union-find,
 // seg_roots_kernel adds the size of every tile root that is not a global root to its global root, and
-// seg_apply*_kernel reads label -> tile root -> global root -> size as before.
-// A vertical link is skipped when the left neighbours make the same link (see seg_merge_kernel); the
+// seg_apply*_kernel reads label -> tile root -> global root -> size.
+// A vertical link is skipped when the left neighbours make the same link (both rows continue their runs
+// to the left and the left pixels are vertically similar too: the link is implied by those three); the
 // links that argument relies on are in-tile run links or vertical links further left in the same tile,
 // never links that could be skipped for the mirrored reason: at a tile's left column and on vertical
 // tile borders every link is made.
@@ -1028,36 +845,19 @@ void post_lr(const Geo& g, int B, Workspace& ws, cudaStream_t s, bool need_right
 }
 
 void post_segments(const Geo& g, int B, Workspace& ws, int side, cudaStream_t s) {
-  dim3 pg((g.Wd + 255) / 256, g.Hd, B);
-  static const bool tiled = !(getenv("JN_SEG_TILED") && getenv("JN_SEG_TILED")[0] == '0');
-  if (tiled) {
-    const int n = g.Wd * g.Hd;
-    seg_tile_kernel<<<dim3((g.Wd + CT_W - 1) / CT_W, (g.Hd + CT_H - 1) / CT_H, B), CT_THREADS, 0, s>>>(g, ws, side);
-    const int nb = ((g.Hd - 1) / CT_H) * g.Wd + ((g.Wd - 1) / CT_W) * g.Hd;
-    if (nb > 0) seg_border_kernel<<<dim3((nb + 255) / 256, B), 256, 0, s>>>(g, ws, side);
-    if (n % 4 == 0) seg_roots_kernel<true><<<dim3((n / 4 + 255) / 256, B), 256, 0, s>>>(g, ws);
-    else seg_roots_kernel<false><<<dim3((n + 255) / 256, B), 256, 0, s>>>(g, ws);
-    if (g.Wd % 4 == 0) {
-      dim3 qg((g.Wd / 4 + Q_THREADS - 1) / Q_THREADS, g.Hd, B);
-      seg_apply4_kernel<<<qg, Q_THREADS, 0, s>>>(g, ws, side);
-    } else {
-      seg_apply_kernel<<<pg, 256, 0, s>>>(g, ws, side);
-    }
-    g_jn_launches += nb > 0 ? 4 : 3;
-    return;
-  }
-  seg_rows_kernel<<<dim3((g.Hd + SEG_ROWS_PER_CTA - 1) / SEG_ROWS_PER_CTA, B), 32 * SEG_ROWS_PER_CTA, 0, s>>>(g, ws, side);
+  const int n = g.Wd * g.Hd;
+  seg_tile_kernel<<<dim3((g.Wd + CT_W - 1) / CT_W, (g.Hd + CT_H - 1) / CT_H, B), CT_THREADS, 0, s>>>(g, ws, side);
+  const int nb = ((g.Hd - 1) / CT_H) * g.Wd + ((g.Wd - 1) / CT_W) * g.Hd;
+  if (nb > 0) seg_border_kernel<<<dim3((nb + 255) / 256, B), 256, 0, s>>>(g, ws, side);
+  if (n % 4 == 0) seg_roots_kernel<true><<<dim3((n / 4 + 255) / 256, B), 256, 0, s>>>(g, ws);
+  else seg_roots_kernel<false><<<dim3((n + 255) / 256, B), 256, 0, s>>>(g, ws);
   if (g.Wd % 4 == 0) {
     dim3 qg((g.Wd / 4 + Q_THREADS - 1) / Q_THREADS, g.Hd, B);
-    seg_merge4_kernel<<<qg, Q_THREADS, 0, s>>>(g, ws, side);
-    seg_count4_kernel<<<qg, Q_THREADS, 0, s>>>(g, ws, side);
     seg_apply4_kernel<<<qg, Q_THREADS, 0, s>>>(g, ws, side);
   } else {
-    seg_merge_kernel<<<pg, 256, 0, s>>>(g, ws, side);
-    seg_count_kernel<<<pg, 256, 0, s>>>(g, ws, side);
-    seg_apply_kernel<<<pg, 256, 0, s>>>(g, ws, side);
+    seg_apply_kernel<<<dim3((g.Wd + 255) / 256, g.Hd, B), 256, 0, s>>>(g, ws, side);
   }
-  g_jn_launches += 4;
+  g_jn_launches += nb > 0 ? 4 : 3;
 }
 
 void post_gap(const Geo& g, int B, Workspace& ws, int side, cudaStream_t s) {

@@ -352,12 +352,14 @@ support_match_kernel(Geo g, const uint8_t* __restrict__ desc1, const uint8_t* __
 
 // c0(p) = number of lattice points q in the (2r+1)^2 window (p included) that are
 // valid and within incon_threshold of p, on the ORIGINAL candidate image.
+// RC = window radius known at compile time (5: both presets; fully unrolled), 0 = run-time radius
+template <int RC>
 __global__ void __launch_bounds__(256) incon_count_kernel(Geo g, const int16_t* __restrict__ dcan,
                                                           int32_t* __restrict__ cnt) {
   // candidate tile + window halo in shared memory (window radius <= 16, checked in make_geo);
   // lattice points outside the image read as invalid
   __shared__ int16_t tile[(8 + 32) * (32 + 32)];
-  const int Wc = g.Wc, Hc = g.Hc, r = g.p.incon_window_size, thr = g.p.incon_threshold;
+  const int Wc = g.Wc, Hc = g.Hc, r = RC ? RC : g.p.incon_window_size, thr = g.p.incon_threshold;
   const int frame = blockIdx.z;
   const int tid = threadIdx.y * 32 + threadIdx.x;
   const int TWD = 32 + 2 * r, THT = 8 + 2 * r;
@@ -379,8 +381,10 @@ __global__ void __launch_bounds__(256) incon_count_kernel(Geo g, const int16_t* 
   if (d >= 0) {
     const int dlo = d - thr;
     const unsigned span = 2u * (unsigned)thr;
+#pragma unroll
     for (int dv = 0; dv <= 2 * r; dv++) {
       const int16_t* row = tile + (threadIdx.y + dv) * TWD + threadIdx.x;
+#pragma unroll
       for (int du = 0; du <= 2 * r; du++) c += ((unsigned)((int)row[du] - dlo) <= span) ? 1 : 0;
     }
   }
@@ -738,7 +742,8 @@ int launch_support_match(const Geo& g, int B, Workspace& ws, cudaStream_t s) {
 // Filtering + compaction of the candidate images in ws.dcan (also driven directly by the tests).
 int launch_support_filter(const Geo& g, int B, Workspace& ws, cudaStream_t s) {
   dim3 cb(32, 8), cg((g.Wc + 31) / 32, (g.Hc + 7) / 8, B);
-  incon_count_kernel<<<cg, cb, 0, s>>>(g, ws.dcan, ws.cnt);
+  if (g.p.incon_window_size == 5) incon_count_kernel<5><<<cg, cb, 0, s>>>(g, ws.dcan, ws.cnt);
+  else incon_count_kernel<0><<<cg, cb, 0, s>>>(g, ws.dcan, ws.cnt);
   // + 16: the byte arrays of the frontier phase (two of NP bytes, the second one word aligned) end up to
   // three bytes past 2 * NP
   const size_t np = (size_t)g.Wc * g.Hc;
