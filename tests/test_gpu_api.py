@@ -138,6 +138,28 @@ def test_rolling_device_submissions_equal_stream_api(jn, synth):
     e.close(); e2.close(); sc.close()
 
 
+def test_forty_calls_on_one_handle_leave_no_state_behind(jn, oracle, synth):
+    """Workspace buffers are reused from call to call (plane maps, labels, candidate images, grids): 40 calls on one
+    handle, scenes alternating so that triangles and uncovered areas move, every result bit-exact."""
+    W, H, dm = 200, 150, 48
+    e = jn.Elas(jn.parameters(jn.ROBOTICS, disp_max=dm))
+    D1 = np.zeros((H, W), np.float32)
+    refs = {}
+    for call in range(40):
+        seed, scene = 300 + call % 5, ("textured" if call % 2 else "random_dot")
+        L, R = synth.scene_batch(scene, W, H, dm, [seed])
+        I1, I2 = L[0].copy(), R[0].copy()
+        if call % 3 == 0:                       # a textureless band: pixels no triangle of THIS call covers
+            I1[: H // 3] = 128; I2[: H // 3] = 128
+        key = (seed, scene, call % 3 == 0)
+        if key not in refs:
+            refs[key] = oracle.process(ol.robotics(dm), I1, I2)[0]
+        D1[:] = 7
+        rc = e.process(I1, I2, D1, None, (W, H, W))
+        assert rc == 0 and np.array_equal(D1, refs[key]), call
+    e.close()
+
+
 def test_c4_seeds_full_size(jn, oracle, synth):
     """BASELINE config C4: 1920x1200 pairs with seeds 1000.. -- 32 of them (spread over the 1024),
     final maps bit-exact against the oracle, in one batch through the device-resident entry point."""
