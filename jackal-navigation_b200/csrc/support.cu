@@ -4,24 +4,26 @@
 // (elas.cpp:375-443), removeInconsistentSupportPoints (elas.cpp:153-179) and
 // removeRedundantSupportPoints (elas.cpp:181-235).
 //
-// support_match_kernel: one CTA per candidate row.  The four descriptor rows a
-// candidate row touches (v-2 and v+2 of both images, W*16 bytes each) are
-// fetched once with 1-D bulk async copies (TMA unit) into shared memory; a warp
-// owns four neighbouring candidates, its lanes stride the POSITIONS of the
-// searched rows: a lane loads the four searched descriptors of its position once
-// (conflict-free 128-bit shared loads) and scores them against all four
-// candidates, 16 VABSDIFF4.U8.ACC each.  The (best, second best) pair is order
-// independent (second best = second smallest energy of the multiset, best =
-// lowest disparity among the minima, H7), so it is kept as two packed keys per
-// lane and reduced over the warp with two REDUX.MIN.  The kernel is bound by the
-// integer ALU pipe (85 % busy, 61 % of that in the SADs themselves).
+// support_match_kernel: a CTA matches the candidates of (part of) a candidate row.  The
+// descriptor rows they touch (v-2 and v+2 of both images; only the columns those candidates
+// can reach) are fetched with 1-D bulk async copies (TMA unit) into shared memory; at 1920 px
+// two half-row CTAs share an SM.  A warp owns four neighbouring candidates, its lanes stride
+// the POSITIONS of the searched rows: a lane loads the four searched descriptors of its
+// position once (conflict-free 128-bit shared loads) and scores them against all four
+// candidates, 16 VABSDIFF4.U8.ACC each; the four equally long ranges are tiled without masked
+// lanes (wrapped tiling, see match_group).  The (best, second best) pair is order independent
+// (second best = second smallest energy of the multiset, best = lowest disparity among the
+// minima, H7), so it is kept as two packed keys per lane and reduced over the warp with two
+// REDUX.MIN.  The kernel is bound by the integer ALU pipe (~60 % of the VABSDIFF4 issue ceiling).
 //
 // The in-place, scan-ordered inconsistency filter (H3) is computed exactly by
 // a monotone frontier propagation: a point's final validity only depends on
 // how many EARLIER similar neighbours were invalidated, so starting from the
 // points whose original support count is too low and decrementing the counters
 // of their later neighbours reaches the unique fixed point = the sequential
-// result.  The two redundancy passes carry dependencies along one axis only.
+// result; it runs on byte arrays in shared memory.  The two redundancy passes carry
+// dependencies along one axis only: the side that looks at unprocessed entries is evaluated for
+// all points in parallel, the serial walk keeps the last five decided entries in registers.
 #include "common.cuh"
 #include "blockutil.cuh"
 
