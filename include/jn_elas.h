@@ -167,7 +167,10 @@ typedef struct jn_scan_meta {
 typedef struct jn_scan jn_scan;
 
 /* Builds the per-pixel ground-plane gate cache on the device
- * (cacheDisparityValues, point_cloud.cpp:104-147). */
+ * (cacheDisparityValues, point_cloud.cpp:104-147).
+ * Concurrency: like a jn_elas handle, a jn_scan handle owns one set of accumulators (bins, extrema,
+ * point counters) -- one call in flight at a time, one stream at a time; the gate cache itself is
+ * read-only after creation.  Use one handle per thread / per stream. */
 jn_scan* jn_scan_create(const jn_calib* c, int width, int height,
                         int crop_offset_x, int crop_offset_y, int device);
 void     jn_scan_destroy(jn_scan* s);

@@ -37,11 +37,14 @@
 // functions.  Everything around them (ordering, partition, level-synchronous scheduling, the
 // table layouts, the subtree tiling) is this kernel's own organisation.
 //
-// Known deviation: among duplicate right-image points (u-d,v) Triangle keeps
-// the one its randomized quicksort happens to put first; this kernel keeps the
-// lowest support index.
+// Coincident points (right-image points (u-d,v) of two support points of a row; possible only with
+// lr_threshold >= candidate_stepsize / 2, i.e. not with the presets): Triangle keeps the copy its
+// randomised quicksort happens to put first.  The radix sort cannot know that order, so a point set
+// that contains copies (and only such a set) has that quicksort replayed by one thread
+// (vertexsort.cuh, checked against the compiled reference on the host) to pick the survivors.
 #include "common.cuh"
 #include "blockutil.cuh"
+#include "vertexsort.cuh"
 
 namespace {
 
@@ -558,6 +561,17 @@ __device__ int partition_levels(TI*& xl, TI*& yl, TI*& sp, TI* scan, TI* seglo, 
 
 constexpr int OCC_EMPTY = 0x7f7f7f7f;   // cudaMemset(0x7f) pattern
 
+// vertexsort_replay operands: support indices with their packed (x,y) keys in a table (shared
+// memory path), or (key, index) records (global memory path)
+struct KeyByIndex {
+  const unsigned* k;
+  __host__ __device__ unsigned operator()(unsigned short v) const { return k[v]; }
+};
+struct KeyVertex { unsigned k; int v; };
+struct KeyOfRecord {
+  __host__ __device__ unsigned operator()(const KeyVertex& r) const { return r.k; }
+};
+
 __global__ void __launch_bounds__(DT, 1)
 delaunay_kernel(Geo g, Workspace ws) {
   extern __shared__ __align__(16) unsigned char dsm[];
@@ -602,11 +616,39 @@ delaunay_kernel(Geo g, Workspace ws) {
     radix_pass(K1, R1, K0, R0, n, RADIX_BITS, hist, s_part);
     radix_pass(K0, R0, K1, R1, n, 2 * RADIX_BITS, hist, s_part);
     radix_pass(K1, R1, K0, R0, n, 3 * RADIX_BITS, hist, s_part);
-    // 1b. the first of every (x,y) run survives = lowest support index (K1 is free: scan scratch)
+    // 1b. the first of every (x,y) run survives (K1 is free: scan scratch)
     int* scan32 = reinterpret_cast<int*>(K1);
     for (int i = tid; i < n; i += DT) scan32[i] = (i == 0) || (K0[i] != K0[i - 1]);
     __syncthreads();
     nu = block_exclusive_scan(scan32, n, s_part);
+    if (nu < n) {
+      // Coincident points.  Which copy is "first" in Triangle's sortarray is decided by its randomised
+      // quicksort (vertexsort.cuh): replay it -- serial, one thread, keys by support index in K1, the
+      // index array in R1, the stack of pending parts in R6 -- and take the order of the copies inside
+      // every run from it.  The runs themselves sit where the radix sort put them (same keys).
+      unsigned* KI = K1;
+      u16* A = R1;
+      for (int i = tid; i < n; i += DT) {
+        KI[i] = ((unsigned)px[i] << 13) | (unsigned)py[i];
+        A[i] = (u16)i;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        KeyByIndex key;
+        key.k = KI;
+        s_flag = vertexsort_replay(A, n, key, reinterpret_cast<u16*>(R6), SORT_MAX / 4) ? 1 : 0;
+      }
+      __syncthreads();
+      if (!s_flag) {   // more than 4 096 pending parts: not a quicksort that terminates in this lifetime
+        if (tid == 0) { info->status = JN_ERR_UNSUPPORTED; info->n_tri[side] = 0; }
+        return;
+      }
+      for (int i = tid; i < n; i += DT) R0[i] = A[i];
+      __syncthreads();
+      for (int i = tid; i < n; i += DT) scan32[i] = (i == 0) || (K0[i] != K0[i - 1]);
+      __syncthreads();
+      nu = block_exclusive_scan(scan32, n, s_part);
+    }
     u16* xl = R1;
     for (int i = tid; i < n; i += DT)
       if ((i == 0) || (K0[i] != K0[i - 1])) xl[scan32[i]] = R0[i];
@@ -652,6 +694,33 @@ delaunay_kernel(Geo g, Workspace ws) {
     for (int c = tid; c < cells; c += DT) scanbig[c] = occ[c] != OCC_EMPTY;
     __syncthreads();
     nu = block_exclusive_scan(scanbig, cells, s_part);
+    if (nu < n) {
+      // Coincident points: the occupancy grid kept the lowest support index of every cell, Triangle
+      // keeps the copy its quicksort puts first.  Replay the quicksort (vertexsort.cuh; serial, one
+      // thread) on (key, index) records in the rows of the global triangle table, which the merges
+      // only start to use later, with the stack in the idle shared memory, and put the first record of
+      // every run into its cell.  Which cells are occupied does not change: the scan above stands.
+      KeyVertex* A = reinterpret_cast<KeyVertex*>(ws.nb[side] + (size_t)frame * g.cap_t * 3);
+      for (int i = tid; i < n; i += DT) {
+        A[i].k = ((unsigned)px[i] << 13) | (unsigned)py[i];
+        A[i].v = i;
+      }
+      __syncthreads();
+      if (tid == 0)
+        s_flag = vertexsort_replay(A, n, KeyOfRecord(), reinterpret_cast<int*>(dsm), (int)(DELAUNAY_SMEM / 8)) ? 1 : 0;
+      __syncthreads();
+      if (!s_flag) {
+        if (tid == 0) { info->status = JN_ERR_UNSUPPORTED; info->n_tri[side] = 0; }
+        return;
+      }
+      for (int i = tid; i < n; i += DT) {
+        if (i == 0 || A[i].k != A[i - 1].k) {
+          const int id = A[i].v;
+          occ[((px[id] - xb) / xdiv) * Hc + py[id] / step] = id;
+        }
+      }
+      __syncthreads();
+    }
     for (int c = tid; c < cells; c += DT) {
       int id = occ[c];
       if (id != OCC_EMPTY) xl[scanbig[c]] = id;

@@ -3,6 +3,7 @@ symbol, presets equal the reference's, the YAML reader, loud failure without a G
 import ctypes as C
 import os
 import re
+import subprocess
 import numpy as np
 import pytest
 import oracle_lib as ol
@@ -179,3 +180,61 @@ def test_calibration_to_q_without_opencv(jn):
     for name, (cw, ch, nw, nh, scale) in {"640x480": (640, 360, 640, 480, 1), "320x180": (640, 360, 320, 180, 1)}.items():
         cal.stereo_rectify(cw, ch, nw, nh)
         assert np.allclose(cal.arrays()["Q"], np.array(fx[name]), rtol=1e-9, atol=1e-10), name
+
+
+def _vertexsort_lib(tmp_path):
+    so = str(tmp_path / "libvs.so")
+    subprocess.run(["g++", "-O1", "-std=c++14", "-shared", "-fPIC", "-I", os.path.join(ROOT, "jackal-navigation_b200", "csrc"),
+                    os.path.join(ROOT, "tests", "cpp", "vertexsort_host.cpp"), "-o", so], check=True, capture_output=True)
+    lib = C.CDLL(so)
+    lib.vs_sorted_order.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    lib.vs_sorted_order_records.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    return lib
+
+
+def test_vertexsort_replay_keeps_the_copies_triangle_keeps(oracle, tmp_path):
+    """csrc/vertexsort.cuh (run by one thread of the delaunay kernel when a point set holds coincident
+    points) compiled for the host: the first entry of every run of equal points in its sorted order is
+    the copy Triangle keeps (triangle.cpp:5446-5499, 6179-6195) = the vertex ids its triangles use."""
+    lib = _vertexsort_lib(tmp_path)
+    rng = np.random.default_rng(77)
+    checked = 0
+    for it in range(400):
+        n = int(rng.integers(3, 400))
+        mode = it % 4
+        if mode == 0:
+            pts = rng.integers(1, 7, size=(n, 2)) * 5                       # almost only copies
+        elif mode == 1:
+            pts = rng.integers(1, int(rng.integers(3, 40)), size=(n, 2)) * 5
+        elif mode == 2:                                                     # right-image like: (u - d, v)
+            pts = np.stack([rng.integers(1, 60, size=n) * 5 - rng.integers(0, 12, size=n) + 64,
+                            rng.integers(1, 12, size=n) * 5], 1)
+        else:
+            pts = rng.integers(0, 2000, size=(n, 2))                        # (almost) no copies
+        x = np.ascontiguousarray(pts[:, 0], np.int32); y = np.ascontiguousarray(pts[:, 1], np.int32)
+        order = np.empty(n, np.int32)
+        assert lib.vs_sorted_order(x.ctypes.data, y.ctypes.data, n, order.ctypes.data, 4096) == 0
+        assert np.array_equal(np.sort(order), np.arange(n))
+        order2 = np.empty(n, np.int32)     # (key, vertex) records instead of vertex numbers: same order
+        assert lib.vs_sorted_order_records(x.ctypes.data, y.ctypes.data, n, order2.ctypes.data, 4096) == 0
+        assert np.array_equal(order, order2)
+        key = (x[order].astype(np.int64) << 13) | y[order]
+        assert np.all(np.diff(key) >= 0)
+        first = np.concatenate([[True], np.diff(key) != 0])
+        survivors = np.sort(order[first])
+        tri = oracle.triangulate(pts)
+        if len(tri) == 0:
+            continue                      # collinear / fewer than three distinct points: nothing to read the ids from
+        assert np.array_equal(np.unique(tri), survivors), (it, mode, n)
+        checked += 1 if len(survivors) < n else 0
+    assert checked >= 150                 # sets with coincident points that produced triangles
+
+
+def test_vertexsort_replay_reports_a_full_stack(tmp_path):
+    lib = _vertexsort_lib(tmp_path)
+    rng = np.random.default_rng(5)
+    pts = rng.integers(0, 3000, size=(2000, 2)).astype(np.int32)
+    x = np.ascontiguousarray(pts[:, 0]); y = np.ascontiguousarray(pts[:, 1])
+    order = np.empty(2000, np.int32)
+    assert lib.vs_sorted_order(x.ctypes.data, y.ctypes.data, 2000, order.ctypes.data, 2) == -1
+    assert lib.vs_sorted_order(x.ctypes.data, y.ctypes.data, 2000, order.ctypes.data, 64) == 0
