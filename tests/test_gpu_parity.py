@@ -49,6 +49,8 @@ def test_cuda_matches_golden(jn, name, H):
     (320, 240, 64, 8, {"ipol_gap_width": 5000, "filter_median": 1, "filter_adaptive_mean": 0,
                        "postprocess_only_left": 0, "match_texture": 0, "gamma": 5.0, "sradius": 3.0,
                        "support_threshold": 0.95}),                                    # MIDDLEBURY minus add_corners
+    (320, 240, 64, 4, {"sradius": 4.0}),                               # plane radius 4: run-time radius kernel
+    (333, 251, 100, 6, {"sigma": 2.0, "sradius": 3.5, "match_texture": 3}),   # plane radius 7 (the largest covered)
     (2200, 1300, 255, 2, {}),                                          # lattice too large for the smem filter
     (1920, 600, 255, 1001, {}),                                        # C3 with -h 600 crop
 ])
@@ -228,6 +230,7 @@ def test_few_support_points_leave_outputs_untouched(jn, capsys):
     (320, 240, 64, 8, "robotics", {"ipol_gap_width": 40, "speckle_size": 30}),
     (320, 240, 64, 3, "middlebury", {}),
     (640, 480, 255, 12, "middlebury", {}),
+    (320, 240, 64, 4, "robotics", {"sradius": 5.0}),                      # run-time plane radius, subsampled
     (1920, 1200, 255, 1001, "robotics", {}),
 ])
 def test_subsampling_every_stage_matches_oracle(jn, oracle, synth, W, H, dm, seed, preset, kw):
