@@ -237,16 +237,15 @@ __device__ __forceinline__ void eval_bits_checked(unsigned& best, unsigned bits,
 #define JN_DENSE_MINB (2048 / JN_DENSE_THREADS)   // 32 registers: all 64 warps of an SM resident
 #endif
 
-#ifndef JN_DENSE_BASES
-#define JN_DENSE_BASES 1
-#endif
-
-#if JN_DENSE_BASES
 // Frame-level base addresses of a CTA (frame and side are the same for all its threads), kept in
 // SHARED memory and re-read where they are needed (LDS.64 + one IMAD.WIDE per address).  Held in
 // registers they do not fit next to the candidate loop at 32 registers per thread, and ptxas then
-// rebuilds every address from the kernel parameters and the CTA / thread ids at every use: ~90 of
-// the ~270 instructions per pixel of this issue-bound kernel were such address arithmetic.
+// rebuilds every address from the kernel parameters and the CTA / thread ids at every use: ~50 of
+// the ~270 instructions per pixel of this issue-bound kernel were such address arithmetic
+// (2.75 -> 2.52 ms per 64 frames).  Measured on top of this and NOT kept (profiles/r02_dense_variants.txt;
+// ptxas is at the edge of the 32-register budget here and answers small changes with spills): an outer
+// loop over grid rows instead of the per-row "cell changed?" test (+3.5 %), retiring the four border
+// columns before the row loop (+14 %), 20 rows per CTA (+0.5 %), 42 registers at 12 CTAs per SM (+17 %).
 enum { DB_PMAP = 0, DB_A, DB_B, DB_OUT, DB_CELLS, DB_MASKS, DB_COUNT };
 // sb = shared-space address of the table (a link-time constant: the load is LDS.64 [imm]); volatile: every
 // use re-reads it instead of keeping twelve registers alive across the row loop
@@ -426,183 +425,6 @@ dense_kernel(Geo g, Workspace ws) {
   if (side) dense_body<R, SUB, 1>(g, ws, sb);
   else dense_body<R, SUB, -1>(g, ws, sb);
 }
-#else
-template <int R, bool SUB, int DIR>
-__device__ __forceinline__ void dense_body(const Geo& g, const Workspace& ws) {
-  constexpr int side = DIR > 0 ? 1 : 0;
-  const int frame = blockIdx.z >> 1;
-  const int W = g.W, H = g.H;
-  const int um = blockIdx.x * DENSE_THREADS + threadIdx.x;     // map column
-  const unsigned am = __ballot_sync(0xffffffffu, um < g.Wd);   // lanes that stay
-  if (um >= g.Wd) return;
-  const int u = SUB ? 2 * um : um;
-  // frame-level bases once per thread; everything below is 32-bit offsets from them
-  const size_t fpix = (size_t)frame * W * H;
-  const uint4* __restrict__ Af = reinterpret_cast<const uint4*>(ws.desc[side] + fpix * 16);
-  const uint4* __restrict__ Bf = reinterpret_cast<const uint4*>(ws.desc[side ^ 1] + fpix * 16);
-  const unsigned* __restrict__ pmap = reinterpret_cast<const unsigned*>(ws.trimap[side]) + fpix;
-  float* __restrict__ outp = ws.Draw[side] + (SUB ? (size_t)frame * g.Wd * g.Hd : fpix);
-  const uint32_t* __restrict__ masks = ws.gridmask[side] + (size_t)frame * g.gw * g.gh * g.gwords;
-  const uint4* __restrict__ cells =
-      reinterpret_cast<const uint4*>(ws.gridlist[side] + (size_t)frame * g.gw * g.gh * GRID_LIST);
-  // Per-column pointers.  The compiler rebuilds them from the kernel parameters in every row instead
-  // of keeping them in registers; that costs ~40 instructions per row but keeps the kernel at 32
-  // registers = 64 resident warps per SM, and the latency tolerance of full occupancy is worth more
-  // here than the instructions (pinned pointers, a two-row software pipeline with prefetch, and
-  // batched grid loads were all measured: 48-64 registers, 1.8-2.0 ms against 1.43 ms per 32 frames).
-  const unsigned* pm_u = pmap + u;
-  const uint4* A_u = Af + u;
-  const uint4* B_u = Bf + u;
-  float* o_u = outp + (SUB ? um : u);
-  const unsigned gx = __umulhi((unsigned)u, g.gs_magic);
-  constexpr int dir = DIR;
-  const int dmax = g.p.disp_max;
-  const unsigned wm4 = (unsigned)(W - 4);
-  const bool u_ok = u >= 2 && u < W - 2;
-  const int r = R ? R : g.plane_radius;
-  const int dbits = g.pm_dbits;
-  const unsigned dmask = (1u << dbits) - 1u;
-  // no candidate of this column can leave the image: u_warp = u + dir*d in [2, W-3] for all d in [0, disp_max]
-  const bool col_free = side ? (u >= 2 && u + dmax <= W - 3) : (u - dmax >= 2 && u <= W - 3);
-  const bool warp_free = R != 0 && __all_sync(am, col_free);
-  // key addends of the plane range per |k|: (2048 + prior) << 13 | class bit, with and without the prior
-  const unsigned addv0 = ((unsigned)(2048 + g.P[0]) << 13) | KEY_PLANE;
-  const unsigned addv1 = ((unsigned)(2048 + g.P[1]) << 13) | KEY_PLANE;
-  const unsigned addv2 = ((unsigned)(2048 + g.P[2]) << 13) | KEY_PLANE;
-  const unsigned addv3 = ((unsigned)(2048 + g.P[3]) << 13) | KEY_PLANE;
-  const unsigned addn = KEY_BIAS | KEY_PLANE;
-  const int vm_end = min((int)(blockIdx.y + 1) * DENSE_ROWS, g.Hd);
-  int vm = blockIdx.y * DENSE_ROWS;
-  uint4 cw = make_uint4(0u, 0u, 0u, 0u), cm = make_uint4(0u, 0u, 0u, 0u);
-  unsigned ci = 0u, gy_cur = 0xFFFFFFFFu;
-  int nwords = 0;
-  auto load_row = [&](int vmr, unsigned& e, uint4& a) {
-    const int v = SUB ? 2 * vmr : vmr;
-    e = __ldg(pm_u + (unsigned)(v * W));
-    a = __ldg(A_u + (unsigned)(max(min(v, H - 3), 2) * W));
-  };
-  auto match_row = [&](const int vm, const unsigned e, const uint4& a) {
-      const int v = SUB ? 2 * vm : vm;
-      // rows inside one grid row share the cell: (re)load its candidate words when the grid row changes
-      const unsigned gy = __umulhi((unsigned)v, g.gs_magic);
-      if (gy != gy_cur) {
-        gy_cur = gy;
-        ci = gy * (unsigned)g.gw + gx;
-        cw = __ldg(cells + 2u * ci);
-        cm = __ldg(cells + 2u * ci + 1u);
-        nwords = (int)cm.y;
-      }
-      const unsigned rowoff = (unsigned)(max(min(v, H - 3), 2) * W);
-      const bool act = e != 0u && u_ok && (int)texture16(a) >= g.p.match_texture;
-      const int d_plane = (int)(e & dmask) - (r + 1);
-      const bool valid = (e >> dbits) & 1u;
-      const bool inside = d_plane - r >= 0 && d_plane + r <= dmax;       // whole plane range in [0, disp_max]
-      const bool quick = warp_free && __all_sync(am, inside || !act);
-      float out = -10.f;
-      if (act) {
-        unsigned best = KEY_NONE;
-        if (R != 0 && quick) {
-          // ---- no per-candidate test anywhere
-          const uint4* __restrict__ Brow = B_u + rowoff;                   // candidate d at Brow[dir * d]
-          const int lo = d_plane - R, hi = d_plane + R;
-          const uint4* __restrict__ Bp = step16<DIR>(Brow, d_plane);
-          unsigned bestg = KEY_NONE;
-          if (nwords != GRID_OVERFLOW) {
-#pragma unroll
-            for (int j = 0; j < GRID_WORDS; j++) {
-              if (j < nwords) {
-                const int wbase = 32 * (int)((cm.x >> (8 * j)) & 0xFFu);
-                unsigned bits =
-                    outside_range(j == 0 ? cw.x : (j == 1 ? cw.y : (j == 2 ? cw.z : cw.w)), wbase, lo, hi);
-                if (bits) {
-                  const uint4* __restrict__ Bw = step16<DIR>(Brow, wbase);
-                  unsigned bw = KEY_NONE;
-                  do {
-                    const int b = top_bit(bits);
-                    bits ^= 1u << b;
-                    const uint4 c = __ldg(step16<DIR>(Bw, b));
-                    bw = min(bw, sad16(a, c, 0u) * 8192u + (unsigned)b);
-                  } while (bits);
-                  bestg = min(bestg, bw + (unsigned)wbase);
-                }
-              }
-            }
-          } else {
-            const uint32_t* cell = masks + ci * (unsigned)g.gwords;
-            for (int w = 0; w < g.gwords; w++) {
-              unsigned bits = outside_range(__ldg(cell + w), 32 * w, lo, hi);
-              while (bits) {
-                const int b = top_bit(bits);
-                bits ^= 1u << b;
-                const int d = 32 * w + b;
-                const uint4 c = __ldg(step16<DIR>(Brow, d));
-                bestg = min(bestg, sad16(a, c, 0u) * 8192u + (unsigned)d);
-              }
-            }
-          }
-          if (bestg != KEY_NONE) best = bestg + KEY_BIAS;
-          // the 2R+1 plane-range descriptors are consecutive: one address, immediate offsets, all loads
-          // issued before the first SAD (after the grid walk: 20 registers that must not be live during it)
-          uint4 bb[2 * R + 1];
-#pragma unroll
-          for (int q = -R; q <= R; q++) bb[q + R] = __ldg(Bp + q);        // disparity d_plane + dir * q
-          const unsigned k0 = (valid ? addv0 : addn) + (unsigned)d_plane;
-          const unsigned k1 = (valid ? addv1 : addn) + (unsigned)d_plane;
-          const unsigned k2 = (valid ? addv2 : addn) + (unsigned)d_plane;
-          const unsigned k3 = (valid ? addv3 : addn) + (unsigned)d_plane;
-#pragma unroll
-          for (int q = -R; q <= R; q++) {
-            const int aq = q < 0 ? -q : q;
-            const unsigned kq = (aq == 0 ? k0 : (aq == 1 ? k1 : (aq == 2 ? k2 : k3))) + (unsigned)(dir * q);
-            best = min(best, sad16(a, bb[q + R], 0u) * 8192u + kq);
-          }
-        } else {
-          // ---- checked path: image borders, plane ranges clipped by [0, disp_max], run-time radius
-          const int lo = max(d_plane - r, 0), hi = min(d_plane + r, dmax);
-          if (nwords != GRID_OVERFLOW) {
-#pragma unroll
-            for (int j = 0; j < GRID_WORDS; j++) {
-              if (j < nwords) {
-                const int wbase = 32 * (int)((cm.x >> (8 * j)) & 0xFFu);
-                const unsigned bits =
-                    outside_range(j == 0 ? cw.x : (j == 1 ? cw.y : (j == 2 ? cw.z : cw.w)), wbase, lo, hi);
-                eval_bits_checked(best, bits, wbase, a, Bf, rowoff, u, dir, wm4);
-              }
-            }
-          } else {
-            const uint32_t* cell = masks + ci * (unsigned)g.gwords;
-            for (int w = 0; w < g.gwords; w++)
-              eval_bits_checked(best, outside_range(__ldg(cell + w), 32 * w, lo, hi), 32 * w, a, Bf, rowoff, u,
-                                dir, wm4);
-          }
-          for (int d = lo; d <= hi; d++) {
-            const int ad = abs(d - d_plane);
-            const unsigned add = valid ? (((unsigned)(2048 + g.P[ad]) << 13) | KEY_PLANE) : addn;
-            eval_candidate(best, a, Bf, rowoff, u, dir, d, add, wm4);
-          }
-        }
-        out = (best != KEY_NONE) ? (float)(best & 0xFFFu) : -1.f;
-      }
-      o_u[(unsigned)(vm * g.Wd)] = out;
-  };
-#pragma unroll 1
-  for (; vm < vm_end; vm++) {
-    unsigned e;
-    uint4 a;
-    load_row(vm, e, a);
-    match_row(vm, e, a);
-  }
-}
-
-template <int R, bool SUB>
-__global__ void __launch_bounds__(DENSE_THREADS, JN_DENSE_MINB)
-dense_kernel(Geo g, Workspace ws) {
-  if (ws.info[blockIdx.z >> 1].status != JN_OK) return;
-  if (blockIdx.z & 1) dense_body<R, SUB, 1>(g, ws);
-  else dense_body<R, SUB, -1>(g, ws);
-}
-
-#endif  // JN_DENSE_BASES
 
 }  // namespace
 
