@@ -68,6 +68,26 @@ def test_port_matches_reference_on_textured_scene(ref, port, synth, W, H, dm, se
         assert valid.mean() > 0.8 and (np.abs(a["D1"] - gt)[valid] <= 1).mean() > 0.97
 
 
+@pytest.mark.parametrize("scene,W,H,dm,seed,kw", [
+    ("random_dot", 320, 240, 64, 4, {"sradius": 4.0}),                                   # plane radius 4
+    ("random_dot", 333, 251, 100, 6, {"sigma": 2.0, "sradius": 3.5, "match_texture": 3}),  # plane radius 7
+    ("random_dot", 320, 240, 64, 4, {"sradius": 5.0, "subsampling": 1}),
+    ("textured", 640, 480, 64, 8, {"lr_threshold": 5, "incon_threshold": 8}),            # coincident right-image points
+    ("textured", 640, 480, 64, 3, {"candidate_stepsize": 2, "lr_threshold": 4, "incon_threshold": 8}),
+])
+def test_port_matches_reference_off_preset_parameters(ref, port, synth, scene, W, H, dm, seed, kw):
+    """The parameter sets of the GPU tests that leave the presets: larger plane radii (prior table, plane range)
+    and cross-check tolerances that let two support points share a right-image position, where the copy Triangle
+    keeps depends on its seeded quicksort (reproduced by oracle/delaunay_port.c)."""
+    I1, I2, _ = synth.SCENES[scene](W, H, dm, seed)
+    p = ol.robotics(dm, **kw)
+    a, b = ref.stages(p, I1, I2), port.stages(p, I1, I2)
+    assert a["rc"] == b["rc"] == 0
+    for k in STAGE_KEYS:
+        assert a[k].shape == b[k].shape, k
+        assert np.array_equal(a[k], b[k]), "%s: %d mismatches" % (k, int((a[k] != b[k]).sum()))
+
+
 def test_port_middlebury_matches_reference(ref, port, synth):
     I1, I2, _ = synth.synth_pair(320, 240, 64, 3)
     p = ol.middlebury(64)
