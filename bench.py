@@ -77,6 +77,76 @@ def workload_name(a, scene=None, cfg=None):
         scene or a.scene)
 
 
+def bench_config(a, world):
+    """The `config` object of the JSON line; both arms print the same one (the reference arm describes the
+    bounded sample it times in cpu_baseline.sample)."""
+    n = a.width * a.height
+    B = a.batch
+    if a.total_frames:
+        pairs = "%d pairs, seeds %d..%d, split contiguously over the ranks (BASELINE config C4)" % (
+            a.total_frames, SEED0, SEED0 + a.total_frames - 1)
+    else:
+        pairs = "%d distinct pairs per GPU, seeds %d + rank * %d + i" % (B, SEED0, B)
+    return {"workload": workload_name(a), "frames_per_step_per_gpu": B, "pairs": pairs,
+            "l2": "inputs per step (%.0f MB) and working set (>4 GB) exceed the 126 MB L2" % (2 * B * n / 1e6),
+            "parallelism": "frames sharded across %d GPU(s), no data-path collective" % world,
+            "total_frames": a.total_frames or None}
+
+
+# SURVEY 8(d): compulsory traffic of a stage in units of N = W*H bytes per frame (ROBOTICS, left image
+# post-processed: L/R 16 + segments 8 + gaps 16 + mean 16, 179 N with the 4 N of the scan; C5 post-processes both
+# images and adds the median) and, for the support matcher, the integer-pipe
+# ceiling (VABSDIFF4.U8.ACC issues at 16 lanes/clk/SMSP, profiles/r01_int_pipe_microbench.txt).
+STAGE_BYTES_N = {"descriptor": 34.0, "support": 12.9, "dense_match": 72.0, "post": 56.0}
+STAGE_BYTES_N_C5 = dict(STAGE_BYTES_N, post=128.0)     # L/R 16 + segments 16 + gaps 32 + mean 32 + median 32 (251 N in all)
+
+
+def support_warp_sads(W, H, dm, step=5):
+    """Warp-level VABSDIFF4 instructions the support matcher needs per frame if every lattice candidate is matched
+    in both directions (elas.cpp:269-373: 4 blocks of 16 B per candidate and disparity = 16 four-byte SADs per
+    lane, 32 disparities per warp instruction; ranges shorter than 10 are rejected).  An upper bound of the
+    compulsory work: the backward match only runs where the forward match succeeded."""
+    wc, hc = -(-W // step), -(-H // step)
+    rows = sum(1 for vc in range(1, hc) if 5 <= vc * step <= H - 6)
+    per_row = 0.0
+    for uc in range(1, wc):
+        u = uc * step
+        if u < 5 or u > W - 6:
+            continue
+        for hi in (min(dm, u - 5), min(dm, W - u - 5)):
+            if hi >= 10:
+                per_row += (hi + 1) / 32.0 * 16.0
+    return per_row * rows
+
+
+def stage_roofline(stages_ms, W, H, dm, B, peak_gbs, sm_mhz, sms=148, cfg="robotics"):
+    """max(t_HBM, t_INT) / t_measured per stage from the live stage events (ms per B-frame step), SURVEY 8(d)."""
+    n = W * H
+    table = STAGE_BYTES_N_C5 if cfg == "c5" else STAGE_BYTES_N
+    out = {}
+    for k, ms in stages_ms.items():
+        if k == "raster":
+            out[k] = {"bound": "scattered stores (the plane map is this implementation's intermediate: no compulsory "
+                               "traffic in SURVEY 8(d))", "ms": ms, "frac": None}
+            continue
+        if k not in table or not ms or ms <= 0:
+            out[k] = {"bound": "latency (one or two CTAs per frame)", "ms": ms, "frac": None}
+            continue
+        byts = table[k] * n * B
+        t_hbm = byts / (peak_gbs * 1e9) * 1e3
+        ent = {"bound": "hbm", "ms": ms, "algorithmic_bytes": byts, "t_hbm_ms": t_hbm, "frac": t_hbm / ms}
+        if k == "support":
+            # VABSDIFF4.U8.ACC: 16 lanes per clock per SM sub-partition = 0.5 warp instructions per clock, 4 per SM
+            wsads = support_warp_sads(W, H, dm) * B
+            t_int = wsads / (0.5 * 4 * sms * (sm_mhz or 1965.0) * 1e6) * 1e3
+            ent.update({"bound": "integer pipe" if t_int > t_hbm else "hbm", "warp_sads": wsads, "t_int_ms": t_int,
+                        "frac": max(t_hbm, t_int) / ms,
+                        "note": "stage = matcher + inconsistency counts + support filter; warp_sads is an upper bound "
+                                "of the compulsory work (every candidate matched in both directions)"})
+        out[k] = ent
+    return out
+
+
 def q_matrix(W, H):
     import numpy as np
     import scan_lib
@@ -205,7 +275,9 @@ def run_reference(a):
             "warmup": a.warmup, "ms_per_step": 1000.0 * cb["cores"] / v, "higher_is_better": True,
             "scaling": "strong" if a.total_frames else "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": workload_name(a), "step": "one frame per host core (%d cores)" % cb["cores"]},
+            "config": bench_config(a, int(os.environ.get("WORLD_SIZE", "1"))),
+            "step_what": "bounded sample of the workload above: one frame per host core (%d cores) per step, "
+                         "frames = seeds %d + core" % (cb["cores"], SEED0),
             "cpu_baseline": cb,
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -588,11 +660,8 @@ def run_ours(a):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": max(a.warmup, 3),
         "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "strong" if a.total_frames else "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": workload_name(a), "frames_per_step_per_gpu": B,
-                   "pairs": "%d distinct pairs per GPU, seeds %d+ (generated in %.0f s)" % (len(seeds), SEED0, t_gen),
-                   "l2": "inputs per step (%.0f MB) and working set (>4 GB) exceed the 126 MB L2" % (2 * B * n / 1e6),
-                   "parallelism": "frames sharded across %d GPU(s), no data-path collective" % world,
-                   "total_frames": a.total_frames or None},
+        "config": bench_config(a, world),
+        "input_generation_s": t_gen,
         "mpix_per_s": value * n / 1e6, "ms_per_frame": ms / steps / B,
         "value_what": "device-resident image pairs through jn_stereo_scan_submit_device / _wait (ELAS + scan kernels on "
                       "the library's rolling sub-batch streams, two submissions in flight, outputs stay on the device)",
@@ -613,6 +682,8 @@ def run_ours(a):
                 "rank_pinning": pin},
         "gpu_launches": int(launches),
         "stage_ms_per_step": {k: float(v) for k, v in zip(STAGES, stages)},
+        "stage_roofline": stage_roofline({k: float(v) for k, v in zip(STAGES, stages)}, W, H, dm, B, peak,
+                                         (clocks or {}).get("sm_mhz"), cfg=a.config),
         "roofline": {"bound": "hbm", "kernel": "dense_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "traffic_source": tsrc,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",

@@ -238,3 +238,57 @@ def test_vertexsort_replay_reports_a_full_stack(tmp_path):
     order = np.empty(2000, np.int32)
     assert lib.vs_sorted_order(x.ctypes.data, y.ctypes.data, 2000, order.ctypes.data, 2) == -1
     assert lib.vs_sorted_order(x.ctypes.data, y.ctypes.data, 2000, order.ctypes.data, 64) == 0
+
+
+def _bench_module():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("jn_bench", os.path.join(ROOT, "bench.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def test_bench_config_is_shared_by_both_arms_and_run_independent():
+    """The driver compares the `config` object of the two arms: it must not contain anything arm- or run-specific."""
+    import argparse
+    b = _bench_module()
+    a = argparse.Namespace(width=1920, height=1200, disp_max=255, batch=64, scene="random_dot", config="robotics",
+                           total_frames=0)
+    c1, c2 = b.bench_config(a, 1), b.bench_config(a, 1)
+    assert c1 == c2 and c1["workload"].startswith("1920x1200 disp_max=255 ROBOTICS")
+    assert set(c1) == {"workload", "frames_per_step_per_gpu", "pairs", "l2", "parallelism", "total_frames"}
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    assert src.count('"config": bench_config(') == 2          # GPU arm and reference arm
+    a.total_frames = 1024
+    assert "1000..2023" in b.bench_config(a, 8)["pairs"]     # BASELINE config C4
+
+
+def test_bench_stage_roofline_figures():
+    """179 N bytes per frame end to end (ROBOTICS), 251 N for C5; the support matcher's SAD count
+    against a brute-force enumeration of elas.cpp:269-373's loops."""
+    b = _bench_module()
+    assert abs(sum(b.STAGE_BYTES_N.values()) + 4 - 179) < 0.2
+    assert abs(sum(b.STAGE_BYTES_N_C5.values()) + 4 - 251) < 0.2
+    W, H, dm = 640, 480, 64
+    n = 0
+    for vc in range(1, -(-H // 5)):
+        v = vc * 5
+        if v < 5 or v > H - 6:
+            continue
+        for uc in range(1, -(-W // 5)):
+            u = uc * 5
+            if u < 5 or u > W - 6:
+                continue
+            for right in (0, 1):
+                d_hi = min(dm, (W - u - 5) if right else (u - 5))
+                if d_hi - 0 < 10:                        # elas.cpp:320-331: ranges shorter than 10 are rejected
+                    continue
+                n += (d_hi + 1) * 16                     # 4 blocks of 16 bytes = 16 four-byte SADs per disparity
+    assert abs(b.support_warp_sads(W, H, dm) - n / 32.0) < 1e-6 * n
+    st = {"descriptor": 1.3, "support": 4.8, "delaunay": 0.7, "planes_grid": 0.4, "raster": 1.2, "dense_match": 2.515,
+          "post": 3.0}
+    r = b.stage_roofline(st, 1920, 1200, 255, 64, 6447.8, 1965.0)
+    assert abs(r["dense_match"]["frac"] - 72 * 1920 * 1200 * 64 / 6447.8e9 / 2.515e-3) < 1e-9
+    assert r["support"]["bound"] == "integer pipe" and 0.3 < r["support"]["frac"] < 1.0
+    assert r["delaunay"]["frac"] is None and r["raster"]["frac"] is None
+    assert b.stage_roofline(st, 1920, 1200, 255, 64, 6447.8, None)["support"]["frac"] == r["support"]["frac"]
