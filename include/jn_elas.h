@@ -75,9 +75,33 @@ enum {
   JN_FEW_SUPPORT   = 1,
   JN_ERR_ARG       = -1,
   JN_ERR_CUDA      = -2,
-  JN_ERR_UNSUPPORTED = -3,  /* outside what the kernels cover (plane radius > 7, image >= 8192 px, ...) */
+  JN_ERR_UNSUPPORTED = -3,  /* outside what the kernels cover, see "Supported envelope" below */
   JN_ERR_IO        = -4
 };
+
+/* Supported envelope.  The reference has none of these limits (it allocates per call and Triangle grows its
+ * pools); inside the envelope the results are the reference's bit for bit, outside it a call fails loudly and
+ * writes no output -- it never returns a different answer.
+ *
+ *   JN_ERR_ARG (rejected before any work is queued)
+ *     width, height >= 16, bytes_per_line >= width
+ *     10 <= disp_max <= 4095, disp_min <= disp_max, candidate_stepsize >= 1, 1 <= grid_size < 32768,
+ *     0 <= incon_window_size <= 16, 0 <= incon_threshold <= 8191
+ *   JN_ERR_UNSUPPORTED at the first process call of a size
+ *     width, height < 8192              exact Delaunay predicates are evaluated in 64-bit integers
+ *     ceil(sigma * sradius) <= 7        plane radius; the presets have 2 (ROBOTICS) and 3 (MIDDLEBURY)
+ *     prior table entries (elas.cpp:802-806) within [-2000, 1900]   packed (energy, disparity) keys
+ *     subsampling == 0 for the jn_stereo_scan_* entry points          the scan takes full-resolution maps
+ *   JN_ERR_UNSUPPORTED per frame (status[i]; the frame's outputs are left untouched, the other frames of the
+ *   batch are unaffected)
+ *     add_corners together with more than 16 384 support points in one frame (the corner points are off the
+ *       candidate lattice the large-set ordering is built on); without add_corners there is no limit below
+ *       the lattice size.  The presets at 1920x1200 give 6-10 k support points.
+ *     more triangles than the index field of a plane-map entry holds: 2^(31 - b) with b = bits of
+ *       disp_max + 2 r + 3 (r = plane radius), i.e. millions at disp_max 255 against at most 2 * lattice size
+ *       = 184 336 triangles at 1920x1200 -- reachable only above ~50 Mpixel at the presets' lattice step
+ *     a point set with coincident points whose replay of Triangle's quicksort needs more than 4 096 pending
+ *       partitions (seen on no input; a guard, not a known case) */
 
 typedef struct jn_elas jn_elas;
 
