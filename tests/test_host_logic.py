@@ -292,3 +292,16 @@ def test_bench_stage_roofline_figures():
     assert r["support"]["bound"] == "integer pipe" and 0.3 < r["support"]["frac"] < 1.0
     assert r["delaunay"]["frac"] is None and r["raster"]["frac"] is None
     assert b.stage_roofline(st, 1920, 1200, 255, 64, 6447.8, None)["support"]["frac"] == r["support"]["frac"]
+
+
+def test_documents_name_only_declared_entry_points():
+    """INTEGRATION.md / DESIGN.md / README.md show a maintainer what to bind: every jn_* name they mention is
+    declared in include/*.h (a prefix such as jn_navigate_ or jn_scan_ stands for a family of declared names)."""
+    decl = set()
+    for h in os.listdir(os.path.join(ROOT, "include")):
+        decl |= set(re.findall(r"\b(jn_[a-z0-9_]+)\b", open(os.path.join(ROOT, "include", h)).read()))
+    for doc in ("INTEGRATION.md", "DESIGN.md", "README.md"):
+        names = set(re.findall(r"\b(jn_[a-z0-9_]+)\b", open(os.path.join(ROOT, doc)).read()))
+        assert names, doc
+        missing = sorted(n for n in names if n not in decl and not any(d.startswith(n) for d in decl))
+        assert not missing, "%s mentions undeclared %s" % (doc, missing)
