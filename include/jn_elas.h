@@ -271,7 +271,7 @@ int jn_pointcloud_batch(jn_scan* s, int n, const float* D, const uint8_t* image,
                         jn_scan_meta* meta, void* stream);
 
 /* Compacted LaserScan.ranges as the reference publishes them: finite bins,
- * k = 89..0 (point_cloud.cpp:278-282).  Returns the count. */
+ * k = 89..0 (point_cloud.cpp:278-282).  Returns the count (JN_ERR_ARG for a NULL pointer). */
 int jn_scan_compact(const double ranges[JN_SCAN_BINS], float* out);
 
 /* ---- rectification ahead of the stereo path ------------

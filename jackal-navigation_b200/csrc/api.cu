@@ -101,6 +101,7 @@ extern "C" long long jn_launch_count(void) { return g_jn_launches.load(); }
 
 extern "C" void jn_elas_params_default(jn_elas_params* p, int setting) {
   // Elas::parameters(setting), elas.h:87-144
+  if (!p) return;
   p->disp_min = 0;
   p->disp_max = 255;
   p->support_texture = 10;
@@ -1057,6 +1058,7 @@ extern "C" int jn_calib_load_yaml(const char* path, jn_calib* c) {
 }
 
 extern "C" void jn_calib_set_q(jn_calib* c, double cx, double cy, double f, double tx) {
+  if (!c) return;
   memset(c->Q, 0, sizeof(c->Q));
   c->Q[0] = 1;  c->Q[3] = -cx;
   c->Q[5] = 1;  c->Q[7] = -cy;

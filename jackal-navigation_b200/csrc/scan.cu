@@ -848,6 +848,7 @@ extern "C" int jn_pointcloud_batch(jn_scan* s, int n, const float* D, const uint
 }
 
 extern "C" int jn_scan_compact(const double ranges[JN_SCAN_BINS], float* out) {
+  if (!ranges || !out) return JN_ERR_ARG;
   int n = 0;
   for (int i = JN_SCAN_BINS - 1; i >= 0; i--)
     if (ranges[i] < SCAN_INF - 1) out[n++] = (float)ranges[i];
