@@ -310,7 +310,11 @@ int jn_jpeg_decode_gray_batch(jn_jpeg* j, int n, const uint8_t* const* data, con
  * laserScanCallback / checkObstacle / chooseDirection of the `navigate` node
  * (src/obstacle_avoidance/navigate.cpp:344-363, 101-153, 155-197): host code, O(90) per frame.
  *   jn_navigate_set_scan        LaserScan.ranges (compacted float32, as jn_scan_compact emits) + angle_min/max
- *   jn_navigate_set_scan_bins   the 90-bin output of jn_scan_from_disparity directly
+ *   jn_navigate_set_scan_bins   the 90-bin output of jn_scan_from_disparity directly (angle_min/max rounded to
+ *                               float32, as the LaserScan message between the two nodes carries them)
+ *   jn_navigate_points          the laser points (x, y pairs) the node holds and publishes as Marker points
+ *                               (visualizeLaserPoints, navigate.cpp:77-98); returns their number, copies at most
+ *                               `capacity` of them
  *   jn_navigate_check_obstacle  returns isObstacle after the spatial filter, the 50 cm rule and the 20-frame
  *                               vote; report[4] = {points in the safe box, laser points, closest, confidence}
  *   jn_navigate_choose_direction  0 keep / 1 left / 2 right, with the reference's hysteresis on last_dir
@@ -324,6 +328,7 @@ void jn_navigate_set_last_dir(jn_navigate* n, int dir);
 int  jn_navigate_last_dir(const jn_navigate* n);
 int  jn_navigate_set_scan(jn_navigate* n, const float* ranges, int count, double angle_min, double angle_max);
 int  jn_navigate_set_scan_bins(jn_navigate* n, const double ranges[JN_SCAN_BINS], const jn_scan_meta* meta);
+int  jn_navigate_points(const jn_navigate* n, double* xy, int capacity);
 int  jn_navigate_check_obstacle(jn_navigate* n, double report[4]);
 int  jn_navigate_choose_direction(const jn_navigate* n);
 

@@ -53,12 +53,22 @@ extern "C" int jn_navigate_set_scan(jn_navigate* n, const float* ranges, int cou
 }
 
 // The 90-bin scan of jn_scan_from_disparity straight into the vote: compaction as the reference
-// publishes it (point_cloud.cpp:278-282), then laserScanCallback.
+// publishes it (point_cloud.cpp:278-282), then laserScanCallback.  Between the two nodes the scan travels as a
+// sensor_msgs/LaserScan, whose angle_min / angle_max are float32 (point_cloud.cpp:271-272 assign doubles to them):
+// the angles are rounded the same way here, so the laser points are the ones the navigate node computes.
 extern "C" int jn_navigate_set_scan_bins(jn_navigate* n, const double ranges[JN_SCAN_BINS], const jn_scan_meta* meta) {
   if (!n || !ranges || !meta) return JN_ERR_ARG;
   float tmp[JN_SCAN_BINS];
   const int count = jn_scan_compact(ranges, tmp);
-  return jn_navigate_set_scan(n, tmp, count, meta->angle_min, meta->angle_max);
+  return jn_navigate_set_scan(n, tmp, count, (double)(float)meta->angle_min, (double)(float)meta->angle_max);
+}
+
+// laserPoints (navigate.cpp:22, filled at :356-361): what visualizeLaserPoints (:77-98) publishes as Marker points.
+extern "C" int jn_navigate_points(const jn_navigate* n, double* xy, int capacity) {
+  if (!n || capacity < 0 || (capacity > 0 && !xy)) return JN_ERR_ARG;
+  const int count = (int)n->px.size();
+  for (int i = 0; i < count && i < capacity; i++) { xy[2 * i] = n->px[i]; xy[2 * i + 1] = n->py[i]; }
+  return count;
 }
 
 // checkObstacle (navigate.cpp:101-153).  Returns isObstacle (0/1); report = {count in the safe box,

@@ -1,6 +1,9 @@
 """TEST INFRASTRUCTURE ONLY -- plain-Python restatement of the `navigate` node's scan consumer
-(src/obstacle_avoidance/navigate.cpp), used by tests/ to check jn_navigate_*.  Parity unpinned against the
-reference itself (ROS node, cannot be built here, no fixtures): the statements are transcribed one by one.
+(src/obstacle_avoidance/navigate.cpp), used by tests/ to check jn_navigate_*.  PINNED against the reference's own
+code: navigate.cpp compiled where it lies with stand-in ROS headers (oracle/standins, oracle/navigate_ref_shim.cpp ->
+oracle/_ref/libnavigate_ref.so); tests/test_reference_nodes_pin.py runs 1 500 scans through the node's
+laserScanCallback / checkObstacle / chooseDirection and through this class: equal laser points (bit for bit), votes,
+printed reports and directions.
 
   laser_scan_callback   navigate.cpp:344-363
   check_obstacle        navigate.cpp:101-153

@@ -2,17 +2,21 @@
  * scan_port.c -- TEST INFRASTRUCTURE ONLY.
  *
  * Plain-C restatement of the per-pixel part of the reference's
- * src/obstacle_avoidance/point_cloud.cpp (it needs ROS + OpenCV C++ and cannot
- * be compiled here).  PARITY UNPINNED against the
- * reference itself: it holds no test, fixture or golden output for this code, and
- * the OpenCV it links (2.4-era, version not pinned in package.xml) is not in
- * /root/reference.  The arithmetic below follows the call sites literally, with
- * cv::Mat products evaluated as OpenCV's small-matrix gemm does:
- * ((a0*b0 + a1*b1) + a2*b2) [+ a3*b3], then + C.  PINNED against OpenCV 4.13 for
- * the parts that live in OpenCV: tests/golden/scan_cv2.npz holds cv2.gemm results
- * for Q*V and XR*p+XT (sparse and dense Q) and the saturate_cast<uchar> of
- * convertTo(CV_8U); tests/test_oracle_pin.py checks reproject() and
- * port_convert_u8 against them bit for bit.  atan2/sqrt/floor are libm.
+ * src/obstacle_avoidance/point_cloud.cpp.  PINNED three ways:
+ *  (1) against the reference's own code: point_cloud.cpp compiled where it lies with stand-in ROS / OpenCV
+ *      headers (oracle/standins, oracle/pointcloud_ref_shim.cpp -> oracle/_ref/libpointcloud_ref.so);
+ *      tests/test_reference_nodes_pin.py calls the node's cacheDisparityValues, generateDisparityMap,
+ *      publishPointCloud and both publishObstacleScan overloads and compares the gate cache, the CV_8U map,
+ *      the Point32 / rgb payload and the published LaserScan with the functions below, bit for bit.  That
+ *      pins the statements (loop order, constants, casts, conditions); the stand-in cv::Mat supplies the
+ *      arithmetic of OpenCV's calls, so
+ *  (2) the OpenCV arithmetic is pinned against OpenCV 4.13 itself: cv::Mat products are evaluated as OpenCV's
+ *      small-matrix gemm does, ((a0*b0 + a1*b1) + a2*b2) [+ a3*b3], then + C; tests/golden/scan_cv2.npz holds
+ *      cv2.gemm results for Q*V and XR*p+XT (sparse and dense Q) and the saturate_cast<uchar> of
+ *      convertTo(CV_8U); tests/test_oracle_pin.py checks reproject() and port_convert_u8 against them bit
+ *      for bit (the reference's OpenCV is 2.4-era and not pinned in package.xml: not available here);
+ *  (3) against tests/golden/scan_statements.npz, a statement-by-statement execution of the same functions
+ *      with cv2 (generator committed).  atan2/sqrt/floor are libm.
  *
  * One behaviour is DEFINED here because the reference leaves it undefined (H8):
  * a bin index outside [0,89] (|theta| > 45 deg) is skipped; the reference writes

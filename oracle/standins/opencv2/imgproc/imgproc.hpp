@@ -1,0 +1,2 @@
+/* TEST INFRASTRUCTURE ONLY: stand-in for <opencv2/imgproc/imgproc.hpp>, see oracle/standins/standins.h (found through -Istandins) */
+#include "standins.h"
