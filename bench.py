@@ -255,7 +255,9 @@ def cpu_arm(a, frames_per_core, cores=None, scene=None, cfg=None):
             "kind": "reference" if kind == "ref" else "port",
             "sample": "%d frames (%d per core, one process per core), max worker time %.2fs, pool wall %.2fs; "
                       "single frame on one core, others idle: %.3fs (%.3f frames/s; median of 5 after a warm-up); "
-                      "ELAS built -O3 -msse3, scan with the real gate cache" % (nfr, frames_per_core, busy, wall, t1 / n1, n1 / t1),
+                      "ELAS = the reference's sources built -O3 -msse3; scan step (~8%% of a frame) = the plain-C "
+                      "restatement with the real gate cache: the stock node indexes its 90 bins unchecked and cannot run "
+                      "on this calibration (DESIGN.md section 4)" % (nfr, frames_per_core, busy, wall, t1 / n1, n1 / t1),
             "single_core_frames_per_s": n1 / t1}, frames
 
 
