@@ -257,3 +257,47 @@ def test_scan_message_into_the_vote(jn, sp, synth):
         assert float(np.float32(pm.angle_min)) != float(pm.angle_min)    # the rounding is not a no-op on these scans
         assert l.jn_navigate_choose_direction(nav) == node.choose_direction()
     l.jn_navigate_destroy(nav)
+
+
+def test_random_calibrations_and_crops(sp):
+    """Forty random calibrations (focal length, principal point, baseline, a rotated and shifted camera-to-robot
+    transform, a Q with every entry non-zero in a third of them) on random crops: gate cache, default scan and -g
+    payload of the compiled node against the restatement.  Cases the stock node cannot take (a bin outside [1, 88]
+    or a NaN angle) are counted and skipped; at least half must remain."""
+    rng = np.random.default_rng(2026)
+    W, H = 96, 64
+    ran = 0
+    for case in range(40):
+        f = rng.uniform(300, 2500)
+        cx, cy = rng.uniform(0.3, 0.7) * 4 * W, rng.uniform(0.3, 0.7) * 4 * H
+        tx = -rng.uniform(0.05, 0.3)
+        Q = np.array([[1, 0, 0, -cx], [0, 1, 0, -cy], [0, 0, 0, f], [0, 0, -1 / tx, 0]], np.float64)
+        if case % 3 == 0:
+            Q = Q + rng.uniform(-1e-3, 1e-3, (4, 4))                  # dense Q: every product term contributes
+        a, b, c = rng.uniform(-0.08, 0.08, 3)
+        Rx = np.array([[1, 0, 0], [0, np.cos(a), -np.sin(a)], [0, np.sin(a), np.cos(a)]])
+        Ry = np.array([[np.cos(b), 0, np.sin(b)], [0, 1, 0], [-np.sin(b), 0, np.cos(b)]])
+        Rz = np.array([[np.cos(c), -np.sin(c), 0], [np.sin(c), np.cos(c), 0], [0, 0, 1]])
+        xr = Rz @ Ry @ Rx @ XR
+        xt = XT.reshape(3) + rng.uniform(-0.1, 0.1, 3)
+        ox, oy = int(rng.integers(0, 3 * W)), int(rng.integers(0, 3 * H))
+        node = rn.PointCloudNode(Q, xr, xt, W, H, ox, oy)
+        gate = node.cache_gate()
+        assert np.array_equal(gate, sp.gate(Q, xr, xt, W, H, ox, oy)), case
+        u8 = rng.integers(1, 256, (H, W)).astype(np.uint8)
+        u8[rng.random((H, W)) < 0.3] = 0
+        u8[(gate[..., 0] == 0) & (u8 == 0)] = 1                        # H8: no zero on a wrapped gate entry
+        if not (rn.safe_for_reference(Q, xr, xt, u8, gate=gate, ox=ox, oy=oy)
+                and rn.safe_for_reference(Q, xr, xt, u8, min_d=2, ox=ox, oy=oy)):
+            continue
+        ran += 1
+        ranges, meta = node.scan(u8)
+        pr, pm = sp.scan(Q, xr, xt, gate, u8, ox, oy)
+        assert np.array_equal(ranges, sp.compact(pr)) and np.array_equal(meta, meta_f32(pm)), case
+        img = rng.integers(0, 256, (H, W, 3)).astype(np.uint8)
+        xyz, rgb, ranges2, meta2 = node.pointcloud(u8, img)
+        pxyz, prgb = sp.pointcloud(Q, xr, xt, u8, img, ox, oy)
+        assert np.array_equal(xyz, pxyz) and np.array_equal(rgb.view(np.int32), prgb.view(np.int32)), case
+        pr2, pm2 = sp.scan_points(sp.points(Q, xr, xt, u8, ox, oy))
+        assert np.array_equal(ranges2, sp.compact(pr2)) and np.array_equal(meta2, meta_f32(pm2)), case
+    assert ran >= 20, ran
