@@ -500,6 +500,83 @@ def scan_compact(ranges):
     return out[:n]
 
 
+class Navigate:
+    """The scan's consumer without ROS: the `navigate` node's laserScanCallback / checkObstacle / chooseDirection
+    (navigate.cpp:344-363, 101-153, 155-197).  Host code, no device needed."""
+
+    def __init__(self):
+        l = lib()
+        l.jn_navigate_create.restype = _P
+        l.jn_navigate_destroy.argtypes = [_P]
+        l.jn_navigate_set_clearance.argtypes = [_P, C.c_double, C.c_double, C.c_int]
+        l.jn_navigate_set_last_dir.argtypes = [_P, C.c_int]
+        l.jn_navigate_last_dir.argtypes = [_P]
+        l.jn_navigate_set_scan.argtypes = [_P, _P, C.c_int, C.c_double, C.c_double]
+        l.jn_navigate_set_scan_bins.argtypes = [_P, _P, C.POINTER(ScanMeta)]
+        l.jn_navigate_points.argtypes = [_P, _P, C.c_int]
+        l.jn_navigate_check_obstacle.argtypes = [_P, _P]
+        l.jn_navigate_choose_direction.argtypes = [_P]
+        self._h = l.jn_navigate_create()
+        if not self._h:
+            raise JnError("jn_navigate_create failed")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().jn_navigate_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_clearance(self, clear_front, clear_side, laser_pt_thresh):
+        """clear_front / clear_side / laser_pt_thresh (navigate.cpp:37-42; -c and -l of the node)."""
+        lib().jn_navigate_set_clearance(self._h, clear_front, clear_side, int(laser_pt_thresh))
+
+    def set_scan(self, ranges, angle_min, angle_max):
+        """A LaserScan as point_cloud publishes it: compacted float32 ranges + angle_min / angle_max."""
+        r = np.ascontiguousarray(ranges, np.float32)
+        return _check(lib().jn_navigate_set_scan(self._h, _ptr(r), len(r), float(angle_min), float(angle_max)),
+                      "jn_navigate_set_scan")
+
+    def set_scan_bins(self, ranges, meta):
+        """The 90-bin scan + ScanMeta of ObstacleScan.from_disparity directly."""
+        r = np.ascontiguousarray(ranges, np.float64)
+        if r.size != SCAN_BINS:
+            raise ValueError("ranges must hold %d bins" % SCAN_BINS)
+        return _check(lib().jn_navigate_set_scan_bins(self._h, _ptr(r), C.byref(meta)), "jn_navigate_set_scan_bins")
+
+    def points(self):
+        """laserPoints: n x 2 doubles (what visualizeLaserPoints publishes, navigate.cpp:77-98)."""
+        n = lib().jn_navigate_points(self._h, None, 0)
+        xy = np.zeros((max(n, 0), 2), np.float64)
+        if n > 0:
+            lib().jn_navigate_points(self._h, _ptr(xy), n)
+        return xy
+
+    def check_obstacle(self):
+        """-> (isObstacle, (points in the safe box, laser points, closest distance, confidence of the vote))"""
+        rep = (C.c_double * 4)()
+        r = lib().jn_navigate_check_obstacle(self._h, rep)
+        if r < 0:
+            _check(r, "jn_navigate_check_obstacle")
+        return r, (int(rep[0]), int(rep[1]), rep[2], rep[3])
+
+    def choose_direction(self):
+        """0 keep / 1 left / 2 right, with the reference's hysteresis on last_dir."""
+        return lib().jn_navigate_choose_direction(self._h)
+
+    @property
+    def last_dir(self):
+        return lib().jn_navigate_last_dir(self._h)
+
+    @last_dir.setter
+    def last_dir(self, d):
+        lib().jn_navigate_set_last_dir(self._h, int(d))
+
+
 class Rectifier:
     """cv::remap(frame, out, mapx, mapy, INTER_LINEAR) + ROI crop of one camera (point_cloud.cpp:440-442),
     with the CV_32FC1 map pair of cv::initUndistortRectifyMap (point_cloud.cpp:553-554)."""

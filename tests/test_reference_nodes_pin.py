@@ -301,3 +301,35 @@ def test_random_calibrations_and_crops(sp):
         pr2, pm2 = sp.scan_points(sp.points(Q, xr, xt, u8, ox, oy))
         assert np.array_equal(ranges2, sp.compact(pr2)) and np.array_equal(meta2, meta_f32(pm2)), case
     assert ran >= 20, ran
+
+
+def test_python_navigate_mirror_against_the_compiled_node(jn, sp, synth):
+    """jn.Navigate (the Python mirror of the navigate node's scan consumer) fed with the 90-bin scan and with the
+    published LaserScan, against the compiled node fed by the compiled point_cloud node."""
+    W, H, dm = 320, 180, 64
+    Q = np.array(FX["Q"]["320x180"], np.float64)
+    pc = rn.PointCloudNode(Q, XR, XT, W, H)
+    gate = pc.cache_gate()
+    node = rn.NavigateNode()
+    a, b = jn.Navigate(), jn.Navigate()
+    for seed in range(3):
+        I1, I2, _ = synth.synth_pair(W, H, dm, 40 + seed)
+        u8 = pc.generate_disparity(I1, I2)
+        assert rn.safe_for_reference(Q, XR, XT, u8, gate=gate)
+        ranges, meta = pc.scan(u8)
+        node.laser_scan(ranges, meta[0], meta[1])
+        pr, pm = sp.scan(Q, XR, XT, gate, u8)
+        a.set_scan_bins(pr, jn.ScanMeta(pm.angle_min, pm.angle_max, pm.range_min, pm.range_max, pm.n_finite, pm.n_points))
+        b.set_scan(ranges, meta[0], meta[1])
+        assert np.array_equal(a.points(), node.points()) and np.array_equal(b.points(), node.points())
+        exp, fields = node.check_obstacle()
+        for nav in (a, b):
+            got, rep = nav.check_obstacle()
+            assert got == exp and _same_report(fields, rep, exp)
+            assert nav.choose_direction() == node.choose_direction()
+        d = node.choose_direction()
+        node.set_last_dir(d); a.last_dir = d; b.last_dir = d
+        assert a.last_dir == node.last_dir()
+    with pytest.raises(ValueError):
+        a.set_scan_bins(np.zeros(10), jn.ScanMeta())
+    a.close(); b.close()
