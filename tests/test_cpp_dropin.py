@@ -50,3 +50,47 @@ def test_cpp_caller_matches_oracle(jn, oracle, synth, tmp_path):
     D2 = np.fromfile(tmp_path / "or.f32", np.float32).reshape(H, W)
     R1, R2 = oracle.process(ol.robotics(dm), I1, I2)
     assert np.array_equal(D1, R1) and np.array_equal(D2, R2)
+
+
+REF_NODE = "/root/reference/src/obstacle_avoidance/point_cloud.cpp"
+
+
+@pytest.mark.skipif(not os.path.exists(REF_NODE), reason="needs the reference tree")
+def test_reference_node_source_compiles_against_the_dropin_header(jn, synth, tmp_path):
+    """INTEGRATION.md section 1, literally: the reference's point_cloud.cpp, unmodified and where it lies, compiled
+    with include/elas.h ahead of the reference's own elas.h (ROS / OpenCV from oracle/standins) and linked against
+    libjn_elas.so instead of the reference's ELAS objects.  generateDisparityMap's `Elas elas(param);
+    elas.process(...)` (:416-419) then runs this repository's library; without a GPU it must fail loudly."""
+    import sys
+    import torch
+    so = str(tmp_path / "libpointcloud_dropin.so")
+    libdir = os.path.join(ROOT, "jackal-navigation_b200")
+    cmd = ["g++", "-O1", "-fPIC", "-w", "-std=gnu++11", "-shared",
+           "-I", os.path.join(ROOT, "oracle", "standins"), "-I", os.path.dirname(REF_NODE),
+           "-I", os.path.join(ROOT, "include"),                      # our elas.h wins over the reference's
+           "-I", "/root/reference/src/elas",                         # image.h
+           os.path.join(ROOT, "oracle", "pointcloud_ref_shim.cpp"), "-o", so,
+           "-L", libdir, "-ljn_elas", "-Wl,-rpath," + libdir, "-Wl,--no-undefined"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    syms = subprocess.run(["nm", "-D", so], capture_output=True, text=True).stdout
+    assert " U jn_elas_process" in syms and " U jn_elas_create" in syms      # the node calls the product library
+    assert "computeSupportMatches" not in syms                               # and carries no ELAS of its own
+    if torch.cuda.is_available():
+        return
+    I1, I2, _ = synth.synth_pair(160, 120, 32, 1)
+    I1.tofile(tmp_path / "l.u8"); I2.tofile(tmp_path / "r.u8")
+    child = ("import ctypes as C, numpy as np\n"
+             "l = C.CDLL(%r)\n"
+             "P = C.c_void_p\n"
+             "l.ref_pc_setup.argtypes = [P, P, P, C.c_int, C.c_int, C.c_int, C.c_int]\n"
+             "l.ref_pc_generate_disparity.argtypes = [P, P, P]\n"
+             "Q = np.eye(4); XR = np.eye(3); XT = np.zeros(3)\n"
+             "p = lambda a: a.ctypes.data_as(P)\n"
+             "l.ref_pc_setup(p(Q), p(XR), p(XT), 160, 120, 0, 0)\n"
+             "I1 = np.fromfile(%r, np.uint8); I2 = np.fromfile(%r, np.uint8); out = np.zeros(160 * 120, np.uint8)\n"
+             "l.ref_pc_generate_disparity(p(I1), p(I2), p(out))\n"
+             "print('returned')\n" % (so, str(tmp_path / "l.u8"), str(tmp_path / "r.u8")))
+    r = subprocess.run([sys.executable, "-c", child], capture_output=True, text=True)
+    assert r.returncode != 0 and "returned" not in r.stdout
+    assert "Elas" in r.stderr and "no CPU path" in r.stderr, r.stderr[-500:]
