@@ -94,3 +94,26 @@ def test_reference_node_source_compiles_against_the_dropin_header(jn, synth, tmp
     r = subprocess.run([sys.executable, "-c", child], capture_output=True, text=True)
     assert r.returncode != 0 and "returned" not in r.stdout
     assert "Elas" in r.stderr and "no CPU path" in r.stderr, r.stderr[-500:]
+
+
+def test_c_abi_is_plain_c99_and_the_example_builds(jn, tmp_path):
+    """include/jn_elas.h + jn_elas_debug.h are what an FFI binds: they must be valid strict C99 on their own, and
+    examples/camera_to_command.c (calibration -> ELAS -> scan -> vote through host-pointer entry points only) must
+    build against them with every warning an error.  Without a GPU the program stops after the calibration step
+    with exit code 3 and the library's "no CPU path" message."""
+    import torch
+    hdr = tmp_path / "hdr.c"
+    hdr.write_text('#include "jn_elas.h"\n#include "jn_elas_debug.h"\nint main(void) { return 0; }\n')
+    strict = ["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include")]
+    r = subprocess.run(strict + ["-c", str(hdr), "-o", str(tmp_path / "hdr.o")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    exe = str(tmp_path / "camera_to_command")
+    libdir = os.path.join(ROOT, "jackal-navigation_b200")
+    r = subprocess.run(strict + ["-O1", os.path.join(ROOT, "examples", "camera_to_command.c"), "-o", exe, "-L", libdir,
+                                 "-ljn_elas", "-Wl,-rpath," + libdir, "-lm"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    if torch.cuda.is_available():
+        return
+    r = subprocess.run([exe, os.path.join(ROOT, "tests", "golden", "calib_c920.yml"), "2"], capture_output=True, text=True)
+    assert r.returncode == 3 and "no CPU path" in r.stderr
+    assert r.stdout.startswith("Q: cx ")                       # the OpenCV-free stereoRectify ran on the host
