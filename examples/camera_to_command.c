@@ -14,6 +14,15 @@
  * Frames are synthetic (a textured floor and a box that comes closer; rectified by construction, so the remap
  * step of jn_rectify_* is not needed here).  Only host-pointer, synchronous entry points are used: what a caller
  * without the CUDA runtime links.  Exit code 3: no usable GPU (the library has no CPU path).
+ *
+ * Expected output with the shipped calibration: what the CPU checkers give for the same frames (tools/example_expected.py:
+ * the compiled reference ELAS, the scan restatement, the same vote) -- the box is left of the centre and approaches:
+ *   frame 0: 61 scan bins, closest 1.61 m, 0 points in the safe box -> free
+ *   frame 1: 61 scan bins, closest 0.84 m, 19 points in the safe box -> obstacle, turn right
+ *   frame 2: 61 scan bins, closest 0.56 m, 27 points in the safe box -> obstacle, turn right
+ *   frame 3: 61 scan bins, closest 0.42 m, 25 points in the safe box -> obstacle, turn right
+ *   frame 4: 61 scan bins, closest 0.34 m, 22 points in the safe box -> obstacle, turn right
+ *   frame 5: 61 scan bins, closest 0.28 m, 20 points in the safe box -> obstacle, turn right
  */
 #include <math.h>
 #include <stdio.h>
@@ -35,7 +44,7 @@ static void make_pair(uint8_t* L, uint8_t* R, int box_d, unsigned seed) {
   for (pass = 0; pass < 2; pass++)            /* far surface first, the box over it */
     for (v = 0; v < H; v++)
       for (u = 0; u < W; u++) {
-        const int in_box = u > W / 3 && u < 2 * W / 3 && v > H / 4 && v < 3 * H / 4;
+        const int in_box = u > W / 8 && u < W / 2 && v > H / 4 && v < 3 * H / 4;   /* left of the centre */
         const int d = in_box ? box_d : 6 + 40 * v / H;
         if (in_box != pass) continue;
         if (u - d >= 0) R[v * W + u - d] = L[v * W + u];
