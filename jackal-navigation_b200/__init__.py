@@ -150,6 +150,13 @@ def _ptr(a):
     return a.ctypes.data_as(_P) if a is not None else None
 
 
+def _need(a, count, what):
+    """The C side reads `count` elements through a raw pointer: an undersized array is a host out-of-bounds read."""
+    if a.size < count:
+        raise ValueError("%s must hold at least %d elements, got %d" % (what, count, a.size))
+    return a
+
+
 class Elas:
     """Mirror of class Elas (elas.h:52-234)."""
     ROBOTICS, MIDDLEBURY = ROBOTICS, MIDDLEBURY
@@ -441,7 +448,7 @@ class ObstacleScan:
         return out
 
     def from_disparity(self, D, want_u8=False):
-        D = np.ascontiguousarray(D, np.float32)
+        D = _need(np.ascontiguousarray(D, np.float32), self.W * self.H, "disparity map")
         ranges = np.zeros(SCAN_BINS, np.float64)
         meta = ScanMeta()
         u8 = np.zeros((self.H, self.W), np.uint8) if want_u8 else None
@@ -457,7 +464,7 @@ class ObstacleScan:
                       "jn_scan_from_disparity_batch")
 
     def points(self, D):
-        D = np.ascontiguousarray(D, np.float32)
+        D = _need(np.ascontiguousarray(D, np.float32), self.W * self.H, "disparity map")
         pts = np.zeros((self.W * self.H, 3), np.float64)
         n = C.c_int32(0)
         ranges = np.zeros(SCAN_BINS, np.float64)
@@ -469,9 +476,11 @@ class ObstacleScan:
     def pointcloud(self, D, image):
         """sensor_msgs/PointCloud payload (point_cloud.cpp:351-383): (xyz float32 n x 3, rgb float32 n,
         ranges, meta).  image: H x W x 3 BGR or H x W grayscale (the reference's Vec3b-on-gray quirk)."""
-        D = np.ascontiguousarray(D, np.float32)
+        D = _need(np.ascontiguousarray(D, np.float32), self.W * self.H, "disparity map")
         image = np.ascontiguousarray(image, np.uint8)
         channels = 3 if image.ndim == 3 else 1
+        if image.ndim not in (2, 3) or image.shape[0] < self.H or image.shape[1] < self.W or (image.ndim == 3 and image.shape[2] != 3):
+            raise ValueError("image must be H x W (grayscale) or H x W x 3 (BGR) with H >= %d, W >= %d" % (self.H, self.W))
         xyz = np.zeros((self.W * self.H, 3), np.float32)
         rgb = np.zeros(self.W * self.H, np.float32)
         n = C.c_int32(0)
@@ -494,7 +503,7 @@ class ObstacleScan:
 
 def scan_compact(ranges):
     """LaserScan.ranges as the reference publishes them (finite bins, k = 89..0)."""
-    ranges = np.ascontiguousarray(ranges, np.float64)
+    ranges = _need(np.ascontiguousarray(ranges, np.float64), SCAN_BINS, "ranges")
     out = np.zeros(SCAN_BINS, np.float32)
     n = lib().jn_scan_compact(_ptr(ranges), _ptr(out))
     return out[:n]

@@ -305,3 +305,27 @@ def test_documents_name_only_declared_entry_points():
         assert names, doc
         missing = sorted(n for n in names if n not in decl and not any(d.startswith(n) for d in decl))
         assert not missing, "%s mentions undeclared %s" % (doc, missing)
+
+
+def test_python_wrappers_reject_undersized_arrays_before_the_c_call(jn):
+    """The C side reads W*H elements through raw pointers: the Python mirror refuses arrays that are too small
+    (ValueError) instead of letting the library read past them.  No device needed: the check comes first, and a
+    right-sized call on a NULL handle comes back as the library's JN_ERR_ARG."""
+    class Fake:
+        W, H, _h = 64, 48, None
+    small = np.zeros((10, 10), np.float32)
+    full = np.zeros((48, 64), np.float32)
+    for call in (lambda: jn.ObstacleScan.from_disparity(Fake, small),
+                 lambda: jn.ObstacleScan.points(Fake, small),
+                 lambda: jn.ObstacleScan.pointcloud(Fake, small, np.zeros((48, 64), np.uint8)),
+                 lambda: jn.ObstacleScan.pointcloud(Fake, full, np.zeros((20, 64), np.uint8)),
+                 lambda: jn.ObstacleScan.pointcloud(Fake, full, np.zeros((48, 64, 4), np.uint8)),
+                 lambda: jn.scan_compact(np.zeros(10))):
+        with pytest.raises(ValueError):
+            call()
+    for call in (lambda: jn.ObstacleScan.from_disparity(Fake, full),
+                 lambda: jn.ObstacleScan.points(Fake, full),
+                 lambda: jn.ObstacleScan.pointcloud(Fake, full, np.zeros((48, 64, 3), np.uint8))):
+        with pytest.raises(jn.JnError):
+            call()
+    assert len(jn.scan_compact(np.full(90, 1e9))) == 0
