@@ -179,6 +179,12 @@ int jn_calib_stereo_rectify(jn_calib* c, int calib_w, int calib_h, int new_w, in
 int jn_calib_init_undistort_rectify_map(const double K[9], const double D[5], const double R[9],
                                         const double P[12], int w, int h, float* mapx, float* mapy);
 
+/* XR / XT from three Euler angles and a translation, as the node's -m mode composes them while the extrinsics are
+ * tuned (composeRotationCamToRobot / composeTranslationCamToRobot, point_cloud.cpp:76-102, 305-311): XR = Z * Y * X,
+ * the six values taken as float like the reference's signatures.  A jn_scan built afterwards uses them. */
+int jn_calib_compose_cam_to_robot(jn_calib* c, double phi_x, double phi_y, double phi_z, double trans_x,
+                                  double trans_y, double trans_z);
+
 #define JN_SCAN_BINS 90
 
 typedef struct jn_scan_meta {

@@ -337,6 +337,12 @@ class Calibration:
     def set_q(self, cx, cy, f, tx):
         lib().jn_calib_set_q(C.byref(self.c), cx, cy, f, tx)
 
+    def compose_cam_to_robot(self, phi_x, phi_y, phi_z, trans_x, trans_y, trans_z):
+        """XR, XT from Euler angles + translation as the node's -m mode does (point_cloud.cpp:76-102, 305-311)."""
+        f = lib().jn_calib_compose_cam_to_robot
+        f.argtypes = [C.POINTER(Calib)] + [C.c_double] * 6
+        _check(f(C.byref(self.c), phi_x, phi_y, phi_z, trans_x, trans_y, trans_z), "jn_calib_compose_cam_to_robot")
+
     def stereo_rectify(self, calib_w, calib_h, new_w=0, new_h=0, zero_disparity=True, alpha=0.0):
         """cv::stereoRectify as point_cloud.cpp:543-544 calls it, without OpenCV: sets Q, returns
         (R1, R2, P1, P2)."""

@@ -298,3 +298,27 @@ extern "C" int jn_calib_init_undistort_rectify_map(const double K[9], const doub
   }
   return JN_OK;
 }
+
+// composeRotationCamToRobot / composeTranslationCamToRobot (point_cloud.cpp:76-102), what the node's -m mode
+// builds XR and XT from when the extrinsics are tuned through dynamic_reconfigure (:305-311; defaults
+// cfg/CamToRobotCalibParams.cfg:8-13).  The reference takes the six values as `float` and calls cos / sin on
+// floats (the float overloads), stores the results in double matrices and multiplies Z * Y * X with OpenCV's
+// small-matrix product; restated in that order.  Checked bit for bit against the compiled node
+// (tests/test_reference_nodes_pin.py).
+extern "C" int jn_calib_compose_cam_to_robot(jn_calib* c, double phi_x, double phi_y, double phi_z, double trans_x,
+                                             double trans_y, double trans_z) {
+  if (!c) return JN_ERR_ARG;
+  const float x = (float)phi_x, y = (float)phi_y, z = (float)phi_z;
+  M3 X = {{1, 0, 0}, {0, (double)cosf(x), (double)(-sinf(x))}, {0, (double)sinf(x), (double)cosf(x)}};
+  M3 Y = {{(double)cosf(y), 0, (double)sinf(y)}, {0, 1, 0}, {(double)(-sinf(y)), 0, (double)cosf(y)}};
+  M3 Z = {{(double)cosf(z), (double)(-sinf(z)), 0}, {(double)sinf(z), (double)cosf(z), 0}, {0, 0, 1}};
+  M3 ZY, R;
+  matmul3(Z, Y, ZY);
+  matmul3(ZY, X, R);
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) c->XR[3 * i + j] = R[i][j];
+  c->XT[0] = (double)(float)trans_x;
+  c->XT[1] = (double)(float)trans_y;
+  c->XT[2] = (double)(float)trans_z;
+  return JN_OK;
+}

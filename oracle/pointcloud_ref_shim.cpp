@@ -76,6 +76,17 @@ void ref_pc_setup(const double* Q16, const double* XR9, const double* XT3, int W
   jn_standin::captured() = jn_standin::Captured();
 }
 
+/* composeRotationCamToRobot / composeTranslationCamToRobot (:76-102) as publishPointCloud calls them in -m mode
+ * (:305-311): from the dynamic_reconfigure values (doubles, converted to the functions' float parameters). */
+void ref_pc_compose(double phi_x, double phi_y, double phi_z, double tx, double ty, double tz, double* XR9, double* XT3) {
+  Mat r = composeRotationCamToRobot(phi_x, phi_y, phi_z);
+  Mat t = composeTranslationCamToRobot(tx, ty, tz);
+  for (int i = 0; i < 3; i++) {
+    for (int j = 0; j < 3; j++) XR9[3 * i + j] = r.at<double>(i, j);
+    XT3[i] = t.at<double>(i, 0);
+  }
+}
+
 /* cacheDisparityValues(); gate_out receives valid_disp (H x W x Vec2b). */
 void ref_pc_cache_gate(uint8_t* gate_out) {
   Quiet q;

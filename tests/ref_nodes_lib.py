@@ -34,6 +34,13 @@ class PointCloudNode:
         self.XT = np.ascontiguousarray(XT, np.float64)
         l.ref_pc_setup(_p(self.Q), _p(self.XR), _p(self.XT), W, H, ox, oy)
 
+    def compose(self, phi_x, phi_y, phi_z, tx, ty, tz):
+        """composeRotationCamToRobot / composeTranslationCamToRobot -> (XR 3x3, XT 3)."""
+        self.l.ref_pc_compose.argtypes = [C.c_double] * 6 + [P, P]
+        xr, xt = np.zeros(9, np.float64), np.zeros(3, np.float64)
+        self.l.ref_pc_compose(phi_x, phi_y, phi_z, tx, ty, tz, _p(xr), _p(xt))
+        return xr.reshape(3, 3), xt
+
     def cache_gate(self):
         """cacheDisparityValues() -> valid_disp as H x W x 2 bytes."""
         g = np.zeros((self.H, self.W, 2), np.uint8)

@@ -47,6 +47,7 @@ cases = [
     ("stereo_rectify(NULL)", lambda: l.jn_calib_stereo_rectify(N, 640, 360, 0, 0, 1, 0.0, N, N, N, N), ERR),
     ("stereo_rectify(0x0)", lambda: l.jn_calib_stereo_rectify(C.byref(cal), 0, 0, 0, 0, 1, 0.0, N, N, N, N), ERR),
     ("stereo_rectify(zeroed calibration)", lambda: l.jn_calib_stereo_rectify(C.byref(jn.Calib()), 640, 360, 0, 0, 1, 0.0, N, N, N, N), ERR),
+    ("compose_cam_to_robot(NULL)", lambda: l.jn_calib_compose_cam_to_robot(N, d(0), d(0), d(0), d(0), d(0), d(0)), ERR),
     ("undistort_map(NULL)", lambda: l.jn_calib_init_undistort_rectify_map(N, N, N, N, 4, 4, N, N), ERR),
     ("scan_compact(NULL)", lambda: l.jn_scan_compact(N, N), ERR),
     ("scan_create(NULL calib)", lambda: l.jn_scan_create(N, 64, 48, 0, 0, 0), lambda rc: not rc),

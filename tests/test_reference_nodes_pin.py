@@ -333,3 +333,20 @@ def test_python_navigate_mirror_against_the_compiled_node(jn, sp, synth):
     with pytest.raises(ValueError):
         a.set_scan_bins(np.zeros(10), jn.ScanMeta())
     a.close(); b.close()
+
+
+def test_extrinsics_from_euler_angles_equal_the_node(jn):
+    """-m mode: XR = Z * Y * X from float cos / sin, XT as floats (point_cloud.cpp:76-102, 305-311).  The
+    dynamic_reconfigure defaults (cfg/CamToRobotCalibParams.cfg:8-13) and 200 random settings, bit for bit."""
+    node = rn.PointCloudNode(np.eye(4), np.eye(3), np.zeros(3), 8, 8)
+    cal = jn.Calibration(scan_lib.CALIB_YML)
+    rng = np.random.default_rng(9)
+    cases = [(1.3, -3.14, 1.57, 0.0, 0.0, 0.28), (0, 0, 0, 0, 0, 0)]
+    cases += [tuple(rng.uniform(-6.28, 6.28, 3)) + tuple(rng.uniform(-100, 100, 3)) for _ in range(200)]
+    for c in cases:
+        xr, xt = node.compose(*c)
+        cal.compose_cam_to_robot(*c)
+        A = cal.arrays()
+        assert np.array_equal(np.asarray(A["XR"]).reshape(3, 3), xr), c
+        assert np.array_equal(np.asarray(A["XT"]).reshape(3), xt), c
+    assert abs(np.linalg.det(xr) - 1) < 1e-5                     # a rotation, to float precision
