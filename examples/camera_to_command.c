@@ -6,6 +6,7 @@
  *                      per frame: Elas::process + convertTo(CV_8U)       (:406-429)
  *                                 publishObstacleScan                    (:213-296)
  *   navigate node:     laserScanCallback, checkObstacle, chooseDirection (navigate.cpp:344-363, 101-197)
+ *                      safeNavigate in obstacle-avoid mode -> cmd_vel    (:302-342, 229-255)
  *
  *   cc -std=c99 -I include examples/camera_to_command.c -L jackal-navigation_b200 -ljn_elas \
  *      -Wl,-rpath,$PWD/jackal-navigation_b200 -lm -o camera_to_command
@@ -16,13 +17,16 @@
  * without the CUDA runtime links.  Exit code 3: no usable GPU (the library has no CPU path).
  *
  * Expected output with the shipped calibration: what the CPU checkers give for the same frames (tools/example_expected.py:
- * the compiled reference ELAS, the scan restatement, the same vote) -- the box is left of the centre and approaches:
- *   frame 0: 61 scan bins, closest 1.61 m, 0 points in the safe box -> free
- *   frame 1: 61 scan bins, closest 0.84 m, 19 points in the safe box -> obstacle, turn right
- *   frame 2: 61 scan bins, closest 0.56 m, 27 points in the safe box -> obstacle, turn right
- *   frame 3: 61 scan bins, closest 0.42 m, 25 points in the safe box -> obstacle, turn right
- *   frame 4: 61 scan bins, closest 0.34 m, 22 points in the safe box -> obstacle, turn right
- *   frame 5: 61 scan bins, closest 0.28 m, 20 points in the safe box -> obstacle, turn right
+ * the compiled reference ELAS, the scan restatement, the same host code for the command) -- a box left of the centre
+ * approaches, the robot accelerates, brakes, and turns away from it on the spot:
+ *   frame 0: 61 scan bins, nearest 1.61 m -> cmd_vel linear 0.025 m/s, angular +0.000 rad/s (driving)
+ *   frame 1: 61 scan bins, nearest 0.84 m -> cmd_vel linear 0.000 m/s, angular -0.050 rad/s (turning right)
+ *   frame 2: 61 scan bins, nearest 0.56 m -> cmd_vel linear 0.000 m/s, angular -0.100 rad/s (turning right)
+ *   frame 3: 61 scan bins, nearest 0.42 m -> cmd_vel linear 0.000 m/s, angular -0.150 rad/s (turning right)
+ *   frame 4: 61 scan bins, nearest 0.34 m -> cmd_vel linear 0.000 m/s, angular -0.200 rad/s (turning right)
+ *   frame 5: 61 scan bins, nearest 0.28 m -> cmd_vel linear 0.000 m/s, angular -0.250 rad/s (turning right)
+ *   frame 6: 61 scan bins, nearest 0.24 m -> cmd_vel linear 0.000 m/s, angular -0.300 rad/s (turning right)
+ *   frame 7: 61 scan bins, nearest 0.21 m -> cmd_vel linear 0.000 m/s, angular -0.350 rad/s (turning right)
  */
 #include <math.h>
 #include <stdio.h>
@@ -53,7 +57,7 @@ static void make_pair(uint8_t* L, uint8_t* R, int box_d, unsigned seed) {
 
 int main(int argc, char** argv) {
   const char* yml = argc > 1 ? argv[1] : "tests/golden/calib_c920.yml";
-  const int frames = argc > 2 ? atoi(argv[2]) : 6;
+  const int frames = argc > 2 ? atoi(argv[2]) : 8;
   jn_calib cal;
   jn_elas_params par;
   jn_elas* elas;
@@ -86,21 +90,20 @@ int main(int argc, char** argv) {
   D1 = (float*)malloc(sizeof(float) * W * H);
   dims[0] = W; dims[1] = H; dims[2] = W;
   for (f = 0; f < frames; f++) {
-    double ranges[JN_SCAN_BINS], report[4];
+    double ranges[JN_SCAN_BINS], vel[2];
     jn_scan_meta meta;
-    int rc, obstacle, dir;
+    int rc;
     make_pair(L, R, 30 + 25 * f, 1000u + (unsigned)f);             /* the box approaches */
     memset(D1, 0, sizeof(float) * W * H);                          /* the caller zeroes its maps, :413-414 */
     rc = jn_elas_process(elas, L, R, D1, NULL, dims);
     if (rc < 0) { fprintf(stderr, "Elas::process: %s\n", jn_last_error()); return 1; }
     if (jn_scan_from_disparity(scan, D1, ranges, &meta, NULL) != JN_OK) { fprintf(stderr, "%s\n", jn_last_error()); return 1; }
     jn_navigate_set_scan_bins(nav, ranges, &meta);
-    obstacle = jn_navigate_check_obstacle(nav, report);
-    dir = obstacle ? jn_navigate_choose_direction(nav) : 0;
-    jn_navigate_set_last_dir(nav, dir);                            /* obstacleAvoidMode, navigate.cpp:233-255 */
-    printf("frame %d: %d scan bins, closest %.2f m, %d points in the safe box -> %s%s\n", f, (int)meta.n_finite,
-           report[2], (int)report[0], obstacle ? "obstacle" : "free",
-           !obstacle ? "" : dir == 1 ? ", turn left" : dir == 2 ? ", turn right" : ", stop");
+    /* the X button of the joystick held, stick fully forward: obstacleAvoidMode (navigate.cpp:229-255) + the ramp */
+    jn_navigate_command(nav, JN_NAV_OBSTACLE_AVOID, 0.0, 1.0, vel);
+    printf("frame %d: %d scan bins, nearest %.2f m -> cmd_vel linear %.3f m/s, angular %+.3f rad/s (%s)\n", f,
+           (int)meta.n_finite, meta.range_min, vel[0], vel[1],
+           vel[1] > 0 ? "turning left" : vel[1] < 0 ? "turning right" : vel[0] > 0 ? "driving" : "stopped");
   }
   free(L); free(R); free(D1);
   jn_navigate_destroy(nav);

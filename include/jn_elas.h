@@ -325,7 +325,17 @@ int jn_jpeg_decode_gray_batch(jn_jpeg* j, int n, const uint8_t* const* data, con
  *                               vote; report[4] = {points in the safe box, laser points, closest, confidence}
  *   jn_navigate_choose_direction  0 keep / 1 left / 2 right, with the reference's hysteresis on last_dir
  *                               (the caller stores its choice with jn_navigate_set_last_dir, as
- *                               obstacleAvoidMode does) */
+ *                               obstacleAvoidMode does)
+ *   jn_navigate_command         the velocity command of safeNavigate (navigate.cpp:302-342) for one of its modes:
+ *                               runs the vote once, then the node's acceleration ramp on the velocities commanded
+ *                               last; vel = {linear.x, angular.z} of the geometry_msgs/Twist it publishes.
+ *                               side / front = the joystick axes (front only matters below 0.4 in
+ *                               JN_NAV_OBSTACLE_AVOID); the waypoint mode ("navigation doesn't work yet", :317) is not offered */
+enum {
+  JN_NAV_STOP_IN_FRONT_MANUAL = 0,   /* R1 + R2: stopInFrontMode(side, front), navigate.cpp:208-217 */
+  JN_NAV_OBSTACLE_AVOID       = 1,   /* X:       obstacleAvoidMode(front),      navigate.cpp:229-255 */
+  JN_NAV_STOP_IN_FRONT        = 2    /* O:       stopInFrontMode(),             navigate.cpp:219-227 */
+};
 typedef struct jn_navigate jn_navigate;
 jn_navigate* jn_navigate_create(void);
 void jn_navigate_destroy(jn_navigate* n);
@@ -337,6 +347,8 @@ int  jn_navigate_set_scan_bins(jn_navigate* n, const double ranges[JN_SCAN_BINS]
 int  jn_navigate_points(const jn_navigate* n, double* xy, int capacity);
 int  jn_navigate_check_obstacle(jn_navigate* n, double report[4]);
 int  jn_navigate_choose_direction(const jn_navigate* n);
+void jn_navigate_set_max_forward_vel(jn_navigate* n, float max_forward_vel);     /* -f, navigate.cpp:32 */
+int  jn_navigate_command(jn_navigate* n, int mode, double side, double front, double vel[2]);
 
 #ifdef __cplusplus
 }

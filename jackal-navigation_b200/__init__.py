@@ -515,6 +515,9 @@ def scan_compact(ranges):
     return out[:n]
 
 
+NAV_STOP_IN_FRONT_MANUAL, NAV_OBSTACLE_AVOID, NAV_STOP_IN_FRONT = 0, 1, 2
+
+
 class Navigate:
     """The scan's consumer without ROS: the `navigate` node's laserScanCallback / checkObstacle / chooseDirection
     (navigate.cpp:344-363, 101-153, 155-197).  Host code, no device needed."""
@@ -582,6 +585,20 @@ class Navigate:
     def choose_direction(self):
         """0 keep / 1 left / 2 right, with the reference's hysteresis on last_dir."""
         return lib().jn_navigate_choose_direction(self._h)
+
+    def command(self, mode, side=0.0, front=0.0):
+        """safeNavigate's velocity command for one mode (NAV_STOP_IN_FRONT_MANUAL / NAV_OBSTACLE_AVOID /
+        NAV_STOP_IN_FRONT): (linear.x, angular.z) of the Twist the node publishes (navigate.cpp:302-342)."""
+        f = lib().jn_navigate_command
+        f.argtypes = [_P, C.c_int, C.c_double, C.c_double, _P]
+        v = (C.c_double * 2)()
+        _check(f(self._h, int(mode), float(side), float(front), v), "jn_navigate_command")
+        return v[0], v[1]
+
+    def set_max_forward_vel(self, v):
+        f = lib().jn_navigate_set_max_forward_vel
+        f.argtypes = [_P, C.c_float]
+        f(self._h, float(v))
 
     @property
     def last_dir(self):

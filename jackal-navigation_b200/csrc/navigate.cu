@@ -18,6 +18,8 @@ struct jn_navigate {
   int last_dir;                   // navigate.cpp:46
   double clear_front, clear_side; // navigate.cpp:37-38
   int laser_pt_thresh;            // navigate.cpp:42
+  double forward_vel, rot_vel;    // navigate.cpp:28: the velocities last commanded
+  float max_forward_vel;          // navigate.cpp:32 (a float in the reference; -f)
 };
 
 extern "C" jn_navigate* jn_navigate_create(void) {
@@ -26,6 +28,9 @@ extern "C" jn_navigate* jn_navigate_create(void) {
   n->clear_front = 0.24 + 0.8;
   n->clear_side = 0.3;
   n->laser_pt_thresh = 8;
+  n->forward_vel = 0.;
+  n->rot_vel = 0.;
+  n->max_forward_vel = 0.6f;
   return n;
 }
 extern "C" void jn_navigate_destroy(jn_navigate* n) { delete n; }
@@ -129,4 +134,52 @@ extern "C" int jn_navigate_choose_direction(const jn_navigate* n) {
     else dir = 2;
   }
   return dir;
+}
+
+extern "C" void jn_navigate_set_max_forward_vel(jn_navigate* n, float v) { if (n) n->max_forward_vel = v; }
+
+// safeNavigate (navigate.cpp:302-342) without the joystick message: the mode the buttons select, the two stick
+// axes, and out comes the Twist the node publishes (vel[0] = linear.x, vel[1] = angular.z).
+//   JN_NAV_STOP_IN_FRONT_MANUAL  R1 + R2: stopInFrontMode(side, front)  (:208-217)  drive by stick, no forward motion
+//                                                                                   while there is an obstacle
+//   JN_NAV_OBSTACLE_AVOID        X:       obstacleAvoidMode(front)      (:229-255)  turn away on the spot, else forward
+//   JN_NAV_STOP_IN_FRONT         O:       stopInFrontMode()             (:219-227)  full speed ahead until an obstacle
+// Every mode runs checkObstacle once (the 20-frame vote advances), obstacleAvoidMode also stores the chosen
+// direction; the desired velocities then pass the node's acceleration ramp (:328-337: 0.025 up / 0.1 down per
+// call forward, 0.05 per call in rotation) on the velocities commanded last.
+extern "C" int jn_navigate_command(jn_navigate* n, int mode, double side, double front, double vel[2]) {
+  if (!n || !vel) return JN_ERR_ARG;
+  const double trans_accel = 0.025, trans_decel = 0.1, rot_accel = 0.05, max_rot_vel = 1.3;   // navigate.cpp:30-34
+  double desired_forward_vel, desired_rot_vel;
+  if (mode == JN_NAV_STOP_IN_FRONT_MANUAL) {
+    desired_forward_vel = n->max_forward_vel * front;
+    desired_rot_vel = max_rot_vel * side;
+    if (jn_navigate_check_obstacle(n, nullptr) == 1) desired_forward_vel = fmin(desired_forward_vel, 0.);
+  } else if (mode == JN_NAV_STOP_IN_FRONT) {
+    desired_forward_vel = n->max_forward_vel * 1.0;
+    desired_rot_vel = 0.0;
+    if (jn_navigate_check_obstacle(n, nullptr) == 1) desired_forward_vel = fmin(desired_forward_vel, 0.);
+  } else if (mode == JN_NAV_OBSTACLE_AVOID) {
+    if (jn_navigate_check_obstacle(n, nullptr)) {
+      const int dir = jn_navigate_choose_direction(n);
+      n->last_dir = dir;
+      if (dir == 1) desired_rot_vel = max_rot_vel * 0.4;                  // rotate left
+      else if (dir == 2) desired_rot_vel = max_rot_vel * 0.4 * (-1);      // rotate right
+      else desired_rot_vel = max_rot_vel * 0.0;                           // no good direction
+      desired_forward_vel = n->max_forward_vel * 0.0;                     // stop while rotating
+    } else {
+      desired_forward_vel = n->max_forward_vel * fmax(0.4, front);
+      desired_rot_vel = max_rot_vel * 0.0;
+      n->last_dir = 0;
+    }
+  } else {
+    return JN_ERR_ARG;
+  }
+  if (desired_forward_vel < n->forward_vel) n->forward_vel = fmax(desired_forward_vel, n->forward_vel - trans_decel);
+  else n->forward_vel = fmin(desired_forward_vel, n->forward_vel + trans_accel);
+  if (desired_rot_vel < n->rot_vel) n->rot_vel = fmax(desired_rot_vel, n->rot_vel - rot_accel);
+  else n->rot_vel = fmin(desired_rot_vel, n->rot_vel + rot_accel);
+  vel[0] = n->forward_vel;
+  vel[1] = n->rot_vel;
+  return JN_OK;
 }

@@ -28,6 +28,9 @@ void ref_nav_reset(void) {
   clear_front = 0.24 + 0.8;
   clear_side = 0.3;
   laser_pt_thresh = 8;
+  forward_vel = 0.;
+  rot_vel = 0.;
+  max_forward_vel = 0.6;
 }
 
 void ref_nav_set_clearance(double front, double side, int thresh) {
@@ -79,5 +82,27 @@ int ref_nav_obstacle_avoid_mode(double front, double vel[2]) {
   vel[1] = v.second;
   return last_dir;
 }
+
+/* safeNavigate (navigate.cpp:302-342) on a sensor_msgs/Joy with the given buttons pressed (R2 = 9, R1 = 11,
+ * triangle = 12, O = 13, X = 14) and stick axes; returns 1 and the published Twist's linear.x / angular.z, or 0 if
+ * the node published nothing (no mode button). */
+int ref_nav_safe_navigate(int r1, int r2, int x, int o, float side, float front, double vel[2]) {
+  std::shared_ptr<sensor_msgs::Joy> m(new sensor_msgs::Joy());
+  m->buttons.assign(17, 0);
+  m->axes.assign(4, 0.f);
+  m->buttons[9] = r2; m->buttons[11] = r1; m->buttons[14] = x; m->buttons[13] = o;
+  m->axes[0] = side; m->axes[1] = front;
+  jn_standin::captured().twists.clear();
+  std::ostringstream os;
+  std::streambuf* old = std::cout.rdbuf(os.rdbuf());
+  safeNavigate(m);
+  std::cout.rdbuf(old);
+  if (jn_standin::captured().twists.empty()) return 0;
+  vel[0] = jn_standin::captured().twists.back().linear.x;
+  vel[1] = jn_standin::captured().twists.back().angular.z;
+  return 1;
+}
+
+void ref_nav_set_max_forward_vel(float v) { max_forward_vel = v; }
 
 }  // extern "C"

@@ -122,6 +122,16 @@ class NavigateNode:
     def last_dir(self):
         return self.l.ref_nav_last_dir()
 
+    def safe_navigate(self, r1=0, r2=0, x=0, o=0, side=0.0, front=0.0):
+        """safeNavigate on a Joy message -> (linear.x, angular.z) of the published Twist, or None."""
+        self.l.ref_nav_safe_navigate.argtypes = [C.c_int] * 4 + [C.c_float, C.c_float, P]
+        v = np.zeros(2, np.float64)
+        return tuple(v) if self.l.ref_nav_safe_navigate(r1, r2, x, o, side, front, _p(v)) else None
+
+    def set_max_forward_vel(self, v):
+        self.l.ref_nav_set_max_forward_vel.argtypes = [C.c_float]
+        self.l.ref_nav_set_max_forward_vel(v)
+
     def obstacle_avoid_mode(self, front):
         v = np.zeros(2, np.float64)
         d = self.l.ref_nav_obstacle_avoid_mode(float(front), _p(v))

@@ -69,6 +69,7 @@ cases = [
     ("navigate_set_scan(NULL)", lambda: l.jn_navigate_set_scan(N, N, 0, 0.0, 0.0), ERR),
     ("navigate_set_scan_bins(NULL)", lambda: l.jn_navigate_set_scan_bins(N, N, N), ERR),
     ("navigate_check_obstacle(NULL)", lambda: l.jn_navigate_check_obstacle(N, N), ERR),
+    ("navigate_command(NULL)", lambda: l.jn_navigate_command(N, 1, d(0), d(0), N), ERR),
     ("navigate_points(NULL)", lambda: l.jn_navigate_points(N, N, 0), ERR),
     ("navigate_choose_direction(NULL)", lambda: l.jn_navigate_choose_direction(N), ERR),
     ("host_free(NULL)", lambda: l.jn_host_free(N), ANY),

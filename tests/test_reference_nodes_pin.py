@@ -350,3 +350,45 @@ def test_extrinsics_from_euler_angles_equal_the_node(jn):
         assert np.array_equal(np.asarray(A["XR"]).reshape(3, 3), xr), c
         assert np.array_equal(np.asarray(A["XT"]).reshape(3), xt), c
     assert abs(np.linalg.det(xr) - 1) < 1e-5                     # a rotation, to float precision
+
+
+def test_velocity_command_equals_the_twist_the_node_publishes(jn):
+    """safeNavigate (navigate.cpp:302-342) for its three working modes over 1 200 scans with changing obstacles,
+    stick positions and mode switches: jn_navigate_command returns the linear.x / angular.z of the Twist the
+    compiled node publishes, bit for bit (the vote, the stored direction and the acceleration ramp all carry state
+    from call to call), and no button means no message."""
+    rng = np.random.default_rng(12)
+    node = rn.NavigateNode()
+    nav = jn.Navigate()
+    assert node.safe_navigate() is None                                  # no mode button: nothing published
+    buttons = {jn.NAV_STOP_IN_FRONT_MANUAL: dict(r1=1, r2=1), jn.NAV_OBSTACLE_AVOID: dict(x=1),
+               jn.NAV_STOP_IN_FRONT: dict(o=1)}
+    seen = set()
+    mode = jn.NAV_OBSTACLE_AVOID
+    for frame in range(1200):
+        if frame % 60 == 0:
+            mode = int(rng.integers(0, 3))
+        if frame == 600:
+            node.set_max_forward_vel(0.9); nav.set_max_forward_vel(0.9)   # -f
+        n = int(rng.integers(10, 91))
+        base = np.full(n, 5.0)
+        phase = frame // 45 % 4
+        if phase == 1:
+            base[: n // 2] = 0.8
+        elif phase == 2:
+            base[n // 2:] = 0.8
+        elif phase == 3:
+            base[:] = 0.7
+        ranges = (base * rng.uniform(0.9, 1.1, n)).astype(np.float32)
+        node.laser_scan(ranges, np.float32(-0.5), np.float32(0.5))
+        nav.set_scan(ranges, float(np.float32(-0.5)), float(np.float32(0.5)))
+        side, front = np.float32(rng.uniform(-1, 1)), np.float32(rng.uniform(-1, 1))      # Joy axes are float32
+        exp = node.safe_navigate(side=side, front=front, **buttons[mode])
+        got = nav.command(mode, float(side), float(front))
+        assert exp is not None and got == exp, (frame, mode, got, exp)
+        assert nav.last_dir == node.last_dir()
+        seen.add((mode, got[0] > 0, got[1] > 0, got[1] < 0))
+    assert len(seen) >= 8                                                # forward, stopped, turning either way
+    with pytest.raises(jn.JnError):
+        nav.command(7)
+    nav.close()

@@ -51,9 +51,7 @@ if __name__ == "__main__":
         D1, _ = o.process(ol.robotics(255, postprocess_only_left=1), L, R)
         r, m = sp.scan(A["Q"], A["XR"], A["XT"], gate, sp.convert_u8(D1))
         nav.set_scan_bins(r, jn.ScanMeta(m.angle_min, m.angle_max, m.range_min, m.range_max, m.n_finite, m.n_points))
-        ob, rep = nav.check_obstacle()
-        d = nav.choose_direction() if ob else 0
-        nav.last_dir = d
-        print("frame %d: %d scan bins, closest %.2f m, %d points in the safe box -> %s%s" % (
-            f, m.n_finite, rep[2], rep[0], "obstacle" if ob else "free",
-            "" if not ob else ", turn left" if d == 1 else ", turn right" if d == 2 else ", stop"))
+        v = nav.command(jn.NAV_OBSTACLE_AVOID, 0.0, 1.0)
+        print("frame %d: %d scan bins, nearest %.2f m -> cmd_vel linear %.3f m/s, angular %+.3f rad/s (%s)" % (
+            f, m.n_finite, m.range_min, v[0], v[1],
+            "turning left" if v[1] > 0 else "turning right" if v[1] < 0 else "driving" if v[0] > 0 else "stopped"))
