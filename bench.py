@@ -19,7 +19,7 @@ Prints ONE JSON line (rank 0):
                    H2D and D2H inside the timed region
   roofline         dense-matching kernel: algorithmic bytes (72*W*H per frame) / its event time
   parity           frames of the timed batch re-computed by the CPU checker: maps and scans equal
-  scenes, c5       the same measurement on the second scene family / BASELINE config C5 (short runs)
+  scenes, c5       the same measurement on the second scene family / BASELINE config C5 (short runs; N = 1 only)
   cpu_baseline     the reference's own ELAS (oracle/_ref, built from /root/reference) on the
                    host cores, one frame per core in separate processes
 --impl reference times that CPU arm alone, same metric / config.
@@ -569,7 +569,9 @@ def run_ours(a):
     t_gen = time.perf_counter()
     L, R = make_frames(a.scene, W, H, dm, seeds, procs)
     t_gen = time.perf_counter() - t_gen
-    extras_on = not a.no_extras and not a.total_frames
+    # second scene / C5 / single-frame latency: sections of the single-GPU line only (the scaling runs measure the
+    # headline workload and nothing else, exactly the code path of the N > 1 records under profiles/)
+    extras_on = not a.no_extras and not a.total_frames and world == 1
     other_scene = "textured" if a.scene == "random_dot" else "random_dot"
     nd2 = min(16, B)
     if extras_on:
