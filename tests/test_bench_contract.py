@@ -55,6 +55,23 @@ def test_gpu_arm_strong_scaling_flow():
     assert abs(d["value"] - 12 / (15.0 / 1000.0)) < 1e-6    # the stand-in events report 15 ms
 
 
+def test_gpu_arm_multi_rank_flow():
+    """One process as rank 0 and as rank 1 of a two-rank launch (collectives replaced by no-ops): rank 0 prints the
+    line with the whole-job value and without the single-GPU sections, rank 1 prints nothing."""
+    env = {"WORLD_SIZE": "2", "LOCAL_RANK": "0", "RANK": "0"}
+    d = _json_line(["tools/bench_dryrun.py"] + SMALL + ["--gpus", "2"], env)
+    assert d["n_gpus"] == 2 and d["scaling"] == "weak"
+    assert abs(d["value"] - 2 * 4 * 2 / (15.0 / 1000.0)) < 1e-6          # 2 ranks x 4 frames x 2 steps in 15 ms
+    assert abs(d["e2e"]["value"] - d["value"]) < 1e-6
+    for k in ("scenes", "c5", "single_frame", "cpu_baseline", "parity"):
+        assert k not in d, k                                             # sections of the single-GPU line only
+    assert "2 GPU(s)" in d["config"]["parallelism"] and d["e2e"]["rank_pinning"] is not None
+    r = subprocess.run([sys.executable, "tools/bench_dryrun.py"] + SMALL + ["--gpus", "2"], cwd=ROOT,
+                       capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, WORLD_SIZE="2", LOCAL_RANK="1", RANK="1"))
+    assert r.returncode == 0 and not [ln for ln in r.stdout.splitlines() if ln.startswith("{")], r.stderr[-1500:]
+
+
 def test_reference_arm_prints_the_same_config_and_the_reference_keys():
     ours = _json_line(["tools/bench_dryrun.py"] + SMALL + ["--no-cpu-baseline", "--no-extras"])
     ref = _json_line(["bench.py", "--impl", "reference"] + SMALL)

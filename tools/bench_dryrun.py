@@ -93,6 +93,13 @@ def install_mocks():
     torch.Tensor.pin_memory = lambda self, *a, **k: self
     torch.Tensor.cuda = lambda self, *a, **k: self
     torch.device = lambda *a, **k: cpu
+    # one process stands in for a rank of an N > 1 launch (RANK / WORLD_SIZE / LOCAL_RANK in the environment):
+    # the collectives become no-ops, so the max over ranks is this rank's own time
+    import torch.distributed as dist
+    dist.init_process_group = lambda *a, **k: None
+    dist.barrier = lambda *a, **k: None
+    dist.all_reduce = lambda *a, **k: None
+    dist.destroy_process_group = lambda *a, **k: None
     synth = importlib.import_module(PKG + ".synth")
     sharding = importlib.import_module(PKG + ".sharding")
     fake = types.ModuleType(PKG)
@@ -135,6 +142,9 @@ def dry_run(argv):
     finally:
         sys.argv = old
     lines = [ln for ln in buf.getvalue().splitlines() if ln.startswith("{")]
+    if int(os.environ.get("RANK", "0")) != 0:
+        assert not lines, "only rank 0 prints"
+        return None
     assert len(lines) == 1, "bench.py must print exactly one JSON line, got %d" % len(lines)
     line = json.loads(lines[0])
     line["data"] = "DRY RUN"
@@ -142,5 +152,7 @@ def dry_run(argv):
 
 
 if __name__ == "__main__":
-    print(json.dumps(dry_run(sys.argv[1:] or ["--width", "320", "--height", "240", "--disp-max", "64", "--batch", "4",
-                                              "--steps", "2", "--warmup", "1"])))
+    _line = dry_run(sys.argv[1:] or ["--width", "320", "--height", "240", "--disp-max", "64", "--batch", "4",
+                                              "--steps", "2", "--warmup", "1"])
+    if _line is not None:
+        print(json.dumps(_line))
