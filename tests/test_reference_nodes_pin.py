@@ -392,3 +392,32 @@ def test_velocity_command_equals_the_twist_the_node_publishes(jn):
     with pytest.raises(jn.JnError):
         nav.command(7)
     nav.close()
+
+
+@pytest.mark.parametrize("qname,W,H,dm,seed,rows", [("640x480", 640, 480, 64, 1, 480), ("1920x1200_Kx3", 1920, 1200, 255, 1000, 320)])
+def test_inputs_of_the_gpu_scan_test_through_the_compiled_node(sp, synth, ref, qname, W, H, dm, seed, rows):
+    """The maps tests/test_gpu_parity.py::test_obstacle_scan_matches_port hands the CUDA path (same scene, seed,
+    parameters and calibration), handed to the compiled node instead: the restatement that test compares against equals
+    the node on them, default path and -g path.  At 1920x1200 the stock node cannot take the whole map (the gate of the
+    rows below ~775 wraps to 0 and an invalid pixel there is H8's NaN angle, asserted here); it gets the rows above."""
+    Q = np.array(FX["Q"][qname], np.float64)
+    I1, I2, _ = synth.synth_pair(W, H, dm, seed)
+    D1, _ = ref.process(ol.robotics(dm), I1, I2)
+    u8_full = sp.convert_u8(D1)
+    if rows < H:
+        g_full = sp.gate(Q, XR, XT, W, H)
+        assert not rn.safe_for_reference(Q, XR, XT, u8_full, gate=g_full)
+        assert rn.bin_index_range(Q, XR, XT, u8_full, gate=g_full)[3] > 0          # NaN angles: the reason
+    u8 = np.ascontiguousarray(u8_full[:rows])
+    node = rn.PointCloudNode(Q, XR, XT, W, rows)
+    gate = node.cache_gate()
+    assert np.array_equal(gate, sp.gate(Q, XR, XT, W, rows))
+    assert rn.safe_for_reference(Q, XR, XT, u8, gate=gate) and rn.safe_for_reference(Q, XR, XT, u8, min_d=2)
+    ranges, meta = node.scan(u8)
+    pr, pm = sp.scan(Q, XR, XT, gate, u8)
+    assert np.array_equal(ranges, sp.compact(pr)) and np.array_equal(meta, meta_f32(pm)) and len(ranges) > 20
+    xyz, rgb, ranges2, meta2 = node.pointcloud(u8, np.ascontiguousarray(I1[:rows]))
+    pxyz, prgb = sp.pointcloud(Q, XR, XT, u8, np.ascontiguousarray(I1[:rows]))
+    assert np.array_equal(xyz, pxyz) and np.array_equal(rgb.view(np.int32), prgb.view(np.int32))
+    pr2, pm2 = sp.scan_points(sp.points(Q, XR, XT, u8))
+    assert np.array_equal(ranges2, sp.compact(pr2)) and np.array_equal(meta2, meta_f32(pm2))
